@@ -1,0 +1,354 @@
+// arith.cuh -- modular-arithmetic policies for the sm_100a NTT kernels.
+//
+// One policy per "bit class" of the reference's dispatch (prime32.rs:713-754, prime64.rs:812-864).
+// Only the *final canonical values* are observable (every reference path returns residues in
+// [0,p)), so each policy is free to pick its own lazy ranges; they are documented per policy.
+//
+// A policy provides
+//   W            word type (uint32_t / uint64_t)
+//   Tw           twiddle record as stored in the device heap table
+//   Mod          per-plan constants passed by value in kernel params
+//   fwd_bf       Cooley-Tukey butterfly  (z0,z1) -> (z0 + w z1, z0 - w z1)   [lazy]
+//   inv_bf       Gentleman-Sande butterfly (z0,z1) -> (z0 + z1, (z0 - z1) w) [lazy]
+//   canon_fwd / canon_inv   map the lazy range after the last fwd / inv stage to [0,p)
+//   mul_norm     lhs*rhs*n^-1, norm: v*n^-1, mul_acc: acc+lhs*rhs   -- the reference's own
+//                scalar formulas (prime32.rs:383-408,477-486,575-598; prime64.rs:534-584,690-699)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace cntt {
+
+typedef unsigned __int128 u128_t;
+
+__device__ __forceinline__ uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+__device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+
+// ------------------------------------------------------------------------------------------
+// 32-bit constants shared by all u32 policies
+// ------------------------------------------------------------------------------------------
+struct Mod32 {
+    uint32_t p, two_p, neg_p;
+    uint32_t n_inv, n_inv_shoup;  // N^-1 mod p and floor(N^-1 * 2^32 / p)
+    uint32_t p_barrett, big_q_m1; // prime32.rs:667-671
+};
+
+// Shoup multiply: a * w mod p in [0, 2p) for any 32-bit a (p < 2^31).
+__device__ __forceinline__ uint32_t shoup32(uint32_t a, uint2 t, const Mod32& m)
+{
+    uint32_t q = __umulhi(a, t.y);
+    return a * t.x + q * m.neg_p;
+}
+
+// ---- p < 2^30 : Harvey lazy butterflies, values in [0, 4p) between forward stages and
+//      [0, 2p) between inverse stages (same ranges as prime32/less_than_30bit.rs:115-129,265-282)
+struct A32L4 {
+    typedef uint32_t W;
+    typedef uint2 Tw;
+    typedef Mod32 Mod;
+    static constexpr bool kShoupTable = true;
+
+    static __device__ __forceinline__ void fwd_bf(W& z0, W& z1, Tw t, const Mod& m)
+    {
+        W c = umin32(z0, z0 - m.two_p);
+        W x = shoup32(z1, t, m);
+        z0 = c + x;
+        z1 = c - x + m.two_p;
+    }
+    static __device__ __forceinline__ void inv_bf(W& z0, W& z1, Tw t, const Mod& m)
+    {
+        W s = z0 + z1;
+        W d = z0 - z1 + m.two_p;
+        z0 = umin32(s, s - m.two_p);
+        z1 = shoup32(d, t, m);
+    }
+    static __device__ __forceinline__ W canon_fwd(W x, const Mod& m)
+    {
+        x = umin32(x, x - m.two_p);
+        return umin32(x, x - m.p);
+    }
+    static __device__ __forceinline__ W canon_inv(W x, const Mod& m) { return umin32(x, x - m.p); }
+    // any 32-bit value is a legal forward input for the z1 role; the z0 role needs [0,4p)
+    static __device__ __forceinline__ W mul_norm(W a, W b, const Mod& m)
+    {
+        uint64_t d = (uint64_t)a * b;
+        uint32_t c1 = (uint32_t)(d >> m.big_q_m1);
+        uint32_t c3 = __umulhi(c1, m.p_barrett);
+        uint32_t prod = (uint32_t)d - m.p * c3;
+        uint32_t q = __umulhi(prod, m.n_inv_shoup);
+        uint32_t t = prod * m.n_inv - q * m.p;
+        return umin32(t, t - m.p);
+    }
+    static __device__ __forceinline__ W norm(W v, const Mod& m)
+    {
+        uint32_t q = __umulhi(v, m.n_inv_shoup);
+        uint32_t t = v * m.n_inv - q * m.p;
+        return umin32(t, t - m.p);
+    }
+    static __device__ __forceinline__ W mul_acc(W acc, W a, W b, const Mod& m)
+    {
+        uint64_t d = (uint64_t)a * b;
+        uint32_t c1 = (uint32_t)(d >> m.big_q_m1);
+        uint32_t c3 = __umulhi(c1, m.p_barrett);
+        uint32_t prod = (uint32_t)d - m.p * c3;
+        prod = umin32(prod, prod - m.p);
+        uint32_t s = prod + acc;
+        return umin32(s, s - m.p);
+    }
+};
+
+// ---- 2^30 <= p < 2^31 : values in [0, 2p) between forward stages, [0, p) between inverse stages
+//      (prime32/less_than_31bit.rs:117-133, 214-234)
+struct A32L2 : A32L4 {
+    static __device__ __forceinline__ void fwd_bf(W& z0, W& z1, Tw t, const Mod& m)
+    {
+        W c = umin32(z0, z0 - m.p);
+        W x = shoup32(z1, t, m);
+        x = umin32(x, x - m.p);
+        z0 = c + x;
+        z1 = c - x + m.p;
+    }
+    static __device__ __forceinline__ void inv_bf(W& z0, W& z1, Tw t, const Mod& m)
+    {
+        W s = z0 + z1;
+        W d = z0 - z1 + m.p;
+        z0 = umin32(s, s - m.p);
+        W y = shoup32(d, t, m);
+        z1 = umin32(y, y - m.p);
+    }
+    static __device__ __forceinline__ W canon_fwd(W x, const Mod& m) { return umin32(x, x - m.p); }
+    static __device__ __forceinline__ W canon_inv(W x, const Mod&) { return x; }
+};
+
+// ---- p >= 2^31 : fully reduced values.  The reference has no Shoup table for this class
+//      (prime32.rs:645-652) and divides with Div32; here the device table still carries
+//      floor(w 2^32 / p) and the product is finished in 64 bits (internal choice, same results).
+struct A32G {
+    typedef uint32_t W;
+    typedef uint2 Tw;
+    typedef Mod32 Mod;
+    static constexpr bool kShoupTable = true;
+
+    static __device__ __forceinline__ W mulw(W a, Tw t, const Mod& m) // a < p  ->  a*w mod p
+    {
+        uint32_t q = __umulhi(a, t.y);
+        uint64_t r = (uint64_t)a * t.x - (uint64_t)q * m.p; // in [0, 2p)
+        if (r >= m.p) r -= m.p;
+        return (W)r;
+    }
+    static __device__ __forceinline__ W add(W a, W b, const Mod& m)
+    {
+        W nb = m.p - b;
+        return a >= nb ? a - nb : a + b;
+    }
+    static __device__ __forceinline__ W sub(W a, W b, const Mod& m) { return a >= b ? a - b : a + (m.p - b); }
+    static __device__ __forceinline__ void fwd_bf(W& z0, W& z1, Tw t, const Mod& m)
+    {
+        W x = mulw(z1, t, m);
+        W a = add(z0, x, m), b = sub(z0, x, m);
+        z0 = a; z1 = b;
+    }
+    static __device__ __forceinline__ void inv_bf(W& z0, W& z1, Tw t, const Mod& m)
+    {
+        W a = add(z0, z1, m), b = mulw(sub(z0, z1, m), t, m);
+        z0 = a; z1 = b;
+    }
+    static __device__ __forceinline__ W canon_fwd(W x, const Mod&) { return x; }
+    static __device__ __forceinline__ W canon_inv(W x, const Mod&) { return x; }
+    static __device__ __forceinline__ W mulmod(W a, W b, const Mod& m) { return (W)(((uint64_t)a * b) % m.p); }
+    // prime32.rs:853-863, 893-901, 919-926
+    static __device__ __forceinline__ W mul_norm(W a, W b, const Mod& m) { return mulmod(mulmod(a, b, m), m.n_inv, m); }
+    static __device__ __forceinline__ W norm(W v, const Mod& m) { return mulmod(v, m.n_inv, m); }
+    static __device__ __forceinline__ W mul_acc(W acc, W a, W b, const Mod& m) { return add(acc, mulmod(a, b, m), m); }
+};
+
+// ------------------------------------------------------------------------------------------
+// 64-bit
+// ------------------------------------------------------------------------------------------
+struct Mod64 {
+    uint64_t p, two_p, neg_p;
+    uint64_t n_inv, n_inv_shoup;
+    uint64_t p_barrett;
+    uint32_t big_q_m1;
+};
+
+__device__ __forceinline__ uint64_t shoup64(uint64_t a, ulonglong2 t, const Mod64& m)
+{
+    uint64_t q = __umul64hi(a, t.y);
+    return a * t.x + q * m.neg_p;
+}
+
+// ---- p < 2^62 (prime64/less_than_62bit.rs:117-131, 271-288)
+struct A64L4 {
+    typedef uint64_t W;
+    typedef ulonglong2 Tw;
+    typedef Mod64 Mod;
+    static constexpr bool kShoupTable = true;
+
+    static __device__ __forceinline__ void fwd_bf(W& z0, W& z1, Tw t, const Mod& m)
+    {
+        W c = umin64(z0, z0 - m.two_p);
+        W x = shoup64(z1, t, m);
+        z0 = c + x;
+        z1 = c - x + m.two_p;
+    }
+    static __device__ __forceinline__ void inv_bf(W& z0, W& z1, Tw t, const Mod& m)
+    {
+        W s = z0 + z1;
+        W d = z0 - z1 + m.two_p;
+        z0 = umin64(s, s - m.two_p);
+        z1 = shoup64(d, t, m);
+    }
+    static __device__ __forceinline__ W canon_fwd(W x, const Mod& m)
+    {
+        x = umin64(x, x - m.two_p);
+        return umin64(x, x - m.p);
+    }
+    static __device__ __forceinline__ W canon_inv(W x, const Mod& m) { return umin64(x, x - m.p); }
+    // prime64.rs:534-559
+    static __device__ __forceinline__ W barrett(W a, W b, const Mod& m)
+    {
+        uint64_t lo = a * b, hi = __umul64hi(a, b);
+        uint64_t c1 = m.big_q_m1 == 0 ? lo : (m.big_q_m1 >= 64 ? hi >> (m.big_q_m1 - 64) : (lo >> m.big_q_m1) | (hi << (64 - m.big_q_m1)));
+        uint64_t c3 = __umul64hi(c1, m.p_barrett);
+        return lo - m.p * c3;
+    }
+    static __device__ __forceinline__ W mul_norm(W a, W b, const Mod& m)
+    {
+        uint64_t prod = barrett(a, b, m);
+        uint64_t q = __umul64hi(prod, m.n_inv_shoup);
+        uint64_t t = prod * m.n_inv - q * m.p;
+        return umin64(t, t - m.p);
+    }
+    static __device__ __forceinline__ W norm(W v, const Mod& m)
+    {
+        uint64_t q = __umul64hi(v, m.n_inv_shoup);
+        uint64_t t = v * m.n_inv - q * m.p;
+        return umin64(t, t - m.p);
+    }
+    static __device__ __forceinline__ W mul_acc(W acc, W a, W b, const Mod& m)
+    {
+        uint64_t prod = barrett(a, b, m);
+        prod = umin64(prod, prod - m.p);
+        uint64_t s = prod + acc;
+        return umin64(s, s - m.p);
+    }
+};
+
+// ---- 2^62 <= p < 2^63 (prime64/less_than_63bit.rs:117-133, 214-234)
+struct A64L2 : A64L4 {
+    static __device__ __forceinline__ void fwd_bf(W& z0, W& z1, Tw t, const Mod& m)
+    {
+        W c = umin64(z0, z0 - m.p);
+        W x = shoup64(z1, t, m);
+        x = umin64(x, x - m.p);
+        z0 = c + x;
+        z1 = c - x + m.p;
+    }
+    static __device__ __forceinline__ void inv_bf(W& z0, W& z1, Tw t, const Mod& m)
+    {
+        W s = z0 + z1;
+        W d = z0 - z1 + m.p;
+        z0 = umin64(s, s - m.p);
+        W y = shoup64(d, t, m);
+        z1 = umin64(y, y - m.p);
+    }
+    static __device__ __forceinline__ W canon_fwd(W x, const Mod& m) { return umin64(x, x - m.p); }
+    static __device__ __forceinline__ W canon_inv(W x, const Mod&) { return x; }
+};
+
+// ---- p = 2^64 - 2^32 + 1 (Solinas / Goldilocks), prime64/generic_solinas.rs:77-129.
+//      Values are kept canonical; the multiply uses 2^64 = 2^32 - 1, 2^96 = -1 (mod p).
+struct A64S {
+    typedef uint64_t W;
+    typedef uint64_t Tw; // no Shoup companion
+    typedef Mod64 Mod;
+    static constexpr bool kShoupTable = false;
+    static constexpr uint64_t P = 0xFFFFFFFF00000001ull;
+    static constexpr uint64_t EPS = 0x00000000FFFFFFFFull; // 2^64 - P
+
+    // (hi:lo) mod P, canonical
+    static __device__ __forceinline__ W reduce128(uint64_t lo, uint64_t hi)
+    {
+        uint64_t hh = hi >> 32, hl = hi & EPS;
+        uint64_t t0 = lo - hh;
+        if (lo < hh) t0 -= EPS;            // borrow: +2^64 = +EPS too much
+        uint64_t t1 = (hl << 32) - hl;     // hl * (2^32 - 1)
+        uint64_t t2 = t0 + t1;
+        if (t2 < t1) t2 += EPS;            // carry: 2^64 = EPS
+        if (t2 >= P) t2 -= P;
+        return t2;
+    }
+    static __device__ __forceinline__ W mul(W a, W b) { return reduce128(a * b, __umul64hi(a, b)); }
+    static __device__ __forceinline__ W add(W a, W b) // canonical in, canonical out
+    {
+        uint64_t s = a + b;
+        if (s < a || s >= P) s -= P;
+        return s;
+    }
+    static __device__ __forceinline__ W sub(W a, W b)
+    {
+        uint64_t d = a - b;
+        if (a < b) d += P;
+        return d;
+    }
+    static __device__ __forceinline__ void fwd_bf(W& z0, W& z1, Tw t, const Mod&)
+    {
+        W x = mul(z1, t);
+        W a = add(z0, x), b = sub(z0, x);
+        z0 = a; z1 = b;
+    }
+    static __device__ __forceinline__ void inv_bf(W& z0, W& z1, Tw t, const Mod&)
+    {
+        W a = add(z0, z1), b = mul(sub(z0, z1), t);
+        z0 = a; z1 = b;
+    }
+    static __device__ __forceinline__ W canon_fwd(W x, const Mod&) { return x; }
+    static __device__ __forceinline__ W canon_inv(W x, const Mod&) { return x; }
+    // prime64.rs:1013-1021, 1068-1073, 1116-1120
+    static __device__ __forceinline__ W mul_norm(W a, W b, const Mod& m) { return mul(mul(a, b), m.n_inv); }
+    static __device__ __forceinline__ W norm(W v, const Mod& m) { return mul(v, m.n_inv); }
+    static __device__ __forceinline__ W mul_acc(W acc, W a, W b, const Mod&) { return add(acc, mul(a, b)); }
+};
+
+// ---- any other p >= 2^63 (prime64/generic_solinas.rs:42-75, Div64 remainder).  Device table
+//      carries floor(w 2^64 / p); the product is finished in 128 bits.
+struct A64G {
+    typedef uint64_t W;
+    typedef ulonglong2 Tw;
+    typedef Mod64 Mod;
+    static constexpr bool kShoupTable = true;
+
+    static __device__ __forceinline__ W mulw(W a, Tw t, const Mod& m)
+    {
+        uint64_t q = __umul64hi(a, t.y);
+        u128_t r = (u128_t)a * t.x - (u128_t)q * m.p; // in [0, 2p)
+        if (r >= m.p) r -= m.p;
+        return (W)r;
+    }
+    static __device__ __forceinline__ W add(W a, W b, const Mod& m)
+    {
+        W nb = m.p - b;
+        return a >= nb ? a - nb : a + b;
+    }
+    static __device__ __forceinline__ W sub(W a, W b, const Mod& m) { return a >= b ? a - b : a + (m.p - b); }
+    static __device__ __forceinline__ void fwd_bf(W& z0, W& z1, Tw t, const Mod& m)
+    {
+        W x = mulw(z1, t, m);
+        W a = add(z0, x, m), b = sub(z0, x, m);
+        z0 = a; z1 = b;
+    }
+    static __device__ __forceinline__ void inv_bf(W& z0, W& z1, Tw t, const Mod& m)
+    {
+        W a = add(z0, z1, m), b = mulw(sub(z0, z1, m), t, m);
+        z0 = a; z1 = b;
+    }
+    static __device__ __forceinline__ W canon_fwd(W x, const Mod&) { return x; }
+    static __device__ __forceinline__ W canon_inv(W x, const Mod&) { return x; }
+    static __device__ __forceinline__ W mulmod(W a, W b, const Mod& m) { return (W)(((u128_t)a * b) % m.p); }
+    static __device__ __forceinline__ W mul_norm(W a, W b, const Mod& m) { return mulmod(mulmod(a, b, m), m.n_inv, m); }
+    static __device__ __forceinline__ W norm(W v, const Mod& m) { return mulmod(v, m.n_inv, m); }
+    static __device__ __forceinline__ W mul_acc(W acc, W a, W b, const Mod& m) { return add(acc, mulmod(a, b, m), m); }
+};
+
+} // namespace cntt

@@ -1,0 +1,717 @@
+// capi.cu -- the C ABI (include/cntt_b200.h): plan construction, argument checking, launches and the
+// host-slice staging paths.  No arithmetic happens on the CPU here except plan-time table building.
+#include "../../include/cntt_b200.h"
+#include "dispatch.hpp"
+#include "host_math.hpp"
+#include "native.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace cntt;
+
+#define CNTT_API extern "C" __attribute__((visibility("default")))
+
+// ---- errors ----------------------------------------------------------------------------------------
+static thread_local std::string t_cuda_err;
+
+static int cuda_fail(cudaError_t e, const char* where)
+{
+    t_cuda_err = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    (void)cudaGetLastError(); // clear the sticky-less error state
+    return CNTT_CUDA_ERROR;
+}
+#define CU(expr)                                                  \
+    do {                                                          \
+        cudaError_t _e = (expr);                                  \
+        if (_e != cudaSuccess) return cuda_fail(_e, #expr);       \
+    } while (0)
+
+CNTT_API const char* cntt_status_string(int s)
+{
+    switch (s) {
+    case CNTT_OK: return "ok";
+    case CNTT_INVALID_SIZE: return "invalid polynomial size (try_new -> None)";
+    case CNTT_INVALID_MODULUS: return "modulus is not prime (try_new -> None)";
+    case CNTT_NO_ROOT: return "no primitive 2n-th root of unity (try_new -> None)";
+    case CNTT_LENGTH_MISMATCH: return "buffer length does not match the plan (reference: assert_eq! panic)";
+    case CNTT_CUDA_ERROR: return "CUDA error (see cntt_last_cuda_error)";
+    case CNTT_NULL_POINTER: return "null pointer";
+    case CNTT_UNSUPPORTED: return "operation not supported by this plan";
+    case CNTT_PANIC_MODULUS: return "modulus <= 1 (reference: Div::new assert panic)";
+    default: return "unknown status";
+    }
+}
+CNTT_API const char* cntt_last_cuda_error(void) { return t_cuda_err.c_str(); }
+CNTT_API const char* cntt_version(void) { return "cntt_b200 0.1 (sm_100a; concrete-ntt 0.2.0 semantics)"; }
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+        cur = dev;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0 && prev != cur) cudaSetDevice(prev);
+    }
+    int cur = -1;
+};
+#define GUARD(dev)                                                         \
+    DeviceGuard _guard(dev);                                               \
+    if (!_guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice")
+
+// ---- plan-time helpers -------------------------------------------------------------------------------
+CNTT_API int cntt_is_prime64(uint64_t n) { return host::is_prime_u64(n) ? 1 : 0; }
+CNTT_API int cntt_largest_prime_in_arithmetic_progression64(uint64_t factor, uint64_t offset, uint64_t lo, uint64_t hi, uint64_t* out)
+{
+    uint64_t v;
+    if (!host::largest_prime_in_arithmetic_progression(factor, offset, lo, hi, &v)) return 0;
+    if (out) *out = v;
+    return 1;
+}
+CNTT_API int cntt_find_primitive_root64(uint64_t p, uint64_t degree, uint64_t* root)
+{
+    if (p < 2 || degree < 2 || (degree & (degree - 1))) return 0;
+    uint64_t r;
+    if (!host::primitive_root_pow2(p, degree, &r)) return 0;
+    if (root) *root = r;
+    return 1;
+}
+CNTT_API int cntt_host_alloc(void** ptr, size_t bytes)
+{
+    if (!ptr) return CNTT_NULL_POINTER;
+    CU(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return CNTT_OK;
+}
+CNTT_API int cntt_host_free(void* ptr)
+{
+    if (ptr) CU(cudaFreeHost(ptr));
+    return CNTT_OK;
+}
+
+// ---- staging for the host-slice entry points ----------------------------------------------------------
+// A plan owns (lazily) one internal stream and a device staging arena; host calls on one plan are
+// serialised by a mutex (the reference call is synchronous too).
+struct Staging {
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    void* buf = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        cudaError_t e;
+        if (!stream) {
+            if ((e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if ((e = cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking)) != cudaSuccess) return e;
+            for (auto& v : ev)
+                if ((e = cudaEventCreateWithFlags(&v, cudaEventDisableTiming)) != cudaSuccess) return e;
+        }
+        if (bytes > cap) {
+            if (buf) cudaFree(buf);
+            buf = nullptr;
+            cap = 0;
+            if ((e = cudaMalloc(&buf, bytes)) != cudaSuccess) return e;
+            cap = bytes;
+        }
+        return cudaSuccess;
+    }
+    void release()
+    {
+        if (buf) cudaFree(buf);
+        for (auto& v : ev)
+            if (v) cudaEventDestroy(v);
+        if (stream) cudaStreamDestroy(stream);
+        if (stream2) cudaStreamDestroy(stream2);
+    }
+};
+
+// ---- prime plans ------------------------------------------------------------------------------------------
+enum Cls32 { C32_L4 = 0, C32_L2 = 1, C32_G = 2 };
+enum Cls64 { C64_L4 = 0, C64_L2 = 1, C64_S = 2, C64_G = 3 };
+
+struct cntt_prime32_plan {
+    size_t n;
+    uint32_t p;
+    int device;
+    int cls;
+    int logn;
+    Mod32 mod;
+    uint2* d_fwd;
+    uint2* d_inv;
+    Staging stg;
+};
+struct cntt_prime64_plan {
+    size_t n;
+    uint64_t p;
+    int device;
+    int cls;
+    int logn;
+    Mod64 mod;
+    void* d_fwd; // ulonglong2[n] (Shoup classes) or uint64_t[n] (Solinas)
+    void* d_inv;
+    Staging stg;
+};
+
+static int validate(size_t n, uint64_t p, size_t min_n, uint64_t* psi, int* logn)
+{
+    if (p <= 1) return CNTT_PANIC_MODULUS; // Div32::new / Div64::new assert (fastdiv.rs:49,99)
+    if (n < min_n || (n & (n - 1)) != 0) return CNTT_INVALID_SIZE;
+    int lg = 0;
+    while (((size_t)1 << lg) < n) ++lg;
+    if (lg > kMaxLogN) return CNTT_INVALID_SIZE;
+    if (!host::is_prime_u64(p)) return CNTT_INVALID_MODULUS;
+    if (!host::primitive_root_pow2(p, 2 * (uint64_t)n, psi)) return CNTT_NO_ROOT;
+    *logn = lg;
+    return CNTT_OK;
+}
+
+static int build_prime32(size_t n, uint32_t p, int device, cntt_prime32_plan** out)
+{
+    uint64_t psi;
+    int logn;
+    int st = validate(n, p, 32, &psi, &logn);
+    if (st != CNTT_OK) return st;
+    std::vector<uint64_t> f, iv;
+    host::negacyclic_twiddles(p, logn, psi, f, iv);
+    std::vector<uint2> hf(n), hi(n);
+    for (size_t i = 0; i < n; i++) {
+        hf[i] = make_uint2((uint32_t)f[i], (uint32_t)((f[i] << 32) / p));
+        hi[i] = make_uint2((uint32_t)iv[i], (uint32_t)((iv[i] << 32) / p));
+    }
+    GUARD(device);
+    cntt_prime32_plan* pl = new cntt_prime32_plan();
+    pl->n = n; pl->p = p; pl->device = device; pl->logn = logn;
+    pl->cls = p < (1u << 30) ? C32_L4 : p < (1u << 31) ? C32_L2 : C32_G;
+    host::Fp fp(p);
+    Mod32& m = pl->mod;
+    m.p = p; m.two_p = 2u * p; m.neg_p = 0u - p;
+    m.n_inv = (uint32_t)fp.inv(n % p);
+    m.n_inv_shoup = (uint32_t)(((uint64_t)m.n_inv << 32) / p);
+    const int big_q = host::ilog2(p) + 1;                       // prime32.rs:669
+    m.big_q_m1 = (uint32_t)(big_q - 1);
+    m.p_barrett = (uint32_t)((((uint64_t)1) << (big_q + 31)) / p); // prime32.rs:670-671
+    pl->d_fwd = pl->d_inv = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&pl->d_fwd, n * sizeof(uint2))) != cudaSuccess || (e = cudaMalloc(&pl->d_inv, n * sizeof(uint2))) != cudaSuccess ||
+        (e = cudaMemcpy(pl->d_fwd, hf.data(), n * sizeof(uint2), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(pl->d_inv, hi.data(), n * sizeof(uint2), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        if (pl->d_fwd) cudaFree(pl->d_fwd);
+        if (pl->d_inv) cudaFree(pl->d_inv);
+        delete pl;
+        return cuda_fail(e, "prime32 plan upload");
+    }
+    *out = pl;
+    return CNTT_OK;
+}
+
+CNTT_API int cntt_prime32_plan_new(size_t n, uint32_t p, int device, cntt_prime32_plan** out)
+{
+    if (!out) return CNTT_NULL_POINTER;
+    *out = nullptr;
+    return build_prime32(n, p, device, out);
+}
+CNTT_API void cntt_prime32_plan_free(cntt_prime32_plan* pl)
+{
+    if (!pl) return;
+    DeviceGuard g(pl->device);
+    pl->stg.release();
+    cudaFree(pl->d_fwd);
+    cudaFree(pl->d_inv);
+    delete pl;
+}
+CNTT_API size_t cntt_prime32_ntt_size(const cntt_prime32_plan* pl) { return pl ? pl->n : 0; }
+CNTT_API uint32_t cntt_prime32_modulus(const cntt_prime32_plan* pl) { return pl ? pl->p : 0; }
+
+template <class A> static PlanDev<A> dev32(const cntt_prime32_plan* pl)
+{
+    PlanDev<A> d;
+    d.logn = pl->logn; d.mod = pl->mod; d.tw_fwd = pl->d_fwd; d.tw_inv = pl->d_inv;
+    return d;
+}
+static cudaError_t run_ntt32(const cntt_prime32_plan* pl, uint32_t* d, size_t batch, bool fwd, cudaStream_t st)
+{
+    switch (pl->cls) {
+    case C32_L4: return ntt_A32L4(dev32<A32L4>(pl), d, batch, fwd, st);
+    case C32_L2: return ntt_A32L2(dev32<A32L2>(pl), d, batch, fwd, st);
+    default: return ntt_A32G(dev32<A32G>(pl), d, batch, fwd, st);
+    }
+}
+static cudaError_t run_pw32(const cntt_prime32_plan* pl, int op, uint32_t* dst, const uint32_t* a, const uint32_t* b, size_t nwords, cudaStream_t st)
+{
+    switch (pl->cls) {
+    case C32_L4: return pointwise_A32L4(dev32<A32L4>(pl), op, dst, a, b, nwords, st);
+    case C32_L2: return pointwise_A32L2(dev32<A32L2>(pl), op, dst, a, b, nwords, st);
+    default: return pointwise_A32G(dev32<A32G>(pl), op, dst, a, b, nwords, st);
+    }
+}
+
+CNTT_API int cntt_prime32_fwd(const cntt_prime32_plan* pl, uint32_t* d_buf, size_t batch, void* stream)
+{
+    if (!pl || (!d_buf && batch)) return CNTT_NULL_POINTER;
+    GUARD(pl->device);
+    CU(run_ntt32(pl, d_buf, batch, true, (cudaStream_t)stream));
+    return CNTT_OK;
+}
+CNTT_API int cntt_prime32_inv(const cntt_prime32_plan* pl, uint32_t* d_buf, size_t batch, void* stream)
+{
+    if (!pl || (!d_buf && batch)) return CNTT_NULL_POINTER;
+    GUARD(pl->device);
+    CU(run_ntt32(pl, d_buf, batch, false, (cudaStream_t)stream));
+    return CNTT_OK;
+}
+// The reference zips the slices and its SIMD bodies only touch whole vectors (prime32.rs:348); n is a
+// multiple of 32, so whole-polynomial streams are always whole vectors.  A ragged tail (nwords not a
+// multiple of 4) is rejected instead of being silently dropped.
+CNTT_API int cntt_prime32_mul_assign_normalize(const cntt_prime32_plan* pl, uint32_t* l, const uint32_t* r, size_t nwords, void* stream)
+{
+    if (!pl || ((!l || !r) && nwords)) return CNTT_NULL_POINTER;
+    if (nwords % 4) return CNTT_LENGTH_MISMATCH;
+    GUARD(pl->device);
+    CU(run_pw32(pl, OP_MUL_ASSIGN_NORMALIZE, l, r, nullptr, nwords, (cudaStream_t)stream));
+    return CNTT_OK;
+}
+CNTT_API int cntt_prime32_normalize(const cntt_prime32_plan* pl, uint32_t* v, size_t nwords, void* stream)
+{
+    if (!pl || (!v && nwords)) return CNTT_NULL_POINTER;
+    if (nwords % 4) return CNTT_LENGTH_MISMATCH;
+    GUARD(pl->device);
+    CU(run_pw32(pl, OP_NORMALIZE, v, nullptr, nullptr, nwords, (cudaStream_t)stream));
+    return CNTT_OK;
+}
+CNTT_API int cntt_prime32_mul_accumulate(const cntt_prime32_plan* pl, uint32_t* acc, const uint32_t* l, const uint32_t* r, size_t nwords, void* stream)
+{
+    if (!pl || ((!acc || !l || !r) && nwords)) return CNTT_NULL_POINTER;
+    if (nwords % 4) return CNTT_LENGTH_MISMATCH;
+    GUARD(pl->device);
+    CU(run_pw32(pl, OP_MUL_ACCUMULATE, acc, l, r, nwords, (cudaStream_t)stream));
+    return CNTT_OK;
+}
+
+// ---- prime64 ------------------------------------------------------------------------------------------------
+static int build_prime64(size_t n, uint64_t p, int device, cntt_prime64_plan** out)
+{
+    typedef unsigned __int128 u128;
+    uint64_t psi;
+    int logn;
+    int st = validate(n, p, 16, &psi, &logn);
+    if (st != CNTT_OK) return st;
+    std::vector<uint64_t> f, iv;
+    host::negacyclic_twiddles(p, logn, psi, f, iv);
+    const int cls = p == CNTT_SOLINAS_P ? C64_S : p < (1ull << 62) ? C64_L4 : p < (1ull << 63) ? C64_L2 : C64_G;
+    GUARD(device);
+    cntt_prime64_plan* pl = new cntt_prime64_plan();
+    pl->n = n; pl->p = p; pl->device = device; pl->logn = logn; pl->cls = cls;
+    host::Fp fp(p);
+    Mod64& m = pl->mod;
+    m.p = p; m.two_p = 2ull * p; m.neg_p = 0ull - p;
+    m.n_inv = fp.inv(n % p);
+    m.n_inv_shoup = (uint64_t)((((u128)m.n_inv) << 64) / p);
+    const int big_q = host::ilog2(p) + 1;                           // prime64.rs:754
+    m.big_q_m1 = (uint32_t)(big_q - 1);
+    m.p_barrett = (uint64_t)((((u128)1) << (big_q + 63)) / p);      // prime64.rs:755-756 (unused when p >= 2^63)
+    pl->d_fwd = pl->d_inv = nullptr;
+    cudaError_t e;
+    size_t bytes;
+    std::vector<ulonglong2> sf, si;
+    const void *hf, *hi;
+    if (cls == C64_S) {
+        bytes = n * sizeof(uint64_t);
+        hf = f.data(); hi = iv.data();
+    } else {
+        sf.resize(n); si.resize(n);
+        for (size_t i = 0; i < n; i++) {
+            sf[i] = make_ulonglong2(f[i], (uint64_t)((((u128)f[i]) << 64) / p));
+            si[i] = make_ulonglong2(iv[i], (uint64_t)((((u128)iv[i]) << 64) / p));
+        }
+        bytes = n * sizeof(ulonglong2);
+        hf = sf.data(); hi = si.data();
+    }
+    if ((e = cudaMalloc(&pl->d_fwd, bytes)) != cudaSuccess || (e = cudaMalloc(&pl->d_inv, bytes)) != cudaSuccess ||
+        (e = cudaMemcpy(pl->d_fwd, hf, bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(pl->d_inv, hi, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        if (pl->d_fwd) cudaFree(pl->d_fwd);
+        if (pl->d_inv) cudaFree(pl->d_inv);
+        delete pl;
+        return cuda_fail(e, "prime64 plan upload");
+    }
+    *out = pl;
+    return CNTT_OK;
+}
+CNTT_API int cntt_prime64_plan_new(size_t n, uint64_t p, int device, cntt_prime64_plan** out)
+{
+    if (!out) return CNTT_NULL_POINTER;
+    *out = nullptr;
+    return build_prime64(n, p, device, out);
+}
+CNTT_API void cntt_prime64_plan_free(cntt_prime64_plan* pl)
+{
+    if (!pl) return;
+    DeviceGuard g(pl->device);
+    pl->stg.release();
+    cudaFree(pl->d_fwd);
+    cudaFree(pl->d_inv);
+    delete pl;
+}
+CNTT_API size_t cntt_prime64_ntt_size(const cntt_prime64_plan* pl) { return pl ? pl->n : 0; }
+CNTT_API uint64_t cntt_prime64_modulus(const cntt_prime64_plan* pl) { return pl ? pl->p : 0; }
+
+template <class A> static PlanDev<A> dev64(const cntt_prime64_plan* pl)
+{
+    PlanDev<A> d;
+    d.logn = pl->logn; d.mod = pl->mod;
+    d.tw_fwd = reinterpret_cast<const typename A::Tw*>(pl->d_fwd);
+    d.tw_inv = reinterpret_cast<const typename A::Tw*>(pl->d_inv);
+    return d;
+}
+static cudaError_t run_ntt64(const cntt_prime64_plan* pl, uint64_t* d, size_t batch, bool fwd, cudaStream_t st)
+{
+    switch (pl->cls) {
+    case C64_L4: return ntt_A64L4(dev64<A64L4>(pl), d, batch, fwd, st);
+    case C64_L2: return ntt_A64L2(dev64<A64L2>(pl), d, batch, fwd, st);
+    case C64_S: return ntt_A64S(dev64<A64S>(pl), d, batch, fwd, st);
+    default: return ntt_A64G(dev64<A64G>(pl), d, batch, fwd, st);
+    }
+}
+static cudaError_t run_pw64(const cntt_prime64_plan* pl, int op, uint64_t* dst, const uint64_t* a, const uint64_t* b, size_t nwords, cudaStream_t st)
+{
+    switch (pl->cls) {
+    case C64_L4: return pointwise_A64L4(dev64<A64L4>(pl), op, dst, a, b, nwords, st);
+    case C64_L2: return pointwise_A64L2(dev64<A64L2>(pl), op, dst, a, b, nwords, st);
+    case C64_S: return pointwise_A64S(dev64<A64S>(pl), op, dst, a, b, nwords, st);
+    default: return pointwise_A64G(dev64<A64G>(pl), op, dst, a, b, nwords, st);
+    }
+}
+CNTT_API int cntt_prime64_fwd(const cntt_prime64_plan* pl, uint64_t* d_buf, size_t batch, void* stream)
+{
+    if (!pl || (!d_buf && batch)) return CNTT_NULL_POINTER;
+    GUARD(pl->device);
+    CU(run_ntt64(pl, d_buf, batch, true, (cudaStream_t)stream));
+    return CNTT_OK;
+}
+CNTT_API int cntt_prime64_inv(const cntt_prime64_plan* pl, uint64_t* d_buf, size_t batch, void* stream)
+{
+    if (!pl || (!d_buf && batch)) return CNTT_NULL_POINTER;
+    GUARD(pl->device);
+    CU(run_ntt64(pl, d_buf, batch, false, (cudaStream_t)stream));
+    return CNTT_OK;
+}
+CNTT_API int cntt_prime64_mul_assign_normalize(const cntt_prime64_plan* pl, uint64_t* l, const uint64_t* r, size_t nwords, void* stream)
+{
+    if (!pl || ((!l || !r) && nwords)) return CNTT_NULL_POINTER;
+    if (nwords % 2) return CNTT_LENGTH_MISMATCH;
+    GUARD(pl->device);
+    CU(run_pw64(pl, OP_MUL_ASSIGN_NORMALIZE, l, r, nullptr, nwords, (cudaStream_t)stream));
+    return CNTT_OK;
+}
+CNTT_API int cntt_prime64_normalize(const cntt_prime64_plan* pl, uint64_t* v, size_t nwords, void* stream)
+{
+    if (!pl || (!v && nwords)) return CNTT_NULL_POINTER;
+    if (nwords % 2) return CNTT_LENGTH_MISMATCH;
+    GUARD(pl->device);
+    CU(run_pw64(pl, OP_NORMALIZE, v, nullptr, nullptr, nwords, (cudaStream_t)stream));
+    return CNTT_OK;
+}
+CNTT_API int cntt_prime64_mul_accumulate(const cntt_prime64_plan* pl, uint64_t* acc, const uint64_t* l, const uint64_t* r, size_t nwords, void* stream)
+{
+    if (!pl || ((!acc || !l || !r) && nwords)) return CNTT_NULL_POINTER;
+    if (nwords % 2) return CNTT_LENGTH_MISMATCH;
+    GUARD(pl->device);
+    CU(run_pw64(pl, OP_MUL_ACCUMULATE, acc, l, r, nwords, (cudaStream_t)stream));
+    return CNTT_OK;
+}
+
+// ---- host-slice flavours of the prime plans --------------------------------------------------------------------
+// Chunked and double-buffered: chunk c+1 uploads on `stream2` while chunk c computes/downloads on `stream`.
+template <class Fn>
+static int host_inplace(Staging& stg, int device, void* h_buf, size_t total_bytes, size_t bytes_per_poly, size_t batch, Fn launch)
+{
+    if (total_bytes == 0) return CNTT_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    std::lock_guard<std::mutex> lk(stg.mu);
+    // two halves of the arena, each holding `chunk` polynomials
+    const size_t target = (size_t)64 << 20;
+    size_t chunk = std::max<size_t>(1, std::min(batch, target / std::max<size_t>(1, bytes_per_poly)));
+    if (chunk >= batch) chunk = batch;
+    const size_t half = chunk * bytes_per_poly;
+    CU(stg.ensure(2 * half));
+    char* h = static_cast<char*>(h_buf);
+    const size_t nchunks = (batch + chunk - 1) / chunk;
+    for (size_t c = 0; c < nchunks; c++) {
+        const size_t b0 = c * chunk, nb = std::min(chunk, batch - b0);
+        char* d = static_cast<char*>(stg.buf) + (c & 1) * half;
+        // the half is free once the download of chunk c-2 finished
+        if (c >= 2) CU(cudaStreamWaitEvent(stg.stream2, stg.ev[2 + (c & 1)], 0));
+        CU(cudaMemcpyAsync(d, h + b0 * bytes_per_poly, nb * bytes_per_poly, cudaMemcpyHostToDevice, stg.stream2));
+        CU(cudaEventRecord(stg.ev[c & 1], stg.stream2));
+        CU(cudaStreamWaitEvent(stg.stream, stg.ev[c & 1], 0));
+        cudaError_t e = launch(d, nb, stg.stream);
+        if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+        CU(cudaMemcpyAsync(h + b0 * bytes_per_poly, d, nb * bytes_per_poly, cudaMemcpyDeviceToHost, stg.stream));
+        CU(cudaEventRecord(stg.ev[2 + (c & 1)], stg.stream));
+    }
+    CU(cudaStreamSynchronize(stg.stream));
+    CU(cudaStreamSynchronize(stg.stream2));
+    return CNTT_OK;
+}
+
+#define PRIME_HOST_NTT(BITS, T, NAME, BODY)                                                                             \
+    CNTT_API int cntt_prime##BITS##_##NAME##_host(const cntt_prime##BITS##_plan* pl, T* h_buf, size_t len, size_t batch) \
+    {                                                                                                                    \
+        if (!pl || (!h_buf && len)) return CNTT_NULL_POINTER;                                                            \
+        if (len != pl->n * batch) return CNTT_LENGTH_MISMATCH;                                                           \
+        auto* mpl = const_cast<cntt_prime##BITS##_plan*>(pl);                                                            \
+        return host_inplace(mpl->stg, pl->device, h_buf, len * sizeof(T), pl->n * sizeof(T), batch,                      \
+                            [&](void* d, size_t nb, cudaStream_t st) -> cudaError_t { BODY });                           \
+    }
+PRIME_HOST_NTT(32, uint32_t, fwd, return run_ntt32(pl, (uint32_t*)d, nb, true, st);)
+PRIME_HOST_NTT(32, uint32_t, inv, return run_ntt32(pl, (uint32_t*)d, nb, false, st);)
+PRIME_HOST_NTT(32, uint32_t, fwd_inv, cudaError_t e = run_ntt32(pl, (uint32_t*)d, nb, true, st); if (e != cudaSuccess) return e;
+               return run_ntt32(pl, (uint32_t*)d, nb, false, st);)
+PRIME_HOST_NTT(64, uint64_t, fwd, return run_ntt64(pl, (uint64_t*)d, nb, true, st);)
+PRIME_HOST_NTT(64, uint64_t, inv, return run_ntt64(pl, (uint64_t*)d, nb, false, st);)
+PRIME_HOST_NTT(64, uint64_t, fwd_inv, cudaError_t e = run_ntt64(pl, (uint64_t*)d, nb, true, st); if (e != cudaSuccess) return e;
+               return run_ntt64(pl, (uint64_t*)d, nb, false, st);)
+
+// pointwise host flavours: simple staged version (streams: dst [+a [+b]])
+template <class T, class Fn>
+static int host_pointwise(Staging& stg, int device, T* h_dst, const T* h_a, const T* h_b, size_t nwords, Fn launch)
+{
+    if (nwords == 0) return CNTT_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    std::lock_guard<std::mutex> lk(stg.mu);
+    const size_t bytes = nwords * sizeof(T);
+    const int nstreams = 1 + (h_a ? 1 : 0) + (h_b ? 1 : 0);
+    CU(stg.ensure(bytes * nstreams));
+    T* d_dst = static_cast<T*>(stg.buf);
+    T* d_a = h_a ? d_dst + nwords : nullptr;
+    T* d_b = h_b ? d_dst + 2 * nwords : nullptr;
+    CU(cudaMemcpyAsync(d_dst, h_dst, bytes, cudaMemcpyHostToDevice, stg.stream));
+    if (h_a) CU(cudaMemcpyAsync(d_a, h_a, bytes, cudaMemcpyHostToDevice, stg.stream));
+    if (h_b) CU(cudaMemcpyAsync(d_b, h_b, bytes, cudaMemcpyHostToDevice, stg.stream));
+    cudaError_t e = launch(d_dst, d_a, d_b, stg.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    CU(cudaMemcpyAsync(h_dst, d_dst, bytes, cudaMemcpyDeviceToHost, stg.stream));
+    CU(cudaStreamSynchronize(stg.stream));
+    return CNTT_OK;
+}
+#define PRIME_HOST_PW(BITS, T, VEC)                                                                                         \
+    CNTT_API int cntt_prime##BITS##_mul_assign_normalize_host(const cntt_prime##BITS##_plan* pl, T* l, const T* r, size_t nwords) \
+    {                                                                                                                        \
+        if (!pl || ((!l || !r) && nwords)) return CNTT_NULL_POINTER;                                                         \
+        if (nwords % VEC) return CNTT_LENGTH_MISMATCH;                                                                       \
+        auto* mpl = const_cast<cntt_prime##BITS##_plan*>(pl);                                                                \
+        return host_pointwise<T>(mpl->stg, pl->device, l, r, nullptr, nwords, [&](T* d, T* a, T*, cudaStream_t st) {         \
+            return run_pw##BITS(pl, OP_MUL_ASSIGN_NORMALIZE, d, a, nullptr, nwords, st);                                     \
+        });                                                                                                                  \
+    }                                                                                                                        \
+    CNTT_API int cntt_prime##BITS##_normalize_host(const cntt_prime##BITS##_plan* pl, T* v, size_t nwords)                   \
+    {                                                                                                                        \
+        if (!pl || (!v && nwords)) return CNTT_NULL_POINTER;                                                                 \
+        if (nwords % VEC) return CNTT_LENGTH_MISMATCH;                                                                       \
+        auto* mpl = const_cast<cntt_prime##BITS##_plan*>(pl);                                                                \
+        return host_pointwise<T>(mpl->stg, pl->device, v, nullptr, nullptr, nwords, [&](T* d, T*, T*, cudaStream_t st) {     \
+            return run_pw##BITS(pl, OP_NORMALIZE, d, nullptr, nullptr, nwords, st);                                          \
+        });                                                                                                                  \
+    }                                                                                                                        \
+    CNTT_API int cntt_prime##BITS##_mul_accumulate_host(const cntt_prime##BITS##_plan* pl, T* acc, const T* l, const T* r, size_t nwords) \
+    {                                                                                                                        \
+        if (!pl || ((!acc || !l || !r) && nwords)) return CNTT_NULL_POINTER;                                                 \
+        if (nwords % VEC) return CNTT_LENGTH_MISMATCH;                                                                       \
+        auto* mpl = const_cast<cntt_prime##BITS##_plan*>(pl);                                                                \
+        return host_pointwise<T>(mpl->stg, pl->device, acc, l, r, nwords, [&](T* d, T* a, T* b, cudaStream_t st) {           \
+            return run_pw##BITS(pl, OP_MUL_ACCUMULATE, d, a, b, nwords, st);                                                 \
+        });                                                                                                                  \
+    }
+PRIME_HOST_PW(32, uint32_t, 4)
+PRIME_HOST_PW(64, uint64_t, 2)
+
+// ---- native plans ---------------------------------------------------------------------------------------------------
+struct cntt_native_plan {
+    size_t n;
+    int kind;
+    int device;
+    int nprimes;
+    cntt_prime32_plan* sub[10];
+    NativePlanDev dev;
+    Staging stg;
+};
+
+CNTT_API int cntt_native_plan_new(size_t n, int word_bits, int binary, int device, cntt_native_plan** out)
+{
+    if (!out) return CNTT_NULL_POINTER;
+    *out = nullptr;
+    int kind;
+    if (word_bits == 32) kind = binary ? NK_BINARY32 : NK_NATIVE32;
+    else if (word_bits == 64) kind = binary ? NK_BINARY64 : NK_NATIVE64;
+    else if (word_bits == 128) kind = binary ? NK_BINARY128 : NK_NATIVE128;
+    else return CNTT_UNSUPPORTED;
+    const NativeConsts& c = native_consts();
+    cntt_native_plan* pl = new cntt_native_plan();
+    pl->n = n; pl->kind = kind; pl->device = device; pl->nprimes = native_num_primes(kind);
+    for (int k = 0; k < 10; k++) pl->sub[k] = nullptr;
+    for (int k = 0; k < pl->nprimes; k++) {
+        // Plan::try_new(n, P_k)? for every prime (src/native64.rs:933-942): first failure -> None
+        int st = build_prime32(n, c.P[k], device, &pl->sub[k]);
+        if (st != CNTT_OK) {
+            for (int j = 0; j < k; j++) cntt_prime32_plan_free(pl->sub[j]);
+            delete pl;
+            return st;
+        }
+    }
+    pl->dev.kind = kind;
+    pl->dev.logn = pl->sub[0]->logn;
+    pl->dev.nprimes = pl->nprimes;
+    for (int k = 0; k < pl->nprimes; k++) pl->dev.sub[k] = dev32<A32L4>(pl->sub[k]);
+    *out = pl;
+    return CNTT_OK;
+}
+CNTT_API void cntt_native_plan_free(cntt_native_plan* pl)
+{
+    if (!pl) return;
+    {
+        DeviceGuard g(pl->device);
+        pl->stg.release();
+    }
+    for (int k = 0; k < pl->nprimes; k++) cntt_prime32_plan_free(pl->sub[k]);
+    delete pl;
+}
+CNTT_API size_t cntt_native_ntt_size(const cntt_native_plan* pl) { return pl ? pl->n : 0; }
+CNTT_API int cntt_native_num_primes(const cntt_native_plan* pl) { return pl ? pl->nprimes : 0; }
+CNTT_API uint32_t cntt_native_prime(const cntt_native_plan* pl, int i) { return (pl && i >= 0 && i < pl->nprimes) ? pl->sub[i]->p : 0; }
+
+static cudaError_t native_fwd_impl(const cntt_native_plan* pl, const void* value, uint32_t* planes, size_t batch, bool binary_copy, cudaStream_t st)
+{
+    const size_t nwords = pl->n * batch;
+    cudaError_t e = native_reduce(pl->dev, value, planes, nwords, nwords, binary_copy, st);
+    if (e != cudaSuccess) return e;
+    for (int k = 0; k < pl->nprimes; k++)
+        if ((e = ntt_A32L4(pl->dev.sub[k], planes + (size_t)k * nwords, batch, true, st)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+static cudaError_t native_inv_impl(const cntt_native_plan* pl, void* value, uint32_t* planes, size_t batch, cudaStream_t st)
+{
+    const size_t nwords = pl->n * batch;
+    cudaError_t e;
+    for (int k = 0; k < pl->nprimes; k++)
+        if ((e = ntt_A32L4(pl->dev.sub[k], planes + (size_t)k * nwords, batch, false, st)) != cudaSuccess) return e;
+    return native_crt(pl->dev, value, planes, nwords, nwords, st);
+}
+
+CNTT_API int cntt_native_fwd(const cntt_native_plan* pl, const void* d_value, uint32_t* d_mod_p, size_t batch, void* stream)
+{
+    if (!pl || ((!d_value || !d_mod_p) && batch)) return CNTT_NULL_POINTER;
+    GUARD(pl->device);
+    CU(native_fwd_impl(pl, d_value, d_mod_p, batch, false, (cudaStream_t)stream));
+    return CNTT_OK;
+}
+CNTT_API int cntt_native_fwd_binary(const cntt_native_plan* pl, const void* d_value, uint32_t* d_mod_p, size_t batch, void* stream)
+{
+    if (!pl || ((!d_value || !d_mod_p) && batch)) return CNTT_NULL_POINTER;
+    if (pl->kind < NK_BINARY32) return CNTT_UNSUPPORTED; // only native_binary* have fwd_binary
+    GUARD(pl->device);
+    CU(native_fwd_impl(pl, d_value, d_mod_p, batch, true, (cudaStream_t)stream));
+    return CNTT_OK;
+}
+CNTT_API int cntt_native_inv(const cntt_native_plan* pl, void* d_value, uint32_t* d_mod_p, size_t batch, void* stream)
+{
+    if (!pl || ((!d_value || !d_mod_p) && batch)) return CNTT_NULL_POINTER;
+    GUARD(pl->device);
+    CU(native_inv_impl(pl, d_value, d_mod_p, batch, (cudaStream_t)stream));
+    return CNTT_OK;
+}
+
+// Unfused pipeline (any N the plan supports): residue planes live in a stream-ordered scratch
+// allocation, processed in batch chunks so the scratch stays bounded.
+static cudaError_t native_polymul_unfused(const cntt_native_plan* pl, void* prod, const void* lhs, const void* rhs, size_t batch, cudaStream_t st)
+{
+    const size_t n = pl->n;
+    const int np = pl->nprimes;
+    const size_t wb = (size_t)native_word_bytes(pl->kind);
+    const size_t per_poly = 2 * (size_t)np * n * sizeof(uint32_t);
+    const size_t budget = (size_t)1 << 30;
+    const size_t chunk = std::max<size_t>(1, std::min(batch, budget / per_poly));
+    uint32_t* scratch = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&scratch, chunk * per_poly, st);
+    if (e != cudaSuccess) return e;
+    const bool binary = pl->kind >= NK_BINARY32;
+    for (size_t b0 = 0; b0 < batch && e == cudaSuccess; b0 += chunk) {
+        const size_t nb = std::min(chunk, batch - b0);
+        const size_t nwords = nb * n;
+        uint32_t* L = scratch;
+        uint32_t* R = scratch + (size_t)np * nwords;
+        const char* l = static_cast<const char*>(lhs) + b0 * n * wb;
+        const char* r = static_cast<const char*>(rhs) + b0 * n * wb;
+        char* o = static_cast<char*>(prod) + b0 * n * wb;
+        if ((e = native_fwd_impl(pl, l, L, nb, false, st)) != cudaSuccess) break;
+        if ((e = native_fwd_impl(pl, r, R, nb, binary, st)) != cudaSuccess) break;
+        for (int k = 0; k < np && e == cudaSuccess; k++)
+            e = pointwise_A32L4(pl->dev.sub[k], OP_MUL_ASSIGN_NORMALIZE, L + (size_t)k * nwords, R + (size_t)k * nwords, nullptr, nwords, st);
+        if (e != cudaSuccess) break;
+        e = native_inv_impl(pl, o, L, nb, st);
+    }
+    cudaError_t e2 = cudaFreeAsync(scratch, st);
+    return e != cudaSuccess ? e : e2;
+}
+
+static cudaError_t native_polymul_impl(const cntt_native_plan* pl, void* prod, const void* lhs, const void* rhs, size_t batch, cudaStream_t st)
+{
+    if (batch == 0) return cudaSuccess;
+    cudaError_t e = native_polymul_fused(pl->dev, prod, lhs, rhs, batch, st);
+    if (e != cudaErrorNotSupported) return e;
+    (void)cudaGetLastError();
+    return native_polymul_unfused(pl, prod, lhs, rhs, batch, st);
+}
+
+CNTT_API int cntt_native_polymul(const cntt_native_plan* pl, void* d_prod, const void* d_lhs, const void* d_rhs, size_t batch, void* stream)
+{
+    if (!pl || ((!d_prod || !d_lhs || !d_rhs) && batch)) return CNTT_NULL_POINTER;
+    GUARD(pl->device);
+    CU(native_polymul_impl(pl, d_prod, d_lhs, d_rhs, batch, (cudaStream_t)stream));
+    return CNTT_OK;
+}
+
+CNTT_API int cntt_native_polymul_host(const cntt_native_plan* pl, void* h_prod, const void* h_lhs, const void* h_rhs, size_t len, size_t batch)
+{
+    if (!pl || ((!h_prod || !h_lhs || !h_rhs) && len)) return CNTT_NULL_POINTER;
+    if (len != pl->n * batch) return CNTT_LENGTH_MISMATCH; // assert_eq!(n, lhs.len()) (src/native64.rs:1043-1045)
+    if (batch == 0) return CNTT_OK;
+    GUARD(pl->device);
+    auto* mpl = const_cast<cntt_native_plan*>(pl);
+    Staging& stg = mpl->stg;
+    std::lock_guard<std::mutex> lk(stg.mu);
+    const size_t wb = (size_t)native_word_bytes(pl->kind);
+    const size_t ppb = pl->n * wb; // bytes per polynomial
+    const size_t target = (size_t)32 << 20;
+    const size_t chunk = std::max<size_t>(1, std::min(batch, target / ppb));
+    const size_t slot = 3 * chunk * ppb; // lhs, rhs, prod
+    CU(stg.ensure(2 * slot));
+    const size_t nchunks = (batch + chunk - 1) / chunk;
+    for (size_t c = 0; c < nchunks; c++) {
+        const size_t b0 = c * chunk, nb = std::min(chunk, batch - b0);
+        char* base = static_cast<char*>(stg.buf) + (c & 1) * slot;
+        char *dl = base, *dr = base + chunk * ppb, *dp = base + 2 * chunk * ppb;
+        if (c >= 2) CU(cudaStreamWaitEvent(stg.stream2, stg.ev[2 + (c & 1)], 0));
+        CU(cudaMemcpyAsync(dl, static_cast<const char*>(h_lhs) + b0 * ppb, nb * ppb, cudaMemcpyHostToDevice, stg.stream2));
+        CU(cudaMemcpyAsync(dr, static_cast<const char*>(h_rhs) + b0 * ppb, nb * ppb, cudaMemcpyHostToDevice, stg.stream2));
+        CU(cudaEventRecord(stg.ev[c & 1], stg.stream2));
+        CU(cudaStreamWaitEvent(stg.stream, stg.ev[c & 1], 0));
+        CU(native_polymul_impl(pl, dp, dl, dr, nb, stg.stream));
+        CU(cudaMemcpyAsync(static_cast<char*>(h_prod) + b0 * ppb, dp, nb * ppb, cudaMemcpyDeviceToHost, stg.stream));
+        CU(cudaEventRecord(stg.ev[2 + (c & 1)], stg.stream));
+    }
+    CU(cudaStreamSynchronize(stg.stream));
+    CU(cudaStreamSynchronize(stg.stream2));
+    return CNTT_OK;
+}

@@ -1,0 +1,37 @@
+// dispatch.hpp -- non-template entry points into the per-class kernel instantiations.
+// Each arithmetic class is compiled in its own translation unit (inst_*.cu) so the build parallelises.
+#pragma once
+#include "ntt_kernels.cuh"
+
+namespace cntt {
+
+#define CNTT_DECLARE_CLASS(A)                                                                                      \
+    cudaError_t ntt_##A(const PlanDev<A>& pl, typename A::W* data, size_t batch, bool fwd, cudaStream_t st);        \
+    cudaError_t pointwise_##A(const PlanDev<A>& pl, int op, typename A::W* dst, const typename A::W* a,            \
+                              const typename A::W* b, size_t nwords, cudaStream_t st);
+
+CNTT_DECLARE_CLASS(A32L4)
+CNTT_DECLARE_CLASS(A32L2)
+CNTT_DECLARE_CLASS(A32G)
+CNTT_DECLARE_CLASS(A64L4)
+CNTT_DECLARE_CLASS(A64L2)
+CNTT_DECLARE_CLASS(A64S)
+CNTT_DECLARE_CLASS(A64G)
+
+#define CNTT_DEFINE_CLASS(A)                                                                                       \
+    cudaError_t ntt_##A(const PlanDev<A>& pl, typename A::W* data, size_t batch, bool fwd, cudaStream_t st)         \
+    {                                                                                                              \
+        return fwd ? launch_ntt<A, true>(pl, data, batch, st) : launch_ntt<A, false>(pl, data, batch, st);         \
+    }                                                                                                              \
+    cudaError_t pointwise_##A(const PlanDev<A>& pl, int op, typename A::W* dst, const typename A::W* a,            \
+                              const typename A::W* b, size_t nwords, cudaStream_t st)                              \
+    {                                                                                                              \
+        switch (op) {                                                                                              \
+        case OP_MUL_ASSIGN_NORMALIZE: return launch_pointwise<A, OP_MUL_ASSIGN_NORMALIZE>(pl, dst, a, b, nwords, st); \
+        case OP_NORMALIZE: return launch_pointwise<A, OP_NORMALIZE>(pl, dst, a, b, nwords, st);                    \
+        case OP_MUL_ACCUMULATE: return launch_pointwise<A, OP_MUL_ACCUMULATE>(pl, dst, a, b, nwords, st);          \
+        default: return cudaErrorInvalidValue;                                                                     \
+        }                                                                                                          \
+    }
+
+} // namespace cntt

@@ -1,0 +1,209 @@
+// ntt_engine.cuh -- the register/shared-memory NTT engine shared by every kernel in the library.
+//
+// Transform (reference semantics, SURVEY.md section 0 / prime32.rs:704-708):
+//   fwd: natural-order in -> bit-reversed out, merged-psi Cooley-Tukey; stage with m blocks uses
+//        twid[m + block] (heap order: twid[brv(k)] = psi^k, prime32.rs:248-282)
+//   inv: bit-reversed in -> natural out, Gentleman-Sande, un-normalised (x N)
+//
+// Decomposition (B200-first, not the reference's loop nest):
+//   A polynomial of N = 2^LOGN words is owned by T = N/R threads, R = 2^LOGR words per thread in
+//   registers.  The LOGN stages are cut into P = ceil(LOGN/LOGR) "passes".  Inside a pass every
+//   thread runs up to LOGR butterfly levels entirely in registers; between passes the words are
+//   re-distributed through (padded, conflict-free) shared memory.  A pass owned by a thread is a
+//   sub-tree of the twiddle heap rooted at node `nu`; level j of the pass uses heap entries
+//   (nu << j) + g, g < 2^j.
+//   Pass 0 covers the first R1 = LOGN - (P-1) LOGR stages with layout   i = tid + k T
+//   Pass q>=1 covers LOGR stages at s0 = R1 + (q-1) LOGR with layout    i = blk B + o + k S,
+//        B = N >> s0, S = B / R, blk = tid / S, o = tid % S,  nu = (nu0 << s0) + blk
+//   so the last pass leaves R consecutive words per thread (vector stores), and the first pass
+//   reads words strided by T (coalesced).  `nu0` = (1 << depth) + half lets the same code run as
+//   the contiguous second level of a two-level large-N transform -- exactly the reference's
+//   (recursion_depth, recursion_half) call (prime32/shoup.rs:597,686-706).
+#pragma once
+#include "arith.cuh"
+
+namespace cntt {
+
+template <int LOGN, int LOGR>
+struct Geo {
+    static_assert(LOGN >= LOGR, "need at least R words per polynomial");
+    static constexpr int N = 1 << LOGN;
+    static constexpr int R = 1 << LOGR;
+    static constexpr int T = N / R;                           // threads per polynomial
+    static constexpr int P = (LOGN + LOGR - 1) / LOGR;        // passes
+    static constexpr int R1 = LOGN - (P - 1) * LOGR;          // levels in pass 0
+    static __host__ __device__ constexpr int s0(int q) { return q == 0 ? 0 : R1 + (q - 1) * LOGR; }
+    static __host__ __device__ constexpr int levels(int q) { return q == 0 ? R1 : LOGR; }
+};
+
+// shared-memory padding: one extra word per 128-byte row makes every power-of-two stride
+// (<= one row) conflict-free for both the scatter and the gather side of an exchange.
+template <class W> struct PadCfg { static constexpr int LOGROW = (sizeof(W) == 4) ? 5 : 4; };
+template <class W> __host__ __device__ constexpr int padded_words(int n) { return n + (n >> PadCfg<W>::LOGROW); }
+template <class W> __device__ __forceinline__ int pad_idx(int i) { return i + (i >> PadCfg<W>::LOGROW); }
+
+template <class A, int LOGN, int LOGR>
+struct Engine {
+    typedef Geo<LOGN, LOGR> G;
+    typedef typename A::W W;
+    typedef typename A::Tw Tw;
+    typedef typename A::Mod Mod;
+    static constexpr int N = G::N, R = G::R, T = G::T, P = G::P;
+    static constexpr int LOGROW = PadCfg<W>::LOGROW;
+    static constexpr int SMEM_WORDS = padded_words<W>(N);      // per polynomial, per buffer
+    static constexpr int NBUF = (P >= 3) ? 2 : 1;              // ping-pong when >1 exchange
+
+    // ---- layouts ------------------------------------------------------------------------
+    // element index of register slot k of thread `tid` in pass q
+    template <int Q> static __device__ __forceinline__ int elem(int tid, int k)
+    {
+        if constexpr (Q == 0) {
+            return tid + k * T;
+        } else {
+            constexpr int B = N >> G::s0(Q);
+            constexpr int S = B >> LOGR;
+            return (tid & ~(S - 1)) * R + (tid & (S - 1)) + k * S;
+        }
+    }
+    template <int Q> static __device__ __forceinline__ unsigned node(int tid, unsigned nu0)
+    {
+        if constexpr (Q == 0) {
+            return nu0;
+        } else {
+            constexpr int s0 = G::s0(Q);
+            constexpr int B = N >> s0;
+            constexpr int S = B >> LOGR;
+            return (nu0 << s0) + (unsigned)(tid / S);
+        }
+    }
+    // padded shared-memory index of slot k: base computed once, per-k offsets are compile-time
+    // whenever the split (base + kS) >> LOGROW == (base >> LOGROW) + (kS >> LOGROW) is exact.
+    template <int Q> static __host__ __device__ constexpr int stride()
+    {
+        if constexpr (Q == 0) return T;
+        else return (N >> G::s0(Q)) >> LOGR;
+    }
+    template <int Q> static __host__ __device__ constexpr bool split_ok()
+    {
+        // Q == 0: exact iff T is a multiple of the row; Q >= 1: always exact
+        if constexpr (Q == 0) return (T % (1 << LOGROW)) == 0;
+        else return true;
+    }
+    template <int Q> static __device__ __forceinline__ int sidx(int base_elem, int base_pad, int k)
+    {
+        constexpr int S = stride<Q>();
+        if constexpr (split_ok<Q>()) return base_pad + k * S + ((k * S) >> LOGROW);
+        else return pad_idx<W>(base_elem + k * S);
+    }
+
+    template <int Q, int NP>
+    static __device__ __forceinline__ void scatter(W (&x)[NP][R], W* sm, int tid)
+    {
+        const int be = elem<Q>(tid, 0);
+        const int bp = pad_idx<W>(be);
+#pragma unroll
+        for (int np = 0; np < NP; np++)
+#pragma unroll
+            for (int k = 0; k < R; k++) sm[np * SMEM_WORDS * NBUF + sidx<Q>(be, bp, k)] = x[np][k];
+    }
+    template <int Q, int NP>
+    static __device__ __forceinline__ void gather(W (&x)[NP][R], const W* sm, int tid)
+    {
+        const int be = elem<Q>(tid, 0);
+        const int bp = pad_idx<W>(be);
+#pragma unroll
+        for (int np = 0; np < NP; np++)
+#pragma unroll
+            for (int k = 0; k < R; k++) x[np][k] = sm[np * SMEM_WORDS * NBUF + sidx<Q>(be, bp, k)];
+    }
+
+    static __device__ __forceinline__ Tw ldtw(const Tw* __restrict__ tw, unsigned idx) { return __ldg(tw + idx); }
+
+    // ---- register passes ------------------------------------------------------------------
+    template <int Q, int NP>
+    static __device__ __forceinline__ void fwd_pass(W (&x)[NP][R], const Tw* __restrict__ tw, unsigned nu, const Mod& m)
+    {
+        constexpr int L = G::levels(Q);
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            constexpr int dummy = 0; (void)dummy;
+            const int half = R >> (j + 1);
+#pragma unroll
+            for (int g = 0; g < (1 << j); g++) {
+                const Tw t = ldtw(tw, (nu << j) + g);
+#pragma unroll
+                for (int u = 0; u < half; u++) {
+#pragma unroll
+                    for (int np = 0; np < NP; np++) A::fwd_bf(x[np][2 * half * g + u], x[np][2 * half * g + u + half], t, m);
+                }
+            }
+        }
+    }
+    template <int Q, int NP>
+    static __device__ __forceinline__ void inv_pass(W (&x)[NP][R], const Tw* __restrict__ tw, unsigned nu, const Mod& m)
+    {
+        constexpr int L = G::levels(Q);
+#pragma unroll
+        for (int j = L - 1; j >= 0; j--) {
+            const int half = R >> (j + 1);
+#pragma unroll
+            for (int g = 0; g < (1 << j); g++) {
+                const Tw t = ldtw(tw, (nu << j) + g);
+#pragma unroll
+                for (int u = 0; u < half; u++) {
+#pragma unroll
+                    for (int np = 0; np < NP; np++) A::inv_bf(x[np][2 * half * g + u], x[np][2 * half * g + u + half], t, m);
+                }
+            }
+        }
+    }
+
+    // ---- whole transforms -------------------------------------------------------------------
+    // fwd: x enters in pass-0 layout (slot k <-> element tid + kT), leaves in pass-(P-1) layout
+    //      (slot k <-> element tid*R + k when P >= 2), lazy range of the policy (not canonical).
+    // `sm` points at this polynomial group's shared memory (NP * NBUF * SMEM_WORDS words).
+    // All threads of the CTA must call (uses __syncthreads()).
+    template <int Q, int NP>
+    static __device__ __forceinline__ void fwd_from(W (&x)[NP][R], W* sm, const Tw* __restrict__ tw, unsigned nu0, int tid, const Mod& m)
+    {
+        fwd_pass<Q, NP>(x, tw, node<Q>(tid, nu0), m);
+        if constexpr (Q + 1 < P) {
+            W* buf = sm + ((NBUF == 2 && (Q & 1)) ? SMEM_WORDS : 0);
+            scatter<Q, NP>(x, buf, tid);
+            __syncthreads();
+            gather<Q + 1, NP>(x, buf, tid);
+            if constexpr (NBUF == 1 && Q + 2 < P) __syncthreads();
+            fwd_from<Q + 1, NP>(x, sm, tw, nu0, tid, m);
+        }
+    }
+    template <int NP>
+    static __device__ __forceinline__ void fwd(W (&x)[NP][R], W* sm, const Tw* __restrict__ tw, unsigned nu0, int tid, const Mod& m)
+    {
+        fwd_from<0, NP>(x, sm, tw, nu0, tid, m);
+    }
+
+    // inv: x enters in pass-(P-1) layout, leaves in pass-0 layout, lazy range of the policy.
+    template <int Q, int NP>
+    static __device__ __forceinline__ void inv_from(W (&x)[NP][R], W* sm, const Tw* __restrict__ tw, unsigned nu0, int tid, const Mod& m)
+    {
+        inv_pass<Q, NP>(x, tw, node<Q>(tid, nu0), m);
+        if constexpr (Q > 0) {
+            W* buf = sm + ((NBUF == 2 && (Q & 1)) ? SMEM_WORDS : 0);
+            scatter<Q, NP>(x, buf, tid);
+            __syncthreads();
+            gather<Q - 1, NP>(x, buf, tid);
+            inv_from<Q - 1, NP>(x, sm, tw, nu0, tid, m);
+        }
+    }
+    template <int NP>
+    static __device__ __forceinline__ void inv(W (&x)[NP][R], W* sm, const Tw* __restrict__ tw, unsigned nu0, int tid, const Mod& m)
+    {
+        inv_from<P - 1, NP>(x, sm, tw, nu0, tid, m);
+    }
+
+    // element index held in slot k after fwd / expected before inv
+    static __device__ __forceinline__ int elem_last(int tid, int k) { return elem<P - 1>(tid, k); }
+    static __device__ __forceinline__ int elem_first(int tid, int k) { return elem<0>(tid, k); }
+};
+
+} // namespace cntt

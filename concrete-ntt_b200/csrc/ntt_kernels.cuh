@@ -1,0 +1,282 @@
+// ntt_kernels.cuh -- batched single-prime kernels built on the engine, and their launchers.
+//
+//   k_ntt_cta      one polynomial (or contiguous sub-block of a large polynomial) per thread group,
+//                  all of its stages in registers + shared memory          (N' <= 4096)
+//   k_ntt_strided  the leading 1..4 stages of a large transform, strided through global memory
+//   k_pointwise    mul_assign_normalize / normalize / mul_accumulate streams
+//
+// Batch layout everywhere: polynomial-major contiguous, buf[b*N + i] (the reference's slices
+// concatenated).
+#pragma once
+#include "ntt_engine.cuh"
+
+namespace cntt {
+
+constexpr int kMaxCtaLogN = 12; // largest transform a single CTA keeps on chip
+constexpr int kMaxLogN = 26;    // two-level + repeated strided passes; table memory is the limit
+
+template <class A>
+struct PlanDev {
+    int logn;
+    typename A::Mod mod;
+    const typename A::Tw* tw_fwd; // heap order, N entries, entry 0 unused (= 1)
+    const typename A::Tw* tw_inv;
+};
+
+// ---- vector helpers -------------------------------------------------------------------------
+template <class W, int R>
+__device__ __forceinline__ void store_contig(W* __restrict__ dst, const W (&x)[R])
+{
+    constexpr int BYTES = R * (int)sizeof(W);
+    if constexpr (BYTES % 16 == 0) {
+        constexpr int PER = 16 / (int)sizeof(W);
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+        for (int v = 0; v < R / PER; v++) {
+            uint4 q;
+            if constexpr (sizeof(W) == 4) {
+                q = make_uint4((uint32_t)x[4 * v], (uint32_t)x[4 * v + 1], (uint32_t)x[4 * v + 2], (uint32_t)x[4 * v + 3]);
+            } else {
+                uint64_t a = (uint64_t)x[2 * v], b = (uint64_t)x[2 * v + 1];
+                q = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
+            }
+            d4[v] = q;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < R; k++) dst[k] = x[k];
+    }
+}
+template <class W, int R>
+__device__ __forceinline__ void load_contig(const W* __restrict__ src, W (&x)[R])
+{
+    constexpr int BYTES = R * (int)sizeof(W);
+    if constexpr (BYTES % 16 == 0) {
+        constexpr int PER = 16 / (int)sizeof(W);
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+        for (int v = 0; v < R / PER; v++) {
+            uint4 q = s4[v];
+            if constexpr (sizeof(W) == 4) {
+                x[4 * v] = q.x; x[4 * v + 1] = q.y; x[4 * v + 2] = q.z; x[4 * v + 3] = q.w;
+            } else {
+                x[2 * v] = (uint64_t)q.x | ((uint64_t)q.y << 32);
+                x[2 * v + 1] = (uint64_t)q.z | ((uint64_t)q.w << 32);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < R; k++) x[k] = src[k];
+    }
+}
+
+// ---- CTA kernel -------------------------------------------------------------------------------
+// nvpoly "virtual polynomials" of N = 2^LOGN words each, contiguous.  With log_sub > 0 they are the
+// 2^log_sub contiguous sub-blocks of larger polynomials and virtual polynomial v uses the twiddle
+// sub-tree rooted at heap node (1 << log_sub) + (v mod 2^log_sub).
+template <class A, int LOGN, int LOGR, int GP, bool FWD>
+__global__ void __launch_bounds__(GP * Geo<LOGN, LOGR>::T)
+k_ntt_cta(const typename A::Tw* __restrict__ tw, const typename A::Mod m, typename A::W* __restrict__ data,
+          unsigned long long nvpoly, int log_sub)
+{
+    typedef Engine<A, LOGN, LOGR> E;
+    typedef typename A::W W;
+    constexpr int T = E::T, R = E::R, N = E::N;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    W* sm_all = reinterpret_cast<W*>(smem_raw);
+
+    const int grp = (GP == 1) ? 0 : (int)(threadIdx.x / T);
+    const int tid = (GP == 1) ? (int)threadIdx.x : (int)(threadIdx.x % T);
+    unsigned long long vp = (unsigned long long)blockIdx.x * GP + grp;
+    const bool active = vp < nvpoly;
+    if (!active) vp = nvpoly - 1; // keep the group in lock-step (barriers), discard its result
+    W* base = data + vp * (unsigned long long)N;
+    const unsigned nu0 = (1u << log_sub) + (unsigned)(vp & ((1ull << log_sub) - 1ull));
+    W* sm = sm_all + (size_t)grp * E::SMEM_WORDS * E::NBUF;
+
+    W x[1][R];
+    if constexpr (FWD) {
+#pragma unroll
+        for (int k = 0; k < R; k++) x[0][k] = base[tid + k * T];
+        E::template fwd<1>(x, sm, tw, nu0, tid, m);
+#pragma unroll
+        for (int k = 0; k < R; k++) x[0][k] = A::canon_fwd(x[0][k], m);
+        if (active) store_contig<W, R>(base + E::elem_last(tid, 0), x[0]);
+    } else {
+        load_contig<W, R>(base + E::elem_last(tid, 0), x[0]);
+        E::template inv<1>(x, sm, tw, nu0, tid, m);
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < R; k++) base[tid + k * T] = A::canon_inv(x[0][k], m);
+        }
+    }
+}
+
+// ---- strided kernel ---------------------------------------------------------------------------
+// Stages s0 .. s0+LOGK-1 of polynomials of 2^logn words.  One thread owns 2^LOGK words spaced
+// (N >> s0) >> LOGK apart; adjacent threads own adjacent columns (coalesced).
+template <class A, int LOGK, bool FWD>
+__global__ void __launch_bounds__(256)
+k_ntt_strided(const typename A::Tw* __restrict__ tw, const typename A::Mod m, typename A::W* __restrict__ data,
+              unsigned long long nitems, int logn, int s0)
+{
+    typedef Engine<A, LOGK, LOGK> E; // a single register pass of LOGK levels
+    typedef typename A::W W;
+    constexpr int K = 1 << LOGK;
+    const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nitems) return;
+    const int log_items = logn - LOGK;            // items per polynomial
+    const int log_bsub = logn - s0 - LOGK;        // column count of one block
+    const unsigned long long b = idx >> log_items;
+    const unsigned it = (unsigned)(idx & ((1ull << log_items) - 1ull));
+    const unsigned blk = it >> log_bsub;
+    const unsigned o = it & ((1u << log_bsub) - 1u);
+    const size_t bsub = (size_t)1 << log_bsub;
+    W* base = data + (b << logn) + ((size_t)blk << (logn - s0)) + o;
+    const unsigned nu = (1u << s0) + blk;
+    W x[1][K];
+#pragma unroll
+    for (int k = 0; k < K; k++) x[0][k] = base[(size_t)k * bsub];
+    if constexpr (FWD) {
+        E::template fwd_pass<0, 1>(x, tw, nu, m);
+#pragma unroll
+        for (int k = 0; k < K; k++) base[(size_t)k * bsub] = x[0][k]; // lazy range, consumed by the next level
+    } else {
+        E::template inv_pass<0, 1>(x, tw, nu, m);
+#pragma unroll
+        for (int k = 0; k < K; k++) base[(size_t)k * bsub] = A::canon_inv(x[0][k], m);
+    }
+}
+
+// ---- pointwise --------------------------------------------------------------------------------
+enum PointwiseOp { OP_MUL_ASSIGN_NORMALIZE = 0, OP_NORMALIZE = 1, OP_MUL_ACCUMULATE = 2 };
+
+template <class A, int OP>
+__global__ void __launch_bounds__(256)
+k_pointwise(const typename A::Mod m, typename A::W* __restrict__ dst, const typename A::W* __restrict__ a,
+            const typename A::W* __restrict__ b, unsigned long long nvec)
+{
+    typedef typename A::W W;
+    constexpr int PER = 16 / (int)sizeof(W);
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        W d[PER], xa[PER], xb[PER];
+        load_contig<W, PER>(dst + v * PER, d);
+        if constexpr (OP != OP_NORMALIZE) load_contig<W, PER>(a + v * PER, xa);
+        if constexpr (OP == OP_MUL_ACCUMULATE) load_contig<W, PER>(b + v * PER, xb);
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            if constexpr (OP == OP_MUL_ASSIGN_NORMALIZE) d[i] = A::mul_norm(d[i], xa[i], m);
+            else if constexpr (OP == OP_NORMALIZE) d[i] = A::norm(d[i], m);
+            else d[i] = A::mul_acc(d[i], xa[i], xb[i], m);
+        }
+        store_contig<W, PER>(dst + v * PER, d);
+    }
+}
+
+// ---- launchers --------------------------------------------------------------------------------
+template <class A, int LOGN, bool FWD>
+cudaError_t launch_cta_one(const PlanDev<A>& pl, typename A::W* data, unsigned long long nvpoly, int log_sub, cudaStream_t st)
+{
+    constexpr int LOGR = LOGN < 4 ? LOGN : 4;
+    typedef Engine<A, LOGN, LOGR> E;
+    constexpr int T = E::T;
+    constexpr int GP = T >= 128 ? 1 : 128 / T;
+    const size_t smem = (size_t)GP * E::NBUF * E::SMEM_WORDS * sizeof(typename A::W);
+    auto kern = k_ntt_cta<A, LOGN, LOGR, GP, FWD>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const unsigned long long nblk = (nvpoly + GP - 1) / GP;
+    if (nblk == 0) return cudaSuccess;
+    if (nblk > 0x7fffffffull) return cudaErrorInvalidValue;
+    kern<<<(unsigned)nblk, GP * T, smem, st>>>(FWD ? pl.tw_fwd : pl.tw_inv, pl.mod, data, nvpoly, log_sub);
+    return cudaGetLastError();
+}
+
+template <class A, bool FWD>
+cudaError_t launch_cta(const PlanDev<A>& pl, int logn_sub, typename A::W* data, unsigned long long nvpoly, int log_sub, cudaStream_t st)
+{
+    switch (logn_sub) {
+    case 4: return launch_cta_one<A, 4, FWD>(pl, data, nvpoly, log_sub, st);
+    case 5: return launch_cta_one<A, 5, FWD>(pl, data, nvpoly, log_sub, st);
+    case 6: return launch_cta_one<A, 6, FWD>(pl, data, nvpoly, log_sub, st);
+    case 7: return launch_cta_one<A, 7, FWD>(pl, data, nvpoly, log_sub, st);
+    case 8: return launch_cta_one<A, 8, FWD>(pl, data, nvpoly, log_sub, st);
+    case 9: return launch_cta_one<A, 9, FWD>(pl, data, nvpoly, log_sub, st);
+    case 10: return launch_cta_one<A, 10, FWD>(pl, data, nvpoly, log_sub, st);
+    case 11: return launch_cta_one<A, 11, FWD>(pl, data, nvpoly, log_sub, st);
+    case 12: return launch_cta_one<A, 12, FWD>(pl, data, nvpoly, log_sub, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+template <class A, int LOGK, bool FWD>
+cudaError_t launch_strided_one(const PlanDev<A>& pl, typename A::W* data, size_t batch, int s0, cudaStream_t st)
+{
+    const unsigned long long nitems = (unsigned long long)batch << (pl.logn - LOGK);
+    const unsigned long long nblk = (nitems + 255) / 256;
+    if (nblk == 0) return cudaSuccess;
+    if (nblk > 0x7fffffffull) return cudaErrorInvalidValue;
+    k_ntt_strided<A, LOGK, FWD><<<(unsigned)nblk, 256, 0, st>>>(FWD ? pl.tw_fwd : pl.tw_inv, pl.mod, data, nitems, pl.logn, s0);
+    return cudaGetLastError();
+}
+template <class A, bool FWD>
+cudaError_t launch_strided(const PlanDev<A>& pl, int logk, typename A::W* data, size_t batch, int s0, cudaStream_t st)
+{
+    switch (logk) {
+    case 1: return launch_strided_one<A, 1, FWD>(pl, data, batch, s0, st);
+    case 2: return launch_strided_one<A, 2, FWD>(pl, data, batch, s0, st);
+    case 3: return launch_strided_one<A, 3, FWD>(pl, data, batch, s0, st);
+    case 4: return launch_strided_one<A, 4, FWD>(pl, data, batch, s0, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+// Full transform of `batch` polynomials.  N <= 4096: one CTA-kernel launch.  Larger: leading stages
+// strided (<= 4 per launch) until the remaining contiguous blocks are 4096 words, then the CTA
+// kernel on all batch * 2^s blocks; the inverse runs the same schedule backwards.
+template <class A, bool FWD>
+cudaError_t launch_ntt(const PlanDev<A>& pl, typename A::W* data, size_t batch, cudaStream_t st)
+{
+    if (batch == 0) return cudaSuccess;
+    if (pl.logn <= kMaxCtaLogN) return launch_cta<A, FWD>(pl, pl.logn, data, batch, 0, st);
+    const int lead = pl.logn - kMaxCtaLogN;
+    cudaError_t e;
+    if constexpr (FWD) {
+        int s0 = 0;
+        while (s0 < lead) {
+            const int k = (lead - s0) < 4 ? (lead - s0) : 4;
+            if ((e = launch_strided<A, true>(pl, k, data, batch, s0, st)) != cudaSuccess) return e;
+            s0 += k;
+        }
+        return launch_cta<A, true>(pl, kMaxCtaLogN, data, (unsigned long long)batch << lead, lead, st);
+    } else {
+        if ((e = launch_cta<A, false>(pl, kMaxCtaLogN, data, (unsigned long long)batch << lead, lead, st)) != cudaSuccess) return e;
+        // mirror of the forward schedule: last forward chunk first
+        int chunks[8], nc = 0, s = 0;
+        while (s < lead) { const int k = (lead - s) < 4 ? (lead - s) : 4; chunks[nc++] = k; s += k; }
+        for (int c = nc - 1; c >= 0; c--) {
+            s -= chunks[c];
+            if ((e = launch_strided<A, false>(pl, chunks[c], data, batch, s, st)) != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+}
+
+template <class A, int OP>
+cudaError_t launch_pointwise(const PlanDev<A>& pl, typename A::W* dst, const typename A::W* a, const typename A::W* b,
+                             size_t nwords, cudaStream_t st)
+{
+    constexpr int PER = 16 / (int)sizeof(typename A::W);
+    const unsigned long long nvec = nwords / PER; // n >= 16 words, so nwords is a multiple of PER
+    if (nvec == 0) return cudaSuccess;
+    unsigned long long nblk = (nvec + 255) / 256;
+    const unsigned long long cap = 148ull * 32ull;
+    if (nblk > cap) nblk = cap;
+    k_pointwise<A, OP><<<(unsigned)nblk, 256, 0, st>>>(pl.mod, dst, a, b, nvec);
+    return cudaGetLastError();
+}
+
+} // namespace cntt

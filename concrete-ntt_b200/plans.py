@@ -1,0 +1,253 @@
+"""Host-side mirror of the reference's Plan API (same names, argument meaning and error behaviour) over
+the C ABI.  One polynomial per call becomes one *batch* per call: every buffer argument is an array whose
+last dimension is the polynomial (``n`` words) and whose leading dimensions are the batch.
+
+Buffers may be
+  * torch CUDA tensors  -> device-resident path, in place, asynchronous on the current torch stream;
+  * numpy arrays        -> host-slice path (pinned or pageable), staged H2D/D2H inside the library.
+Reference: prime32.rs:627-928, prime64.rs:701-1129, native*.rs / native_binary*.rs `impl Plan32`.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ReferencePanic, check
+
+try:  # torch is plumbing (device memory, streams); numpy-only use stays possible
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _is_torch(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _stream_of(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+class _Buf:
+    """Pointer + shape facts of one argument."""
+
+    def __init__(self, x, itemsize, name):
+        self.is_dev = _is_torch(x)
+        if self.is_dev:
+            if not x.is_cuda:
+                raise TypeError("%s: torch tensors must live on a CUDA device (use numpy for host slices)" % name)
+            if not x.is_contiguous():
+                raise ValueError("%s must be contiguous" % name)
+            if x.element_size() != itemsize:
+                raise TypeError("%s: expected %d-byte words" % (name, itemsize))
+            self.ptr = x.data_ptr()
+            self.shape = tuple(x.shape)
+            self.device = x.device.index
+            self.t = x
+        else:
+            if not isinstance(x, np.ndarray):
+                raise TypeError("%s must be a numpy array or a torch CUDA tensor" % name)
+            if not x.flags.c_contiguous:
+                raise ValueError("%s must be C-contiguous" % name)
+            if x.dtype.itemsize != itemsize:
+                raise TypeError("%s: expected %d-byte words" % (name, itemsize))
+            self.ptr = x.ctypes.data
+            self.shape = x.shape
+            self.device = None
+        self.words = int(np.prod(self.shape)) if len(self.shape) else 1
+
+
+class _PrimePlan:
+    _bits = None
+
+    def __init__(self, handle, n, p, device):
+        self._h, self._n, self._p, self._device = handle, n, p, device
+
+    @classmethod
+    def try_new(cls, polynomial_size, modulus, device=0):
+        """Plan::try_new -> Plan or None.  Raises ReferencePanic for modulus in {0, 1} (fastdiv.rs:49,99)."""
+        l = _lib.lib()
+        h = C.c_void_p()
+        st = getattr(l, "cntt_prime%d_plan_new" % cls._bits)(polynomial_size, modulus, device, C.byref(h))
+        if st in (_lib.INVALID_SIZE, _lib.INVALID_MODULUS, _lib.NO_ROOT):
+            return None
+        check(st, "try_new")
+        return cls(h, polynomial_size, modulus, device)
+
+    def __del__(self):
+        try:
+            if self._h:
+                getattr(_lib.lib(), "cntt_prime%d_plan_free" % self._bits)(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _fn(self, name):
+        return getattr(_lib.lib(), "cntt_prime%d_%s" % (self._bits, name))
+
+    def ntt_size(self):
+        return self._fn("ntt_size")(self._h)
+
+    def modulus(self):
+        return self._fn("modulus")(self._h)
+
+    def _ntt(self, name, buf):
+        b = _Buf(buf, self._bits // 8, "buf")
+        if len(b.shape) == 0 or b.shape[-1] != self._n:
+            raise ReferencePanic("assert_eq!(buf.len(), self.ntt_size())")
+        batch = b.words // self._n
+        if b.is_dev:
+            check(self._fn(name)(self._h, b.ptr, batch, _stream_of(b.t)), name)
+        else:
+            check(self._fn(name + "_host")(self._h, b.ptr, b.words, batch), name)
+        return buf
+
+    def fwd(self, buf):
+        """Plan::fwd: in place, natural order in, bit-reversed order out."""
+        return self._ntt("fwd", buf)
+
+    def inv(self, buf):
+        """Plan::inv: in place, bit-reversed in, natural out, not normalised (inv(fwd(x)) = n x)."""
+        return self._ntt("inv", buf)
+
+    def fwd_inv(self, buf):
+        """fwd then inv with one upload/download (host slices) -- the round trip of BASELINE config 1/2."""
+        b = _Buf(buf, self._bits // 8, "buf")
+        if len(b.shape) == 0 or b.shape[-1] != self._n:
+            raise ReferencePanic("assert_eq!(buf.len(), self.ntt_size())")
+        batch = b.words // self._n
+        if b.is_dev:
+            check(self._fn("fwd")(self._h, b.ptr, batch, _stream_of(b.t)), "fwd")
+            check(self._fn("inv")(self._h, b.ptr, batch, _stream_of(b.t)), "inv")
+        else:
+            check(self._fn("fwd_inv_host")(self._h, b.ptr, b.words, batch), "fwd_inv")
+        return buf
+
+    def _pw(self, name, *arrs):
+        bufs = [_Buf(a, self._bits // 8, "arg%d" % i) for i, a in enumerate(arrs)]
+        # izip! truncates to the shortest slice (prime32.rs:397); whole vectors only (prime32.rs:348)
+        nwords = min(b.words for b in bufs)
+        dev = bufs[0].is_dev
+        if any(b.is_dev != dev for b in bufs):
+            raise TypeError("all arguments must be on the same side (all device or all host)")
+        ptrs = [b.ptr for b in bufs]
+        if dev:
+            check(self._fn(name)(self._h, *ptrs, nwords, _stream_of(bufs[0].t)), name)
+        else:
+            check(self._fn(name + "_host")(self._h, *ptrs, nwords), name)
+        return arrs[0]
+
+    def mul_assign_normalize(self, lhs, rhs):
+        """lhs[i] = lhs[i] * rhs[i] * n^-1 mod p."""
+        return self._pw("mul_assign_normalize", lhs, rhs)
+
+    def normalize(self, values):
+        """values[i] = values[i] * n^-1 mod p."""
+        return self._pw("normalize", values)
+
+    def mul_accumulate(self, acc, lhs, rhs):
+        """acc[i] = acc[i] + lhs[i] * rhs[i] mod p."""
+        return self._pw("mul_accumulate", acc, lhs, rhs)
+
+
+class Plan32Prime(_PrimePlan):
+    """prime32::Plan"""
+    _bits = 32
+
+
+class Plan64Prime(_PrimePlan):
+    """prime64::Plan"""
+    _bits = 64
+
+
+class _NativePlan:
+    """native{32,64,128}::Plan32 / native_binary{32,64,128}::Plan32.
+
+    Words: 32/64-bit -> arrays of 4/8-byte items, last dim n.  128-bit -> 8-byte items with trailing
+    dims (n, 2) = little-endian {lo, hi}.  Residue planes: uint32, shape (num_primes, batch..., n).
+    """
+    _bits = None
+    _binary = False
+
+    def __init__(self, handle, n, device):
+        self._h, self._n, self._device = handle, n, device
+        self._np = _lib.lib().cntt_native_num_primes(handle)
+
+    @classmethod
+    def try_new(cls, n, device=0):
+        l = _lib.lib()
+        h = C.c_void_p()
+        st = l.cntt_native_plan_new(n, cls._bits, int(cls._binary), device, C.byref(h))
+        if st in (_lib.INVALID_SIZE, _lib.INVALID_MODULUS, _lib.NO_ROOT):
+            return None
+        check(st, "try_new")
+        return cls(h, n, device)
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib().cntt_native_plan_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def ntt_size(self):
+        return _lib.lib().cntt_native_ntt_size(self._h)
+
+    def num_primes(self):
+        return self._np
+
+    def ntt_modulus(self, i):
+        """modulus of Plan32::ntt_i()"""
+        return _lib.lib().cntt_native_prime(self._h, i)
+
+    def _word_buf(self, x, name):
+        b = _Buf(x, 8 if self._bits == 128 else self._bits // 8, name)
+        tail = (self._n, 2) if self._bits == 128 else (self._n,)
+        if b.shape[len(b.shape) - len(tail):] != tail:
+            raise ReferencePanic("assert_eq!(n, %s.len())" % name)
+        b.batch = b.words // int(np.prod(tail))
+        return b
+
+    def _planes(self, x, batch):
+        b = _Buf(x, 4, "mod_p")
+        if b.words != self._np * batch * self._n:
+            raise ReferencePanic("residue planes must hold num_primes * batch * n words")
+        return b
+
+    def _fwd(self, fn, value, mod_p):
+        v = self._word_buf(value, "value")
+        m = self._planes(mod_p, v.batch)
+        if not (v.is_dev and m.is_dev):
+            raise TypeError("fwd/inv operate on device-resident tensors; use negacyclic_polymul for host slices")
+        check(fn(self._h, v.ptr, m.ptr, v.batch, _stream_of(v.t)))
+        return mod_p
+
+    def fwd(self, value, mod_p):
+        """Plan32::fwd(value, mod_p0, ...): residues of `value` mod each prime, forward-transformed."""
+        return self._fwd(_lib.lib().cntt_native_fwd, value, mod_p)
+
+    def fwd_binary(self, value, mod_p):
+        """Plan32::fwd_binary (binary plans): `value as u32` without reduction, forward-transformed."""
+        if not self._binary:
+            raise AttributeError("fwd_binary exists only on native_binary* plans")
+        return self._fwd(_lib.lib().cntt_native_fwd_binary, value, mod_p)
+
+    def inv(self, value, mod_p):
+        """Plan32::inv(value, mod_p0, ...): inverse transforms (clobbering mod_p) + Garner lift."""
+        return self._fwd(_lib.lib().cntt_native_inv, value, mod_p)
+
+    def negacyclic_polymul(self, prod, lhs, rhs):
+        """Plan32::negacyclic_polymul(prod, lhs, rhs)."""
+        p = self._word_buf(prod, "prod")
+        l = self._word_buf(lhs, "lhs")
+        r = self._word_buf(rhs, "rhs")
+        if not (p.batch == l.batch == r.batch):
+            raise ReferencePanic("assert_eq!(n, lhs.len())")
+        if p.is_dev != l.is_dev or p.is_dev != r.is_dev:
+            raise TypeError("all arguments must be on the same side (all device or all host)")
+        if p.is_dev:
+            check(_lib.lib().cntt_native_polymul(self._h, p.ptr, l.ptr, r.ptr, p.batch, _stream_of(p.t)))
+        else:
+            check(_lib.lib().cntt_native_polymul_host(self._h, p.ptr, l.ptr, r.ptr, p.batch * self._n, p.batch))
+        return prod

@@ -1,0 +1,143 @@
+/*
+ * cntt_b200.h -- C ABI of libcntt_b200.so: a B200 (sm_100a) batched negacyclic NTT library that is a
+ * drop-in for the hot path of zama-ai/concrete-ntt v0.2.0.
+ *
+ * Every entry point replaces one public method of the reference crate; the citation next to it is the
+ * reference definition (paths relative to the crate root).  The reference API is "one polynomial per
+ * call on a host slice"; this ABI adds an explicit batch count and comes in two flavours:
+ *
+ *   cntt_<plan>_<op>(plan, device pointers..., batch, stream)        device-resident batches, async
+ *   cntt_<plan>_<op>_host(plan, host pointers..., batch)            host slices, staged H2D/D2H inside
+ *
+ * Layout: polynomial-major contiguous -- element i of polynomial b is buf[b*n + i] (the reference's
+ * slices concatenated).  Residue planes of the native plans: plane k of polynomial b is
+ * mod_p[(k*batch + b)*n + i] (k-th `mod_pk` slice of the reference, concatenated over the batch).
+ * 128-bit words are little-endian {lo:u64, hi:u64} pairs, 16-byte aligned (Rust u128 on x86-64).
+ *
+ * Results are bit-identical to the reference on the same inputs (same primitive root, same
+ * bit-reversed order, canonical residues, same centred CRT lift).
+ *
+ * All functions return a cntt_status.  Plans are immutable after creation and may be used from
+ * several host threads on distinct streams/buffers (the reference's Plan is Send + Sync).
+ * There is no CPU fallback: without a CUDA device every compute call returns CNTT_CUDA_ERROR.
+ */
+#ifndef CNTT_B200_H
+#define CNTT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum cntt_status {
+    CNTT_OK = 0,
+    CNTT_INVALID_SIZE = 1,    /* try_new -> None: n too small / not a power of two (prime32.rs:635, prime64.rs:709) */
+    CNTT_INVALID_MODULUS = 2, /* try_new -> None: p not prime.  p in {0,1}: the reference panics (fastdiv.rs:49,99); see cntt_status_is_panic */
+    CNTT_NO_ROOT = 3,         /* try_new -> None: no primitive 2n-th root of unity mod p */
+    CNTT_LENGTH_MISMATCH = 4, /* the reference's assert_eq!(buf.len(), n) */
+    CNTT_CUDA_ERROR = 5,
+    CNTT_NULL_POINTER = 6,
+    CNTT_UNSUPPORTED = 7,
+    CNTT_PANIC_MODULUS = 8    /* p in {0,1}: the reference panics before validating */
+} cntt_status;
+
+const char* cntt_status_string(int status);
+/* text of the last CUDA error seen by the calling thread ("" if none) */
+const char* cntt_last_cuda_error(void);
+/* library / build identification, e.g. "cntt_b200 0.1 sm_100a" */
+const char* cntt_version(void);
+
+/* ---- plan-time helpers (host only) ------------------------------------------------------------- */
+/* prime::is_prime64                                   src/prime.rs:76-126  */
+int cntt_is_prime64(uint64_t n);
+/* prime::largest_prime_in_arithmetic_progression64    src/prime.rs:130-180 ; returns 1 and *out on Some */
+int cntt_largest_prime_in_arithmetic_progression64(uint64_t factor, uint64_t offset, uint64_t lo, uint64_t hi, uint64_t* out);
+/* roots::find_primitive_root64                        src/roots.rs:68-91   ; returns 1 and *root on Some */
+int cntt_find_primitive_root64(uint64_t p, uint64_t degree, uint64_t* root);
+
+/* pinned host memory for the *_host entry points (optional; any host pointer works) */
+int cntt_host_alloc(void** ptr, size_t bytes);
+int cntt_host_free(void* ptr);
+
+/* ---- prime32::Plan                                  src/prime32.rs:602-928 ------------------------ */
+typedef struct cntt_prime32_plan cntt_prime32_plan;
+/* Plan::try_new(polynomial_size, modulus)             src/prime32.rs:630-686 ; device = CUDA ordinal */
+int cntt_prime32_plan_new(size_t n, uint32_t p, int device, cntt_prime32_plan** out);
+void cntt_prime32_plan_free(cntt_prime32_plan* plan);
+/* Plan::ntt_size / Plan::modulus                      src/prime32.rs:694-703 */
+size_t cntt_prime32_ntt_size(const cntt_prime32_plan* plan);
+uint32_t cntt_prime32_modulus(const cntt_prime32_plan* plan);
+/* Plan::fwd / Plan::inv (in place)                    src/prime32.rs:709-755, 762-808 */
+int cntt_prime32_fwd(const cntt_prime32_plan* plan, uint32_t* d_buf, size_t batch, void* stream);
+int cntt_prime32_inv(const cntt_prime32_plan* plan, uint32_t* d_buf, size_t batch, void* stream);
+/* Plan::mul_assign_normalize(lhs, rhs)                src/prime32.rs:812-864 ; nwords = words in each stream */
+int cntt_prime32_mul_assign_normalize(const cntt_prime32_plan* plan, uint32_t* d_lhs, const uint32_t* d_rhs, size_t nwords, void* stream);
+/* Plan::normalize(values)                             src/prime32.rs:868-902 */
+int cntt_prime32_normalize(const cntt_prime32_plan* plan, uint32_t* d_values, size_t nwords, void* stream);
+/* Plan::mul_accumulate(acc, lhs, rhs)                 src/prime32.rs:905-927 */
+int cntt_prime32_mul_accumulate(const cntt_prime32_plan* plan, uint32_t* d_acc, const uint32_t* d_lhs, const uint32_t* d_rhs, size_t nwords, void* stream);
+/* host-slice flavours: len = number of words in h_buf; must equal n*batch (CNTT_LENGTH_MISMATCH otherwise) */
+int cntt_prime32_fwd_host(const cntt_prime32_plan* plan, uint32_t* h_buf, size_t len, size_t batch);
+int cntt_prime32_inv_host(const cntt_prime32_plan* plan, uint32_t* h_buf, size_t len, size_t batch);
+/* fwd followed by inv on the device between one upload and one download (round trip = N * x) */
+int cntt_prime32_fwd_inv_host(const cntt_prime32_plan* plan, uint32_t* h_buf, size_t len, size_t batch);
+int cntt_prime32_mul_assign_normalize_host(const cntt_prime32_plan* plan, uint32_t* h_lhs, const uint32_t* h_rhs, size_t nwords);
+int cntt_prime32_normalize_host(const cntt_prime32_plan* plan, uint32_t* h_values, size_t nwords);
+int cntt_prime32_mul_accumulate_host(const cntt_prime32_plan* plan, uint32_t* h_acc, const uint32_t* h_lhs, const uint32_t* h_rhs, size_t nwords);
+
+/* ---- prime64::Plan                                  src/prime64.rs:222-1129 ----------------------- */
+typedef struct cntt_prime64_plan cntt_prime64_plan;
+/* prime64::Solinas::P = 2^64 - 2^32 + 1               src/prime64/generic_solinas.rs:36-40 */
+#define CNTT_SOLINAS_P 0xFFFFFFFF00000001ull
+/* Plan::try_new                                       src/prime64.rs:704-771 */
+int cntt_prime64_plan_new(size_t n, uint64_t p, int device, cntt_prime64_plan** out);
+void cntt_prime64_plan_free(cntt_prime64_plan* plan);
+size_t cntt_prime64_ntt_size(const cntt_prime64_plan* plan);                 /* src/prime64.rs:779-781 */
+uint64_t cntt_prime64_modulus(const cntt_prime64_plan* plan);                /* src/prime64.rs:785-787 */
+int cntt_prime64_fwd(const cntt_prime64_plan* plan, uint64_t* d_buf, size_t batch, void* stream);   /* src/prime64.rs:794-865 */
+int cntt_prime64_inv(const cntt_prime64_plan* plan, uint64_t* d_buf, size_t batch, void* stream);   /* src/prime64.rs:872-943 */
+int cntt_prime64_mul_assign_normalize(const cntt_prime64_plan* plan, uint64_t* d_lhs, const uint64_t* d_rhs, size_t nwords, void* stream); /* src/prime64.rs:947-1032 */
+int cntt_prime64_normalize(const cntt_prime64_plan* plan, uint64_t* d_values, size_t nwords, void* stream);                                 /* src/prime64.rs:1036-1082 */
+int cntt_prime64_mul_accumulate(const cntt_prime64_plan* plan, uint64_t* d_acc, const uint64_t* d_lhs, const uint64_t* d_rhs, size_t nwords, void* stream); /* src/prime64.rs:1085-1128 */
+int cntt_prime64_fwd_host(const cntt_prime64_plan* plan, uint64_t* h_buf, size_t len, size_t batch);
+int cntt_prime64_inv_host(const cntt_prime64_plan* plan, uint64_t* h_buf, size_t len, size_t batch);
+int cntt_prime64_fwd_inv_host(const cntt_prime64_plan* plan, uint64_t* h_buf, size_t len, size_t batch);
+int cntt_prime64_mul_assign_normalize_host(const cntt_prime64_plan* plan, uint64_t* h_lhs, const uint64_t* h_rhs, size_t nwords);
+int cntt_prime64_normalize_host(const cntt_prime64_plan* plan, uint64_t* h_values, size_t nwords);
+int cntt_prime64_mul_accumulate_host(const cntt_prime64_plan* plan, uint64_t* h_acc, const uint64_t* h_lhs, const uint64_t* h_rhs, size_t nwords);
+
+/* ---- native{32,64,128}::Plan32 and native_binary{32,64,128}::Plan32 --------------------------------
+ * One handle type; `word_bits` in {32,64,128} and `binary` in {0,1} select the reference plan:
+ *   native32::Plan32        (P0..P2)  src/native32.rs:8-12,335-433
+ *   native64::Plan32        (P0..P4)  src/native64.rs:16-22,930-1070
+ *   native128::Plan32       (P0..P9)  src/native128.rs:6-17,120-349
+ *   native_binary32::Plan32 (P0..P1)  src/native_binary32.rs:11,187-263
+ *   native_binary64::Plan32 (P0..P2)  src/native_binary64.rs:17-21,342-445
+ *   native_binary128::Plan32(P0..P4)  src/native_binary128.rs:4-10,66-196
+ * Words are passed as void*: uint32_t / uint64_t / 16-byte {lo,hi} according to word_bits.
+ */
+typedef struct cntt_native_plan cntt_native_plan;
+/* Plan32::try_new(n)  -- CNTT_NO_ROOT when n > 32768 (P1 - 1 = 2^16 * odd, src/lib.rs:454) */
+int cntt_native_plan_new(size_t n, int word_bits, int binary, int device, cntt_native_plan** out);
+void cntt_native_plan_free(cntt_native_plan* plan);
+size_t cntt_native_ntt_size(const cntt_native_plan* plan);
+int cntt_native_num_primes(const cntt_native_plan* plan);
+/* Plan32::ntt_i(): modulus of the i-th prime32 sub-plan (src/native64.rs:950-969) */
+uint32_t cntt_native_prime(const cntt_native_plan* plan, int i);
+/* Plan32::fwd(value, mod_p0..)        value: batch*n words in, mod_p: num_primes planes out */
+int cntt_native_fwd(const cntt_native_plan* plan, const void* d_value, uint32_t* d_mod_p, size_t batch, void* stream);
+/* Plan32::fwd_binary(value, mod_p0..) binary plans only; CNTT_UNSUPPORTED otherwise */
+int cntt_native_fwd_binary(const cntt_native_plan* plan, const void* d_value, uint32_t* d_mod_p, size_t batch, void* stream);
+/* Plan32::inv(value, mod_p0..)        mod_p planes are clobbered, like in the reference */
+int cntt_native_inv(const cntt_native_plan* plan, void* d_value, uint32_t* d_mod_p, size_t batch, void* stream);
+/* Plan32::negacyclic_polymul(prod, lhs, rhs) */
+int cntt_native_polymul(const cntt_native_plan* plan, void* d_prod, const void* d_lhs, const void* d_rhs, size_t batch, void* stream);
+/* host-slice flavour: len = words in each of prod/lhs/rhs; must equal n*batch */
+int cntt_native_polymul_host(const cntt_native_plan* plan, void* h_prod, const void* h_lhs, const void* h_rhs, size_t len, size_t batch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNTT_B200_H */

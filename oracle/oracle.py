@@ -1,0 +1,329 @@
+"""ctypes binding of the CPU oracle (oracle/cntt_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  The product package (concrete-ntt_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_u32p = C.POINTER(C.c_uint32)
+_u64p = C.POINTER(C.c_uint64)
+
+
+def build(native=False):
+    """Compile the oracle if the shared object is missing (gcc is in the image)."""
+    name = "libcntt_oracle_native.so" if native else "libcntt_oracle.so"
+    path = os.path.join(_HERE, name)
+    src = os.path.join(_HERE, "cntt_oracle.c")
+    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "native" if native else "all"],
+                              stdout=subprocess.DEVNULL)
+    return path
+
+
+def _load(native=False):
+    lib = C.CDLL(build(native))
+    vp = C.c_void_p
+    sz = C.c_size_t
+    sig = {
+        "o_is_prime64": (C.c_int, [C.c_uint64]),
+        "o_largest_prime_in_arithmetic_progression64": (C.c_int, [C.c_uint64] * 4 + [_u64p]),
+        "o_find_primitive_root64": (C.c_int, [C.c_uint64, C.c_uint64, _u64p]),
+        "o_exp_mod64": (C.c_uint64, [C.c_uint64] * 3),
+        "o_mul_mod64": (C.c_uint64, [C.c_uint64] * 3),
+        "o_plan32_new": (C.c_int, [sz, C.c_uint32, C.POINTER(vp)]),
+        "o_plan32_free": (None, [vp]),
+        "o_plan32_psi": (C.c_uint32, [vp]),
+        "o_plan32_twid": (_u32p, [vp]),
+        "o_plan32_inv_twid": (_u32p, [vp]),
+        "o_plan32_fwd": (None, [vp, vp]),
+        "o_plan32_inv": (None, [vp, vp]),
+        "o_plan32_mul_assign_normalize": (None, [vp, vp, vp, sz]),
+        "o_plan32_normalize": (None, [vp, vp, sz]),
+        "o_plan32_mul_accumulate": (None, [vp, vp, vp, vp, sz]),
+        "o_plan64_new": (C.c_int, [sz, C.c_uint64, C.POINTER(vp)]),
+        "o_plan64_free": (None, [vp]),
+        "o_plan64_psi": (C.c_uint64, [vp]),
+        "o_plan64_twid": (_u64p, [vp]),
+        "o_plan64_inv_twid": (_u64p, [vp]),
+        "o_plan64_fwd": (None, [vp, vp]),
+        "o_plan64_inv": (None, [vp, vp]),
+        "o_plan64_mul_assign_normalize": (None, [vp, vp, vp, sz]),
+        "o_plan64_normalize": (None, [vp, vp, sz]),
+        "o_plan64_mul_accumulate": (None, [vp, vp, vp, vp, sz]),
+        "o_primes32": (C.c_uint32, [C.c_int]),
+        "o_reconstruct_32bit_01": (C.c_uint32, [C.c_uint32] * 2),
+        "o_reconstruct_32bit_012_u32": (C.c_uint32, [C.c_uint32] * 3),
+        "o_reconstruct_32bit_012_u64": (C.c_uint64, [C.c_uint32] * 3),
+        "o_reconstruct_32bit_01234_u64": (C.c_uint64, [C.c_uint32] * 5),
+        "o_reconstruct_32bit_01234_u128": (None, [C.c_uint32] * 5 + [_u64p]),
+        "o_reconstruct_32bit_0123456789_u128": (None, [_u32p, _u64p]),
+        "o_native_new": (C.c_int, [sz, C.c_int, C.c_int, C.POINTER(vp)]),
+        "o_native_free": (None, [vp]),
+        "o_native_nprimes": (C.c_int, [vp]),
+        "o_native_fwd": (None, [vp, vp, vp]),
+        "o_native_fwd_binary": (None, [vp, vp, vp]),
+        "o_native_inv": (None, [vp, vp, vp]),
+        "o_native_polymul": (None, [vp, vp, vp, vp]),
+        "o_schoolbook32": (None, [sz, C.c_uint32, vp, vp, vp]),
+        "o_schoolbook64": (None, [sz, C.c_uint64, vp, vp, vp]),
+        "o_schoolbook128": (None, [sz, vp, vp, vp]),
+        "o_direct_fwd64": (None, [sz, C.c_uint64, C.c_uint64, vp, vp]),
+        "o_max_threads": (C.c_int, []),
+        "o_plan32_fwd_batch": (None, [vp, vp, sz, C.c_int]),
+        "o_plan32_inv_batch": (None, [vp, vp, sz, C.c_int]),
+        "o_plan64_fwd_batch": (None, [vp, vp, sz, C.c_int]),
+        "o_plan64_inv_batch": (None, [vp, vp, sz, C.c_int]),
+        "o_native_polymul_batch": (None, [vp, vp, vp, vp, sz, C.c_int]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+_LIB = None
+
+
+def lib(native=False):
+    global _LIB
+    if native:
+        return _load(True)
+    if _LIB is None:
+        _LIB = _load(False)
+    return _LIB
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class ReferencePanic(Exception):
+    """The reference would panic (Div32::new / Div64::new assert, src/fastdiv.rs:49,99)."""
+
+
+def is_prime64(n):
+    return bool(lib().o_is_prime64(n))
+
+
+def largest_prime_in_arithmetic_progression64(factor, offset, lo, hi):
+    out = C.c_uint64()
+    ok = lib().o_largest_prime_in_arithmetic_progression64(factor, offset, lo, hi, C.byref(out))
+    return out.value if ok else None
+
+
+def find_primitive_root64(p, degree):
+    out = C.c_uint64()
+    ok = lib().o_find_primitive_root64(p, degree, C.byref(out))
+    return out.value if ok else None
+
+
+def exp_mod64(p, b, e):
+    return lib().o_exp_mod64(p, b, e)
+
+
+def primes32(i):
+    return lib().o_primes32(i)
+
+
+class _PrimePlan:
+    _pre = None
+    _dt = None
+
+    def __init__(self, handle, n, p, L):
+        self._h, self.n, self.p, self._L = handle, n, p, L
+
+    @classmethod
+    def try_new(cls, n, p, native=False):
+        L = lib(native)
+        h = C.c_void_p()
+        st = getattr(L, cls._pre + "_new")(n, p, C.byref(h))
+        if st == 2:
+            raise ReferencePanic("divisor > 1")
+        if st != 0:
+            return None
+        return cls(h, n, p, L)
+
+    def __del__(self):
+        try:
+            getattr(self._L, self._pre + "_free")(self._h)
+        except Exception:
+            pass
+
+    def ntt_size(self):
+        return self.n
+
+    def modulus(self):
+        return self.p
+
+    def psi(self):
+        return getattr(self._L, self._pre + "_psi")(self._h)
+
+    def twid(self):
+        ptr = getattr(self._L, self._pre + "_twid")(self._h)
+        return np.ctypeslib.as_array(ptr, shape=(self.n,)).copy()
+
+    def inv_twid(self):
+        ptr = getattr(self._L, self._pre + "_inv_twid")(self._h)
+        return np.ctypeslib.as_array(ptr, shape=(self.n,)).copy()
+
+    def _chk(self, *arrs):
+        for a in arrs:
+            assert a.dtype == self._dt and a.flags.c_contiguous
+
+    def _apply(self, name, buf):
+        """buf: (..., n) array transformed in place, one polynomial per row."""
+        self._chk(buf)
+        assert buf.shape[-1] == self.n, "assert_eq!(buf.len(), self.ntt_size())"
+        flat = buf.reshape(-1, self.n)
+        fn = getattr(self._L, self._pre + "_" + name)
+        for row in flat:
+            fn(self._h, _ptr(row))
+        return buf
+
+    def fwd(self, buf):
+        return self._apply("fwd", buf)
+
+    def inv(self, buf):
+        return self._apply("inv", buf)
+
+    def fwd_batch(self, buf, nthreads):
+        self._chk(buf)
+        getattr(self._L, self._pre + "_fwd_batch")(self._h, _ptr(buf), buf.size // self.n, nthreads)
+
+    def inv_batch(self, buf, nthreads):
+        self._chk(buf)
+        getattr(self._L, self._pre + "_inv_batch")(self._h, _ptr(buf), buf.size // self.n, nthreads)
+
+    def mul_assign_normalize(self, lhs, rhs):
+        self._chk(lhs, rhs)
+        getattr(self._L, self._pre + "_mul_assign_normalize")(self._h, _ptr(lhs), _ptr(rhs), min(lhs.size, rhs.size))
+        return lhs
+
+    def normalize(self, values):
+        self._chk(values)
+        getattr(self._L, self._pre + "_normalize")(self._h, _ptr(values), values.size)
+        return values
+
+    def mul_accumulate(self, acc, lhs, rhs):
+        self._chk(acc, lhs, rhs)
+        getattr(self._L, self._pre + "_mul_accumulate")(self._h, _ptr(acc), _ptr(lhs), _ptr(rhs),
+                                                       min(acc.size, lhs.size, rhs.size))
+        return acc
+
+
+class Plan32(_PrimePlan):
+    """prime32::Plan (src/prime32.rs:602-928)"""
+    _pre = "o_plan32"
+    _dt = np.dtype(np.uint32)
+
+
+class Plan64(_PrimePlan):
+    """prime64::Plan (src/prime64.rs:222-1129)"""
+    _pre = "o_plan64"
+    _dt = np.dtype(np.uint64)
+
+
+SOLINAS_P = 0xFFFFFFFF00000001
+
+
+class Native:
+    """native{32,64,128}::Plan32 / native_binary{32,64,128}::Plan32.
+
+    Words are numpy uint32 / uint64; 128-bit words are uint64 arrays of shape (..., n, 2), little-endian limbs.
+    Residue planes are a (nprimes, n) uint32 array.
+    """
+
+    def __init__(self, h, n, bits, binary, L):
+        self._h, self.n, self.bits, self.binary, self._L = h, n, bits, binary, L
+        self.nprimes = L.o_native_nprimes(h)
+
+    @classmethod
+    def try_new(cls, n, bits, binary=False, native=False):
+        L = lib(native)
+        h = C.c_void_p()
+        if L.o_native_new(n, bits, int(binary), C.byref(h)) != 0:
+            return None
+        return cls(h, n, bits, binary, L)
+
+    def __del__(self):
+        try:
+            self._L.o_native_free(self._h)
+        except Exception:
+            pass
+
+    def word_dtype(self):
+        return np.uint32 if self.bits == 32 else np.uint64
+
+    def word_shape(self, *lead):
+        return tuple(lead) + ((self.n,) if self.bits != 128 else (self.n, 2))
+
+    def fwd(self, value):
+        out = np.empty((self.nprimes, self.n), np.uint32)
+        self._L.o_native_fwd(self._h, _ptr(np.ascontiguousarray(value)), _ptr(out))
+        return out
+
+    def fwd_binary(self, value):
+        assert self.binary
+        out = np.empty((self.nprimes, self.n), np.uint32)
+        self._L.o_native_fwd_binary(self._h, _ptr(np.ascontiguousarray(value)), _ptr(out))
+        return out
+
+    def inv(self, mod_p):
+        """Returns value; mod_p is clobbered like in the reference."""
+        assert mod_p.dtype == np.uint32 and mod_p.shape == (self.nprimes, self.n) and mod_p.flags.c_contiguous
+        out = np.empty(self.word_shape(), self.word_dtype())
+        self._L.o_native_inv(self._h, _ptr(out), _ptr(mod_p))
+        return out
+
+    def negacyclic_polymul(self, lhs, rhs):
+        lhs = np.ascontiguousarray(lhs)
+        rhs = np.ascontiguousarray(rhs)
+        assert lhs.shape == rhs.shape
+        out = np.empty_like(lhs)
+        per = self.word_shape()
+        lead = lhs.shape[: lhs.ndim - len(per)]
+        assert lhs.shape[len(lead):] == per, "assert_eq!(n, lhs.len())"
+        l2 = lhs.reshape((-1,) + per)
+        r2 = rhs.reshape((-1,) + per)
+        o2 = out.reshape((-1,) + per)
+        for i in range(l2.shape[0]):
+            self._L.o_native_polymul(self._h, _ptr(o2[i]), _ptr(l2[i]), _ptr(r2[i]))
+        return out
+
+    def polymul_batch(self, prod, lhs, rhs, batch, nthreads):
+        self._L.o_native_polymul_batch(self._h, _ptr(prod), _ptr(lhs), _ptr(rhs), batch, nthreads)
+
+
+def schoolbook32(p, lhs, rhs):
+    out = np.empty_like(lhs)
+    lib().o_schoolbook32(lhs.size, p, _ptr(lhs), _ptr(rhs), _ptr(out))
+    return out
+
+
+def schoolbook64(p, lhs, rhs):
+    out = np.empty_like(lhs)
+    lib().o_schoolbook64(lhs.size, p, _ptr(lhs), _ptr(rhs), _ptr(out))
+    return out
+
+
+def schoolbook128(lhs, rhs):
+    out = np.empty_like(lhs)
+    lib().o_schoolbook128(lhs.shape[0], _ptr(lhs), _ptr(rhs), _ptr(out))
+    return out
+
+
+def direct_fwd64(n, p, psi, a):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    out = np.empty(n, np.uint64)
+    lib().o_direct_fwd64(n, p, psi, _ptr(a), _ptr(out))
+    return out
+
+
+def max_threads():
+    return lib().o_max_threads()
