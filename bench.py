@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 batched-NTT library (contract: see DESIGN.md "Measurement").
+
+  python bench.py --gpus N --steps K --warmup W            our arm  (torchrun for N > 1, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU algorithm on the host cores
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): prime64::Plan, N = 2048,
+p = Solinas 2^64 - 2^32 + 1, batch 65536 per GPU, one step = fwd pass + inv pass over the whole batch
+(2 * 65536 NTTs per GPU).  Batches are independent, so N GPUs each transform their own 65536 polynomials
+(weak scaling, no collective on the data path).  `value` = NTTs/s with inputs resident in HBM;
+`e2e` = the same job through the host-slice C-ABI call (pinned host buffer -> H2D -> fwd -> inv -> D2H).
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+N_POLY = 2048
+BATCH = 65536
+SOLINAS_P = 0xFFFFFFFF00000001
+WORKLOAD = "prime64 Plan N=2048 p=2^64-2^32+1 (Solinas) batch 65536 per GPU, fwd+inv"
+# algorithmic HBM bytes of one NTT launch over the batch: every word read once and written once
+ALG_BYTES_PER_NTT = 2 * N_POLY * 8
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_ntt_cta<A64S,11> launch over the batch, from the
+# ncu --set full capture under profiles/ (None until captured)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = None
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], None, set(), []
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                smax = float(f[2])
+                if t0 - 0.05 <= ts <= t1 + 0.15:
+                    sm.append(float(f[1]))
+                    power.append(float(f[3]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                continue
+        if not sm:  # region shorter than the sampling period: use every sample we have
+            for ts, line in self.lines:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1]))
+                except Exception:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "power_w_max": max(power) if power else None, "samples": len(sm)}
+
+
+def make_inputs(rank, batch, n, p):
+    g = np.random.Generator(np.random.PCG64(0xC0FFEE + 2 + 1000 * rank))
+    a = g.integers(0, 2**64, size=(batch, n), dtype=np.uint64)
+    a[a >= np.uint64(p)] -= np.uint64(p)       # uniform-enough in [0, p): values >= p (prob 2^-32) folded once
+    return a
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own CPU algorithm for the path (oracle port: no Rust toolchain exists to build the crate),
+    all host threads, bounded sample of the same workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    try:
+        O.build(native=True)
+        native = True
+    except Exception:
+        native = False
+    threads = O.lib(native).o_max_threads()
+    plan = O.Plan64.try_new(N_POLY, SOLINAS_P, native=native)
+    sample = 4096
+    buf = make_inputs(0, sample, N_POLY, SOLINAS_P)
+    for _ in range(max(1, args.warmup)):
+        plan.fwd_batch(buf, threads)
+        plan.inv_batch(buf, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        plan.fwd_batch(buf, threads)
+        plan.inv_batch(buf, threads)
+    dt = time.perf_counter() - t0
+    value = 2.0 * sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "NTTs/sec", "value": value, "unit": "NTT/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n": N_POLY, "batch_per_step": sample, "prime": "0xFFFFFFFF00000001"},
+        "cpu_baseline": {"value": value, "unit": "NTT/s", "cores": threads, "kind": "port",
+                         "sample": "%d polynomials of the workload per step (fwd+inv), C restatement of concrete-ntt's scalar "
+                                   "Solinas path (oracle/cntt_oracle.c, gcc -O3 -march=%s, OpenMP over polynomials)"
+                                   % (sample, "native" if native else "x86-64-v3")},
+        "e2e": {"value": value, "unit": "NTT/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg():
+    """Bounded sample of the workload on the host cores (rank 0, N=1 only): ~10-20 core-seconds."""
+    from oracle import oracle as O
+    try:
+        O.build(native=True)
+        native = True
+    except Exception:
+        native = False
+    threads = O.lib(native).o_max_threads()
+    plan = O.Plan64.try_new(N_POLY, SOLINAS_P, native=native)
+    probe = make_inputs(7, 256, N_POLY, SOLINAS_P)
+    t0 = time.perf_counter()
+    plan.fwd_batch(probe, threads)
+    plan.inv_batch(probe, threads)
+    per_ntt_core_s = (time.perf_counter() - t0) * threads / 512.0
+    sample = int(min(BATCH, max(1024, 12.0 / max(per_ntt_core_s, 1e-9) / 2)))
+    buf = make_inputs(8, sample, N_POLY, SOLINAS_P)
+    t0 = time.perf_counter()
+    plan.fwd_batch(buf, threads)
+    plan.inv_batch(buf, threads)
+    dt = time.perf_counter() - t0
+    return {"value": 2.0 * sample / dt, "unit": "NTT/s", "cores": threads, "kind": "port",
+            "sample": "%d of the %d polynomials, fwd+inv once (%.1f core-s); C restatement of concrete-ntt's scalar Solinas "
+                      "path (oracle/cntt_oracle.c, gcc -O3 -march=%s, OpenMP over polynomials)"
+                      % (sample, BATCH, dt * threads, "native" if native else "x86-64-v3")}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cntt = importlib.import_module("concrete-ntt_b200")
+    plan = cntt.prime64.Plan.try_new(N_POLY, SOLINAS_P, device=local)
+    assert plan is not None
+
+    host = make_inputs(rank, BATCH, N_POLY, SOLINAS_P)
+    pinned = torch.empty((BATCH, N_POLY), dtype=torch.int64).pin_memory()
+    pinned.numpy().view(np.uint64)[...] = host
+    d = pinned.cuda(non_blocking=False)
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+    lib = cntt._lib.lib()
+    h = plan._h
+    dptr = d.data_ptr()
+
+    def step():
+        st = lib.cntt_prime64_fwd(h, dptr, BATCH, sptr)
+        st |= lib.cntt_prime64_inv(h, dptr, BATCH, sptr)
+        if st:
+            raise RuntimeError("kernel launch failed: " + lib.cntt_last_cuda_error().decode())
+        # keep values in [0, p): inv(fwd(x)) = N x is canonical already, so the next step is a valid input
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    barrier()
+    t_wall0 = time.time()
+    for i in range(K):
+        ev[i][0].record(stream)
+        st = lib.cntt_prime64_fwd(h, dptr, BATCH, sptr)
+        ev[i][1].record(stream)
+        st |= lib.cntt_prime64_inv(h, dptr, BATCH, sptr)
+        ev[i][2].record(stream)
+        if st:
+            raise RuntimeError("kernel launch failed: " + lib.cntt_last_cuda_error().decode())
+    barrier()
+    t_wall1 = time.time()
+    total_ms = ev[0][0].elapsed_time(ev[K - 1][2])
+    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    inv_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * 2.0 * BATCH * K / (total_ms * 1e-3)
+
+    # ---- end to end through the host-slice C-ABI call: pinned host -> H2D -> fwd -> inv -> D2H, every step
+    hview = pinned.numpy().view(np.uint64)
+    hview[...] = host
+    ke = max(2, min(K, 6))
+    plan.fwd_inv(hview)
+    hview[...] = host
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(ke):
+        plan.fwd_inv(hview)       # synchronous: returns after the D2H of the last chunk
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * 2.0 * BATCH * ke / e2e_s
+    nbytes = BATCH * N_POLY * 8
+
+    # ---- secondary figure of the same metric line: native64 polymul (BASELINE configs[2]), device-resident
+    extra = {}
+    try:
+        npl = cntt.native64.Plan32.try_new(N_POLY, device=local)
+        g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+        lhs = torch.randint(-2**63, 2**63 - 1, (BATCH, N_POLY), dtype=torch.int64, device="cuda", generator=g)
+        rhs = torch.randint(-2**63, 2**63 - 1, (BATCH, N_POLY), dtype=torch.int64, device="cuda", generator=g)
+        prod = torch.empty_like(lhs)
+        for _ in range(2):
+            npl.negacyclic_polymul(prod, lhs, rhs)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kp = 5
+        e0.record(stream)
+        for _ in range(kp):
+            npl.negacyclic_polymul(prod, lhs, rhs)
+        e1.record(stream)
+        barrier()
+        pm_ms = e0.elapsed_time(e1) / kp
+        if world > 1:
+            t = torch.tensor([pm_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pm_ms = float(t.item())
+        peak, _ = peaks()
+        extra["native64_polymul_n2048_b65536"] = {
+            "polymuls_per_s": world * BATCH / (pm_ms * 1e-3), "ms_per_batch": pm_ms,
+            "hbm_frac": (3 * N_POLY * 8 * BATCH / (pm_ms * 1e-3) / 1e9) / peak,
+            "butterflies_per_clk_per_sm": 168960.0 * BATCH / (pm_ms * 1e-3) / 148 / 1.965e9,
+        }
+        del lhs, rhs, prod
+    except Exception as e:  # never let the secondary figure kill the headline
+        extra["native64_polymul_error"] = repr(e)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        slow_ms, which = (fwd_ms, "fwd") if fwd_ms >= inv_ms else (inv_ms, "inv")
+        achieved = ALG_BYTES_PER_NTT * BATCH / (slow_ms * 1e-3) / 1e9
+        line = {
+            "metric": "NTTs/sec", "value": value, "unit": "NTT/s", "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n": N_POLY, "batch_per_gpu": BATCH, "prime": "0xFFFFFFFF00000001",
+                       "l2": "the 1 GiB batch per GPU is streamed every launch and exceeds the 126 MB L2 (no flush needed)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "NTT/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+                    "steps": ke, "api": "cntt_prime64_fwd_inv_host (pinned host slice, chunked double-buffered staging)"},
+            "gpu_launches": 2 * K,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "kernel": "k_ntt_cta<A64S,11,4> (%s)" % which,
+                         "peak_source": peak_src, "ms_per_launch": {"fwd": fwd_ms, "inv": inv_ms},
+                         "algorithmic_bytes_per_launch": ALG_BYTES_PER_NTT * BATCH,
+                         "note": "integer-issue bound kernel; see DESIGN.md for the integer roofline"},
+            "extra": extra,
+        }
+        if world == 1:
+            try:
+                line["cpu_baseline"] = cpu_baseline_leg()
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": "NTT/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

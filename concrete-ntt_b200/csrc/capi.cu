@@ -561,6 +561,16 @@ CNTT_API int cntt_native_plan_new(size_t n, int word_bits, int binary, int devic
     cntt_native_plan* pl = new cntt_native_plan();
     pl->n = n; pl->kind = kind; pl->device = device; pl->nprimes = native_num_primes(kind);
     for (int k = 0; k < 10; k++) pl->sub[k] = nullptr;
+    // decide Some/None on the host for every prime before touching the device
+    for (int k = 0; k < pl->nprimes; k++) {
+        uint64_t psi;
+        int lg;
+        int st = validate(n, c.P[k], 32, &psi, &lg);
+        if (st != CNTT_OK) {
+            delete pl;
+            return st;
+        }
+    }
     for (int k = 0; k < pl->nprimes; k++) {
         // Plan::try_new(n, P_k)? for every prime (src/native64.rs:933-942): first failure -> None
         int st = build_prime32(n, c.P[k], device, &pl->sub[k]);

@@ -1,8 +1,156 @@
-// native_fused.cuh -- fused negacyclic polymul (placeholder until the fused kernel lands below).
+// native_fused.cuh -- fused negacyclic polymul of the native / native_binary plans (N <= 4096).
+//
+// One thread group owns one polymul.  lhs and rhs are read from HBM exactly once into registers;
+// for every prime the group reduces both operands, runs the two forward NTTs together (shared
+// twiddle loads), multiplies pointwise (x N^-1), runs the inverse NTT, and parks the residue
+// polynomial in shared memory; after the last prime each thread lifts its own coefficients with the
+// Garner reconstruction and writes the product to HBM exactly once.  Residues never touch HBM
+// (the reference round-trips 2 x nprimes scratch vectors per call, src/native64.rs:1047-1068).
 #pragma once
+#include "native_device.cuh"
+
 namespace cntt {
-cudaError_t native_polymul_fused(const NativePlanDev&, void*, const void*, const void*, size_t, cudaStream_t)
+
+struct FusedParams {
+    const uint2* tw_fwd[10];
+    const uint2* tw_inv[10];
+    Mod32 mod[10];
+};
+
+template <int KIND, int LOGN, int LOGR>
+struct FusedCfg {
+    typedef Engine<A32L4, LOGN, LOGR> E;
+    static constexpr int NP = dev::KindInfo<KIND>::NP;
+    static constexpr int T = E::T;
+    static constexpr int GP = T >= 128 ? 1 : 128 / T;
+    static constexpr int XCHG_WORDS = 2 * E::NBUF * E::SMEM_WORDS;   // two polynomials in flight (lhs, rhs)
+    static constexpr int STASH_WORDS = NP * E::N;
+    static constexpr size_t SMEM_BYTES = (size_t)GP * (XCHG_WORDS + STASH_WORDS) * sizeof(uint32_t);
+};
+
+template <int KIND>
+__device__ __forceinline__ void load_word(const void* p, size_t i, uint64_t& lo, uint64_t& hi)
 {
-    return cudaErrorNotSupported;
+    typedef typename dev::KindInfo<KIND>::Word Word;
+    if constexpr (sizeof(Word) == 4) { lo = reinterpret_cast<const uint32_t*>(p)[i]; hi = 0; }
+    else if constexpr (sizeof(Word) == 8) { lo = reinterpret_cast<const uint64_t*>(p)[i]; hi = 0; }
+    else {
+        const uint4 q = reinterpret_cast<const uint4*>(p)[i];
+        lo = (uint64_t)q.x | ((uint64_t)q.y << 32);
+        hi = (uint64_t)q.z | ((uint64_t)q.w << 32);
+    }
 }
+
+template <int KIND, int LOGN, int LOGR>
+__global__ void __launch_bounds__(FusedCfg<KIND, LOGN, LOGR>::GP * FusedCfg<KIND, LOGN, LOGR>::T)
+k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ prod, const void* __restrict__ lhs,
+                const void* __restrict__ rhs, unsigned long long batch)
+{
+    typedef FusedCfg<KIND, LOGN, LOGR> Cfg;
+    typedef typename Cfg::E E;
+    typedef typename dev::KindInfo<KIND>::Word Word;
+    constexpr int T = Cfg::T, R = E::R, N = E::N, NP = Cfg::NP, GP = Cfg::GP;
+    constexpr bool BINARY = KIND >= NK_BINARY32;
+    constexpr int WB = (int)sizeof(Word);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* sm_all = reinterpret_cast<uint32_t*>(smem_raw);
+
+    const int grp = (GP == 1) ? 0 : (int)(threadIdx.x / T);
+    const int tid = (GP == 1) ? (int)threadIdx.x : (int)(threadIdx.x % T);
+    unsigned long long b = (unsigned long long)blockIdx.x * GP + grp;
+    const bool active = b < batch;
+    if (!active) b = batch - 1;
+    uint32_t* sm = sm_all + (size_t)grp * (Cfg::XCHG_WORDS + Cfg::STASH_WORDS);
+    uint32_t* stash = sm + Cfg::XCHG_WORDS;
+    const size_t base = (size_t)b * N;
+
+    // operands: read once, kept in registers for all primes
+    uint64_t llo[R], rlo[R];
+    uint64_t lhi[WB == 16 ? R : 1], rhi[WB == 16 ? R : 1];
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+        uint64_t h0, h1;
+        load_word<KIND>(lhs, base + tid + k * T, llo[k], h0);
+        load_word<KIND>(rhs, base + tid + k * T, rlo[k], h1);
+        if constexpr (WB == 16) { lhi[k] = h0; rhi[k] = h1; }
+    }
+
+#pragma unroll 1
+    for (int pk = 0; pk < NP; pk++) {
+        const Mod32 m = fp.mod[pk];
+        const uint32_t p = c.P[pk];
+        const uint64_t bar = c.barrett[pk];
+        uint32_t x[2][R];
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            if constexpr (WB == 16) {
+                x[0][k] = dev::mod_u128(llo[k], lhi[k], c, pk);
+                x[1][k] = BINARY ? (uint32_t)rlo[k] : dev::mod_u128(rlo[k], rhi[k], c, pk);
+            } else {
+                x[0][k] = dev::mod_u64(llo[k], p, bar);
+                x[1][k] = BINARY ? (uint32_t)rlo[k] : dev::mod_u64(rlo[k], p, bar);
+            }
+        }
+        E::template fwd<2>(x, sm, fp.tw_fwd[pk], 1u, tid, m);
+        uint32_t y[1][R];
+#pragma unroll
+        for (int k = 0; k < R; k++)
+            y[0][k] = A32L4::mul_norm(A32L4::canon_fwd(x[0][k], m), A32L4::canon_fwd(x[1][k], m), m);
+        if constexpr (E::NBUF == 1 && E::P >= 2) __syncthreads(); // single exchange buffer: fwd gather vs inv scatter
+        E::template inv<1>(y, sm, fp.tw_inv[pk], 1u, tid, m);
+#pragma unroll
+        for (int k = 0; k < R; k++) stash[pk * N + tid + k * T] = A32L4::canon_inv(y[0][k], m);
+        if constexpr (E::NBUF == 1 && E::P >= 2) __syncthreads(); // inv gather vs next prime's fwd scatter
+    }
+
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            uint32_t r[NP];
+#pragma unroll
+            for (int pk = 0; pk < NP; pk++) r[pk] = stash[pk * N + tid + k * T];
+            dev::store_word<KIND>(prod, base + tid + k * T, dev::reconstruct<KIND>(r, c));
+        }
+    }
+}
+
+template <int KIND, int LOGN>
+static cudaError_t launch_fused_one(const NativePlanDev& pl, void* prod, const void* lhs, const void* rhs, size_t batch, cudaStream_t st)
+{
+    constexpr int LOGR = LOGN < 3 ? LOGN : 3;
+    typedef FusedCfg<KIND, LOGN, LOGR> Cfg;
+    FusedParams fp;
+    for (int k = 0; k < Cfg::NP; k++) {
+        fp.tw_fwd[k] = pl.sub[k].tw_fwd;
+        fp.tw_inv[k] = pl.sub[k].tw_inv;
+        fp.mod[k] = pl.sub[k].mod;
+    }
+    auto kern = k_polymul_fused<KIND, LOGN, LOGR>;
+    if (Cfg::SMEM_BYTES > 227 * 1024) return cudaErrorNotSupported;
+    if (Cfg::SMEM_BYTES > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+    }
+    const unsigned long long nblk = (batch + Cfg::GP - 1) / Cfg::GP;
+    if (nblk > 0x7fffffffull) return cudaErrorInvalidValue;
+    kern<<<(unsigned)nblk, Cfg::GP * Cfg::T, Cfg::SMEM_BYTES, st>>>(native_consts(), fp, prod, lhs, rhs, batch);
+    return cudaGetLastError();
+}
+
+template <int KIND>
+static cudaError_t launch_fused_kind(const NativePlanDev& pl, void* prod, const void* lhs, const void* rhs, size_t batch, cudaStream_t st)
+{
+    switch (pl.logn) {
+    case 5: return launch_fused_one<KIND, 5>(pl, prod, lhs, rhs, batch, st);
+    case 6: return launch_fused_one<KIND, 6>(pl, prod, lhs, rhs, batch, st);
+    case 7: return launch_fused_one<KIND, 7>(pl, prod, lhs, rhs, batch, st);
+    case 8: return launch_fused_one<KIND, 8>(pl, prod, lhs, rhs, batch, st);
+    case 9: return launch_fused_one<KIND, 9>(pl, prod, lhs, rhs, batch, st);
+    case 10: return launch_fused_one<KIND, 10>(pl, prod, lhs, rhs, batch, st);
+    case 11: return launch_fused_one<KIND, 11>(pl, prod, lhs, rhs, batch, st);
+    case 12: return launch_fused_one<KIND, 12>(pl, prod, lhs, rhs, batch, st);
+    default: return cudaErrorNotSupported; // larger N: unfused two-level pipeline (capi.cu)
+    }
+}
+
 } // namespace cntt

@@ -182,3 +182,20 @@ cudaError_t native_crt(const NativePlanDev& pl, void* value, const uint32_t* pla
 } // namespace cntt
 
 #include "native_fused.cuh"
+
+namespace cntt {
+cudaError_t native_polymul_fused(const NativePlanDev& pl, void* prod, const void* lhs, const void* rhs, size_t batch,
+                                 cudaStream_t st)
+{
+    if (batch == 0) return cudaSuccess;
+    switch (pl.kind) {
+    case NK_NATIVE32: return launch_fused_kind<NK_NATIVE32>(pl, prod, lhs, rhs, batch, st);
+    case NK_NATIVE64: return launch_fused_kind<NK_NATIVE64>(pl, prod, lhs, rhs, batch, st);
+    case NK_NATIVE128: return launch_fused_kind<NK_NATIVE128>(pl, prod, lhs, rhs, batch, st);
+    case NK_BINARY32: return launch_fused_kind<NK_BINARY32>(pl, prod, lhs, rhs, batch, st);
+    case NK_BINARY64: return launch_fused_kind<NK_BINARY64>(pl, prod, lhs, rhs, batch, st);
+    case NK_BINARY128: return launch_fused_kind<NK_BINARY128>(pl, prod, lhs, rhs, batch, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+} // namespace cntt

@@ -794,64 +794,73 @@ static inline u64 solinas_mul(u64 a, u64 b)
 }
 static inline u64 gmul64(u64 p, int solinas, u64 a, u64 b) { return solinas ? solinas_mul(a, b) : mul_mod64(p, a, b); }
 
-/* generic drivers: src/prime64/generic_solinas.rs:449-562 (+ fwd_depth_first_scalar 1338-1388) */
-static void gfwd_breadth_first64(u64 *data, size_t n, u64 p, int sol, const u64 *twid, size_t depth, size_t half)
-{
-    size_t t = n / 2, m = 1, w_idx = (m << depth) + half * m;
-    while (m < n) {
-        const u64 *w = twid + w_idx;
-        for (size_t i = 0; i < m; i++) {
-            u64 *z0 = data + 2 * i * t, *z1 = z0 + t;
-            for (size_t j = 0; j < t; j++) {
-                u64 z1w = gmul64(p, sol, z1[j], w[i]);
-                u64 a = gadd64(p, z0[j], z1w), b = gsub64(p, z0[j], z1w);
-                z0[j] = a; z1[j] = b;
-            }
-        }
-        t /= 2; m *= 2; w_idx *= 2;
+/* generic drivers: src/prime64/generic_solinas.rs:449-562 (+ fwd_depth_first_scalar 1338-1388).
+ * The reference monomorphises them per PrimeModulus impl (u64 / Solinas); the macro below does the
+ * same so the Solinas multiply is inlined into the loops like in the Rust build. */
+#define DEFINE_GENERIC64(SUF, MUL)                                                                              \
+    static void gfwd_breadth_first64##SUF(u64 *data, size_t n, u64 p, const u64 *twid, size_t depth, size_t half) \
+    {                                                                                                           \
+        size_t t = n / 2, m = 1, w_idx = (m << depth) + half * m;                                               \
+        while (m < n) {                                                                                         \
+            const u64 *w = twid + w_idx;                                                                        \
+            for (size_t i = 0; i < m; i++) {                                                                    \
+                u64 *z0 = data + 2 * i * t, *z1 = z0 + t;                                                       \
+                const u64 w1 = w[i];                                                                            \
+                for (size_t j = 0; j < t; j++) {                                                                \
+                    u64 z1w = MUL(p, z1[j], w1);                                                                \
+                    u64 a = gadd64(p, z0[j], z1w), b = gsub64(p, z0[j], z1w);                                   \
+                    z0[j] = a; z1[j] = b;                                                                       \
+                }                                                                                               \
+            }                                                                                                   \
+            t /= 2; m *= 2; w_idx *= 2;                                                                         \
+        }                                                                                                       \
+    }                                                                                                           \
+    static void gfwd_depth_first64##SUF(u64 *data, size_t n, u64 p, const u64 *twid, size_t depth, size_t half) \
+    {                                                                                                           \
+        if (n <= RECURSION_THRESHOLD_64) { gfwd_breadth_first64##SUF(data, n, p, twid, depth, half); return; }   \
+        size_t t = n / 2;                                                                                       \
+        u64 w1 = twid[((size_t)1 << depth) + half];                                                             \
+        for (size_t j = 0; j < t; j++) {                                                                        \
+            u64 z1w = MUL(p, data[j + t], w1);                                                                  \
+            u64 a = gadd64(p, data[j], z1w), b = gsub64(p, data[j], z1w);                                       \
+            data[j] = a; data[j + t] = b;                                                                       \
+        }                                                                                                       \
+        gfwd_depth_first64##SUF(data, n / 2, p, twid, depth + 1, half * 2);                                     \
+        gfwd_depth_first64##SUF(data + n / 2, n / 2, p, twid, depth + 1, half * 2 + 1);                         \
+    }                                                                                                           \
+    static void ginv_breadth_first64##SUF(u64 *data, size_t n, u64 p, const u64 *inv_twid, size_t depth, size_t half) \
+    {                                                                                                           \
+        size_t t = 1, m = n, w_idx = (m << depth) + half * m;                                                   \
+        while (m > 1) {                                                                                         \
+            m /= 2; w_idx /= 2;                                                                                 \
+            const u64 *w = inv_twid + w_idx;                                                                    \
+            for (size_t i = 0; i < m; i++) {                                                                    \
+                u64 *z0 = data + 2 * i * t, *z1 = z0 + t;                                                       \
+                const u64 w1 = w[i];                                                                            \
+                for (size_t j = 0; j < t; j++) {                                                                \
+                    u64 a = gadd64(p, z0[j], z1[j]), b = MUL(p, gsub64(p, z0[j], z1[j]), w1);                   \
+                    z0[j] = a; z1[j] = b;                                                                       \
+                }                                                                                               \
+            }                                                                                                   \
+            t *= 2;                                                                                             \
+        }                                                                                                       \
+    }                                                                                                           \
+    static void ginv_depth_first64##SUF(u64 *data, size_t n, u64 p, const u64 *inv_twid, size_t depth, size_t half) \
+    {                                                                                                           \
+        if (n <= RECURSION_THRESHOLD_64) { ginv_breadth_first64##SUF(data, n, p, inv_twid, depth, half); return; } \
+        ginv_depth_first64##SUF(data, n / 2, p, inv_twid, depth + 1, half * 2);                                 \
+        ginv_depth_first64##SUF(data + n / 2, n / 2, p, inv_twid, depth + 1, half * 2 + 1);                     \
+        size_t t = n / 2;                                                                                       \
+        u64 w1 = inv_twid[((size_t)1 << depth) + half];                                                         \
+        for (size_t j = 0; j < t; j++) {                                                                        \
+            u64 a = gadd64(p, data[j], data[j + t]), b = MUL(p, gsub64(p, data[j], data[j + t]), w1);           \
+            data[j] = a; data[j + t] = b;                                                                       \
+        }                                                                                                       \
     }
-}
-static void gfwd_depth_first64(u64 *data, size_t n, u64 p, int sol, const u64 *twid, size_t depth, size_t half)
-{
-    if (n <= RECURSION_THRESHOLD_64) { gfwd_breadth_first64(data, n, p, sol, twid, depth, half); return; }
-    size_t t = n / 2;
-    u64 w1 = twid[((size_t)1 << depth) + half];
-    for (size_t j = 0; j < t; j++) {
-        u64 z1w = gmul64(p, sol, data[j + t], w1);
-        u64 a = gadd64(p, data[j], z1w), b = gsub64(p, data[j], z1w);
-        data[j] = a; data[j + t] = b;
-    }
-    gfwd_depth_first64(data, n / 2, p, sol, twid, depth + 1, half * 2);
-    gfwd_depth_first64(data + n / 2, n / 2, p, sol, twid, depth + 1, half * 2 + 1);
-}
-static void ginv_breadth_first64(u64 *data, size_t n, u64 p, int sol, const u64 *inv_twid, size_t depth, size_t half)
-{
-    size_t t = 1, m = n, w_idx = (m << depth) + half * m;
-    while (m > 1) {
-        m /= 2; w_idx /= 2;
-        const u64 *w = inv_twid + w_idx;
-        for (size_t i = 0; i < m; i++) {
-            u64 *z0 = data + 2 * i * t, *z1 = z0 + t;
-            for (size_t j = 0; j < t; j++) {
-                u64 a = gadd64(p, z0[j], z1[j]), b = gmul64(p, sol, gsub64(p, z0[j], z1[j]), w[i]);
-                z0[j] = a; z1[j] = b;
-            }
-        }
-        t *= 2;
-    }
-}
-static void ginv_depth_first64(u64 *data, size_t n, u64 p, int sol, const u64 *inv_twid, size_t depth, size_t half)
-{
-    if (n <= RECURSION_THRESHOLD_64) { ginv_breadth_first64(data, n, p, sol, inv_twid, depth, half); return; }
-    ginv_depth_first64(data, n / 2, p, sol, inv_twid, depth + 1, half * 2);
-    ginv_depth_first64(data + n / 2, n / 2, p, sol, inv_twid, depth + 1, half * 2 + 1);
-    size_t t = n / 2;
-    u64 w1 = inv_twid[((size_t)1 << depth) + half];
-    for (size_t j = 0; j < t; j++) {
-        u64 a = gadd64(p, data[j], data[j + t]), b = gmul64(p, sol, gsub64(p, data[j], data[j + t]), w1);
-        data[j] = a; data[j + t] = b;
-    }
-}
+#define MUL_GENERIC(p, a, b) mul_mod64((p), (a), (b))
+#define MUL_SOLINAS(p, a, b) solinas_mul((a), (b))
+DEFINE_GENERIC64(_u64, MUL_GENERIC)
+DEFINE_GENERIC64(_solinas, MUL_SOLINAS)
 
 /* Plan::fwd / inv dispatch (scalar, non-nightly arms): src/prime64.rs:794-865, 872-943 */
 EXPORT void o_plan64_fwd(const o_plan64 *pl, u64 *buf)
@@ -861,8 +870,10 @@ EXPORT void o_plan64_fwd(const o_plan64 *pl, u64 *buf)
         fwd_depth_first64(p, buf, pl->n, pl->twid, pl->twid_shoup, 0, 0, fwd_bf62, fwd_last_bf62);
     else if (p < ((u64)1 << 63))
         fwd_depth_first64(p, buf, pl->n, pl->twid, pl->twid_shoup, 0, 0, fwd_bf63, fwd_last_bf63);
+    else if (p == SOLINAS_P)
+        gfwd_depth_first64_solinas(buf, pl->n, p, pl->twid, 0, 0);
     else
-        gfwd_depth_first64(buf, pl->n, p, p == SOLINAS_P, pl->twid, 0, 0);
+        gfwd_depth_first64_u64(buf, pl->n, p, pl->twid, 0, 0);
 }
 EXPORT void o_plan64_inv(const o_plan64 *pl, u64 *buf)
 {
@@ -871,8 +882,10 @@ EXPORT void o_plan64_inv(const o_plan64 *pl, u64 *buf)
         inv_depth_first64(p, buf, pl->n, pl->inv_twid, pl->inv_twid_shoup, 0, 0, inv_bf62, inv_last_bf62);
     else if (p < ((u64)1 << 63))
         inv_depth_first64(p, buf, pl->n, pl->inv_twid, pl->inv_twid_shoup, 0, 0, inv_bf63, inv_bf63);
+    else if (p == SOLINAS_P)
+        ginv_depth_first64_solinas(buf, pl->n, p, pl->inv_twid, 0, 0);
     else
-        ginv_depth_first64(buf, pl->n, p, p == SOLINAS_P, pl->inv_twid, 0, 0);
+        ginv_depth_first64_u64(buf, pl->n, p, pl->inv_twid, 0, 0);
 }
 
 /* Pointwise: src/prime64.rs:534-584 (scalar Barrett+Shoup), 690-699 (normalize_scalar),

@@ -1,0 +1,158 @@
+"""GPU parity of the native / native_binary plans against the CPU oracle and the wrapping schoolbook."""
+import numpy as np
+import pytest
+
+from conftest import rng, rand_words
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(torch, a):
+    sd = np.int32 if a.dtype.itemsize == 4 else np.int64
+    return torch.from_numpy(a.view(sd).copy()).cuda()
+
+
+def host(t, dtype):
+    return t.cpu().numpy().view(dtype)
+
+
+def plan_pair(cntt, oracle, n, bits, binary):
+    mod = getattr(cntt, ("native_binary%d" if binary else "native%d") % bits)
+    return mod.Plan32.try_new(n), oracle.Native.try_new(n, bits, binary=binary)
+
+
+def make_rhs(g, bits, shape, binary):
+    r = rand_words(g, bits, shape)
+    if binary:
+        r = r & r.dtype.type(1)
+        if bits == 128:
+            r[..., 1] = 0
+    return r
+
+
+@pytest.mark.parametrize("binary", [False, True])
+@pytest.mark.parametrize("bits", [32, 64, 128])
+@pytest.mark.parametrize("n", [32, 64, 256, 1024, 2048, 4096])
+def test_polymul_matches_oracle(cntt, oracle, torch_cuda, n, bits, binary):
+    g = rng(n * 7 + bits + int(binary))
+    gp, op = plan_pair(cntt, oracle, n, bits, binary)
+    batch = 5
+    wdt = np.uint32 if bits == 32 else np.uint64
+    lhs = rand_words(g, bits, (batch, n))
+    rhs = make_rhs(g, bits, (batch, n), binary)
+    ref = op.negacyclic_polymul(lhs, rhs)
+    dl, dr = dev(torch_cuda, lhs), dev(torch_cuda, rhs)
+    dp = torch_cuda.empty_like(dl)
+    gp.negacyclic_polymul(dp, dl, dr)
+    assert (host(dp, wdt) == ref).all()
+    # host-slice flavour
+    hp = np.empty_like(lhs)
+    gp.negacyclic_polymul(hp, lhs, rhs)
+    assert (hp == ref).all()
+    if n <= 256:  # reference's own oracle: wrapping schoolbook (src/native64.rs:1196-1215)
+        sb = [oracle.schoolbook32(0, l, r) if bits == 32 else oracle.schoolbook64(0, l, r) if bits == 64
+              else oracle.schoolbook128(l, r) for l, r in zip(lhs, rhs)]
+        assert (np.stack(sb) == ref).all()
+
+
+@pytest.mark.parametrize("binary", [False, True])
+@pytest.mark.parametrize("bits", [32, 64, 128])
+def test_split_fwd_inv(cntt, oracle, torch_cuda, bits, binary):
+    """Plan32::fwd / fwd_binary / inv on device residue planes (src/native64.rs:971-1038)."""
+    n, batch = 512, 3
+    g = rng(bits + 100 * int(binary))
+    gp, op = plan_pair(cntt, oracle, n, bits, binary)
+    wdt = np.uint32 if bits == 32 else np.uint64
+    val = rand_words(g, bits, (batch, n))
+    npz = gp.num_primes()
+    assert npz == op.nprimes and [gp.ntt_modulus(i) for i in range(npz)] == [oracle.primes32(i) for i in range(npz)]
+    planes = torch_cuda.empty((npz, batch, n), dtype=torch_cuda.int32, device="cuda")
+    gp.fwd(dev(torch_cuda, val), planes)
+    ref_planes = np.stack([op.fwd(v) for v in val], axis=1)          # (np, batch, n)
+    assert (host(planes, np.uint32) == ref_planes).all()
+    if binary:
+        bval = make_rhs(g, bits, (batch, n), True)
+        gp.fwd_binary(dev(torch_cuda, bval), planes)
+        assert (host(planes, np.uint32) == np.stack([op.fwd_binary(v) for v in bval], axis=1)).all()
+        gp.fwd(dev(torch_cuda, val), planes)
+    out = dev(torch_cuda, np.zeros_like(val))
+    gp.inv(out, planes)
+    ref_out = np.stack([op.inv(np.ascontiguousarray(ref_planes[:, b])) for b in range(batch)])
+    assert (host(out, wdt) == ref_out).all()
+
+
+@pytest.mark.parametrize("bits", [32, 64, 128])
+def test_crt_on_arbitrary_residues(cntt, oracle, torch_cuda, bits):
+    """The Garner lift must match the reference formula on *arbitrary* residues, not only on polymul
+    outputs (sign rule v_last > P_last/2; src/native64.rs:1245-1293 pins this for SIMD vs scalar).
+    Feed inv() planes that are forward transforms of arbitrary residue vectors."""
+    n, batch = 64, 4
+    g = rng(bits + 5)
+    for binary in (False, True):
+        gp, op = plan_pair(cntt, oracle, n, bits, binary)
+        npz = op.nprimes
+        res = np.stack([g.integers(0, oracle.primes32(k), size=(batch, n), dtype=np.uint64).astype(np.uint32) for k in range(npz)])
+        # transform each residue vector forward with the per-prime oracle plan so that inv() returns them
+        fw = res.copy()
+        for k in range(npz):
+            pk = oracle.Plan32.try_new(n, oracle.primes32(k))
+            for b in range(batch):
+                pk.fwd(fw[k, b])
+        wdt = np.uint32 if bits == 32 else np.uint64
+        shape = (batch, n) if bits != 128 else (batch, n, 2)
+        out = dev(torch_cuda, np.zeros(shape, wdt))
+        gp.inv(out, dev(torch_cuda, fw))
+        ref = np.stack([op.inv(np.ascontiguousarray(fw[:, b])) for b in range(batch)])
+        assert (host(out, wdt) == ref).all(), (bits, binary)
+
+
+@pytest.mark.parametrize("n", [8192, 32768])
+def test_native_large_n(cntt, oracle, torch_cuda, n):
+    """Reference maximum is 32768 (P1 - 1 = 2^16 * odd); 65536 -> None like the reference."""
+    g = rng(n)
+    for bits, binary in [(64, False), (64, True), (32, False)]:
+        gp, op = plan_pair(cntt, oracle, n, bits, binary)
+        lhs = rand_words(g, bits, (2, n))
+        rhs = make_rhs(g, bits, (2, n), binary)
+        dl, dr = dev(torch_cuda, lhs), dev(torch_cuda, rhs)
+        dp = torch_cuda.empty_like(dl)
+        gp.negacyclic_polymul(dp, dl, dr)
+        assert (host(dp, np.uint32 if bits == 32 else np.uint64) == op.negacyclic_polymul(lhs, rhs)).all()
+    assert cntt.native64.Plan32.try_new(65536) is None
+    assert cntt.native_binary64.Plan32.try_new(65536) is None
+
+
+def test_polymul_errors(cntt, torch_cuda):
+    plan = cntt.native64.Plan32.try_new(64)
+    z = lambda k: torch_cuda.zeros(k, dtype=torch_cuda.int64, device="cuda")
+    with pytest.raises(cntt.ReferencePanic):
+        plan.negacyclic_polymul(z(64), z(63), z(64))          # src/native64.rs:1043-1045
+    with pytest.raises(AttributeError):
+        plan.fwd_binary(z(64), torch_cuda.zeros((5, 64), dtype=torch_cuda.int32, device="cuda"))
+    assert cntt.native64.Plan32.try_new(48) is None
+
+
+def test_full_size_config3_properties(cntt, oracle, torch_cuda):
+    """BASELINE config 3 at full size (native64 N=2048, batch 2^16): oracle on sampled polynomials,
+    plus x * 1 == x and bilinearity (a * (b + c) == a * b + a * c, wrapping) on the whole batch."""
+    torch = torch_cuda
+    n, batch = 2048, 1 << 16
+    g = rng(3)
+    plan = cntt.native64.Plan32.try_new(n)
+    op = oracle.Native.try_new(n, 64)
+    a = rand_words(g, 64, (batch, n))
+    b = rand_words(g, 64, (batch, n))
+    c = rand_words(g, 64, (batch, n))
+    da, db, dc = dev(torch, a), dev(torch, b), dev(torch, c)
+    ab, ac, abc = torch.empty_like(da), torch.empty_like(da), torch.empty_like(da)
+    plan.negacyclic_polymul(ab, da, db)
+    plan.negacyclic_polymul(ac, da, dc)
+    plan.negacyclic_polymul(abc, da, db + dc)       # int64 add wraps mod 2^64
+    assert torch.equal(abc, ab + ac)
+    hab = host(ab, np.uint64)
+    for r in g.integers(0, batch, 6):
+        assert (hab[r] == op.negacyclic_polymul(a[r], b[r])).all()
+    one = torch.zeros_like(da)
+    one[:, 0] = 1
+    plan.negacyclic_polymul(ab, da, one)
+    assert torch.equal(ab, da)
