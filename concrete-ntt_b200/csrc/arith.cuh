@@ -258,7 +258,14 @@ struct A64L2 : A64L4 {
 };
 
 // ---- p = 2^64 - 2^32 + 1 (Solinas / Goldilocks), prime64/generic_solinas.rs:77-129.
-//      Values are kept canonical; the multiply uses 2^64 = 2^32 - 1, 2^96 = -1 (mod p).
+//      2^64 = 2^32 - 1 =: EPS and 2^96 = -1 (mod p), so a 128-bit product (c3,c2,c1,c0) reduces to
+//      (c1:c0) - c3 + c2*EPS with two end-around corrections.  The kernels are integer-issue bound, so
+//      the arithmetic is written on 32-bit limbs with explicit carry chains (PTX add.cc/subc):
+//        mul     10 + 13 + 4 instructions (4 IMAD.WIDE.U32), result canonical
+//        add 6 / sub 5 instructions, valid when the second operand is <= p (any 64-bit first operand)
+//      (carry chains are never mixed: ptxas hands `subc` the raw carry predicate after an add.cc)
+//      Between forward stages values are arbitrary 64-bit representatives ("lazy"); only products are
+//      canonical.  Between inverse stages all values are canonical.
 struct A64S {
     typedef uint64_t W;
     typedef uint64_t Tw; // no Shoup companion
@@ -267,48 +274,119 @@ struct A64S {
     static constexpr uint64_t P = 0xFFFFFFFF00000001ull;
     static constexpr uint64_t EPS = 0x00000000FFFFFFFFull; // 2^64 - P
 
-    // (hi:lo) mod P, canonical
-    static __device__ __forceinline__ W reduce128(uint64_t lo, uint64_t hi)
+    static __device__ __forceinline__ uint64_t pack(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
+
+    // x >= p  ->  x - p   (x - p = (0 : x0 - 1) because x1 must be 0xFFFFFFFF)
+    static __device__ __forceinline__ W canon(W x)
     {
-        uint64_t hh = hi >> 32, hl = hi & EPS;
-        uint64_t t0 = lo - hh;
-        if (lo < hh) t0 -= EPS;            // borrow: +2^64 = +EPS too much
-        uint64_t t1 = (hl << 32) - hl;     // hl * (2^32 - 1)
-        uint64_t t2 = t0 + t1;
-        if (t2 < t1) t2 += EPS;            // carry: 2^64 = EPS
-        if (t2 >= P) t2 -= P;
-        return t2;
+        const uint32_t x0 = (uint32_t)x, x1 = (uint32_t)(x >> 32);
+        if (x1 == 0xFFFFFFFFu && x0 != 0u) x = (uint64_t)(x0 - 1u);
+        return x;
     }
-    static __device__ __forceinline__ W mul(W a, W b) { return reduce128(a * b, __umul64hi(a, b)); }
-    static __device__ __forceinline__ W add(W a, W b) // canonical in, canonical out
+    // (c3:c2:c1:c0) mod p as some 64-bit representative
+    static __device__ __forceinline__ W reduce128(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3)
     {
-        uint64_t s = a + b;
-        if (s < a || s >= P) s -= P;
-        return s;
+        uint32_t r0, r1;
+        asm("{\n\t"
+            ".reg .u32 m, tl, th;\n\t"
+            "sub.cc.u32   %0, %2, %5;\n\t"   // (c1:c0) - c3
+            "subc.cc.u32  %1, %3, 0;\n\t"
+            "subc.u32     m, 0, 0;\n\t"      // m = -borrow
+            "sub.cc.u32   %0, %0, m;\n\t"    // borrowed 2^64 = EPS too much: subtract EPS
+            "subc.u32     %1, %1, 0;\n\t"
+            "sub.cc.u32   tl, 0, %4;\n\t"    // c2 * EPS = (c2 << 32) - c2
+            "subc.u32     th, %4, 0;\n\t"
+            "add.cc.u32   %0, %0, tl;\n\t"
+            "addc.cc.u32  %1, %1, th;\n\t"
+            "addc.u32     m, 0, 0;\n\t"      // m = carry (never mix add.cc with subc: ptxas feeds subc the raw carry)
+            "sub.cc.u32   %0, %0, m;\n\t"    // dropped 2^64 = EPS = (m << 32) - m: add it back
+            "subc.u32     %1, %1, 0;\n\t"
+            "add.u32      %1, %1, m;\n\t"
+            "}"
+            : "=&r"(r0), "=&r"(r1)
+            : "r"(c0), "r"(c1), "r"(c2), "r"(c3));
+        return pack(r0, r1);
     }
-    static __device__ __forceinline__ W sub(W a, W b)
+    static __device__ __forceinline__ W mul(W a, W b) // any a, b; result canonical
     {
-        uint64_t d = a - b;
-        if (a < b) d += P;
-        return d;
+        // 128-bit product from four IMAD.WIDE.U32 without zero-extended addends: the two cross terms
+        // are summed with an explicit carry (their sum can exceed 64 bits).
+        uint32_t c0, c1, c2, c3;
+        asm("{\n\t"
+            ".reg .u64 m00, m01, m10, m11;\n\t"
+            ".reg .u32 h00, l01, h01, l10, h10, l11, h11, x0, x1, xc;\n\t"
+            "mul.wide.u32 m00, %4, %6;\n\t"
+            "mul.wide.u32 m01, %4, %7;\n\t"
+            "mul.wide.u32 m10, %5, %6;\n\t"
+            "mul.wide.u32 m11, %5, %7;\n\t"
+            "mov.b64 {%0, h00}, m00;\n\t"
+            "mov.b64 {l01, h01}, m01;\n\t"
+            "mov.b64 {l10, h10}, m10;\n\t"
+            "mov.b64 {l11, h11}, m11;\n\t"
+            "add.cc.u32  x0, l01, l10;\n\t"
+            "addc.cc.u32 x1, h01, h10;\n\t"
+            "addc.u32    xc, 0, 0;\n\t"
+            "add.cc.u32  %1, h00, x0;\n\t"
+            "addc.cc.u32 %2, l11, x1;\n\t"
+            "addc.u32    %3, h11, xc;\n\t"
+            "}"
+            : "=r"(c0), "=r"(c1), "=r"(c2), "=r"(c3)
+            : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)));
+        return canon(reduce128(c0, c1, c2, c3));
     }
+    // z + x, z - x for any 64-bit z and x <= p; result is some 64-bit representative.
+    // carry: z + x - 2^64 <= p - 1, so adding EPS cannot overflow again; borrow: z - x + 2^64 >= EPS.
+    static __device__ __forceinline__ W add_lazy(W z, W x)
+    {
+        uint32_t r0, r1;
+        asm("{\n\t"
+            ".reg .u32 m;\n\t"
+            "add.cc.u32   %0, %2, %4;\n\t"
+            "addc.cc.u32  %1, %3, %5;\n\t"
+            "addc.u32     m, 0, 0;\n\t"      // carry
+            "sub.cc.u32   %0, %0, m;\n\t"    // + EPS * carry = + (m << 32) - m
+            "subc.u32     %1, %1, 0;\n\t"
+            "add.u32      %1, %1, m;\n\t"
+            "}"
+            : "=&r"(r0), "=&r"(r1)
+            : "r"((uint32_t)z), "r"((uint32_t)(z >> 32)), "r"((uint32_t)x), "r"((uint32_t)(x >> 32)));
+        return pack(r0, r1);
+    }
+    static __device__ __forceinline__ W sub_lazy(W z, W x)
+    {
+        uint32_t r0, r1;
+        asm("{\n\t"
+            ".reg .u32 m;\n\t"
+            "sub.cc.u32   %0, %2, %4;\n\t"
+            "subc.cc.u32  %1, %3, %5;\n\t"
+            "subc.u32     m, 0, 0;\n\t"
+            "sub.cc.u32   %0, %0, m;\n\t"
+            "subc.u32     %1, %1, 0;\n\t"
+            "}"
+            : "=&r"(r0), "=&r"(r1)
+            : "r"((uint32_t)z), "r"((uint32_t)(z >> 32)), "r"((uint32_t)x), "r"((uint32_t)(x >> 32)));
+        return pack(r0, r1);
+    }
+    static __device__ __forceinline__ W add(W a, W b) { return canon(add_lazy(a, b)); } // canonical in/out
     static __device__ __forceinline__ void fwd_bf(W& z0, W& z1, Tw t, const Mod&)
     {
-        W x = mul(z1, t);
-        W a = add(z0, x), b = sub(z0, x);
+        const W x = mul(z1, t);
+        const W a = add_lazy(z0, x), b = sub_lazy(z0, x);
         z0 = a; z1 = b;
     }
-    static __device__ __forceinline__ void inv_bf(W& z0, W& z1, Tw t, const Mod&)
+    static __device__ __forceinline__ void inv_bf(W& z0, W& z1, Tw t, const Mod&) // canonical in/out
     {
-        W a = add(z0, z1), b = mul(sub(z0, z1), t);
-        z0 = a; z1 = b;
+        const W a = canon(add_lazy(z0, z1));
+        const W d = sub_lazy(z0, z1);
+        z0 = a;
+        z1 = mul(d, t);
     }
-    static __device__ __forceinline__ W canon_fwd(W x, const Mod&) { return x; }
+    static __device__ __forceinline__ W canon_fwd(W x, const Mod&) { return canon(x); }
     static __device__ __forceinline__ W canon_inv(W x, const Mod&) { return x; }
     // prime64.rs:1013-1021, 1068-1073, 1116-1120
     static __device__ __forceinline__ W mul_norm(W a, W b, const Mod& m) { return mul(mul(a, b), m.n_inv); }
     static __device__ __forceinline__ W norm(W v, const Mod& m) { return mul(v, m.n_inv); }
-    static __device__ __forceinline__ W mul_acc(W acc, W a, W b, const Mod&) { return add(acc, mul(a, b)); }
+    static __device__ __forceinline__ W mul_acc(W acc, W a, W b, const Mod&) { return add(canon(acc), mul(a, b)); }
 };
 
 // ---- any other p >= 2^63 (prime64/generic_solinas.rs:42-75, Div64 remainder).  Device table

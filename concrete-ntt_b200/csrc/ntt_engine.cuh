@@ -179,7 +179,8 @@ struct Engine {
     template <int NP>
     static __device__ __forceinline__ void fwd(W (&x)[NP][R], W* sm, const Tw* __restrict__ tw, unsigned nu0, int tid, const Mod& m)
     {
-        fwd_from<0, NP>(x, sm, tw, nu0, tid, m);
+        if constexpr (kLoopPasses) fwd_loop<NP>(x, sm, tw, nu0, tid, m);
+        else fwd_from<0, NP>(x, sm, tw, nu0, tid, m);
     }
 
     // inv: x enters in pass-(P-1) layout, leaves in pass-0 layout, lazy range of the policy.
@@ -198,7 +199,97 @@ struct Engine {
     template <int NP>
     static __device__ __forceinline__ void inv(W (&x)[NP][R], W* sm, const Tw* __restrict__ tw, unsigned nu0, int tid, const Mod& m)
     {
-        inv_from<P - 1, NP>(x, sm, tw, nu0, tid, m);
+        if constexpr (kLoopPasses) inv_loop<NP>(x, sm, tw, nu0, tid, m);
+        else inv_from<P - 1, NP>(x, sm, tw, nu0, tid, m);
+    }
+
+    // ---- pass loop (64-bit words) ---------------------------------------------------------------
+    // A 64-bit butterfly is ~40 SASS instructions, so the fully unrolled transform (R/2 * LOGN
+    // butterflies) is ~55 KB of code for N = 2048 and thrashes the 32 KB instruction cache (ncu:
+    // stall_no_instruction was the top stall).  The butterfly levels are therefore emitted once and the
+    // passes iterate at run time; only the (tiny) per-pass exchanges stay specialised at compile time.
+    static constexpr bool kLoopPasses = (sizeof(W) == 8) && (P >= 2);
+
+    template <int Q> static __device__ __forceinline__ unsigned node_rt(int q, int tid, unsigned nu0)
+    {
+        if constexpr (Q + 1 >= P) return node<Q>(tid, nu0);
+        else return q == Q ? node<Q>(tid, nu0) : node_rt<Q + 1>(q, tid, nu0);
+    }
+    // exchange between pass Q and pass Q+1 (either direction), selected at run time
+    template <int Q, int NP, bool FWD>
+    static __device__ __forceinline__ void xchg_rt(int q, W (&x)[NP][R], W* sm, int tid)
+    {
+        if constexpr (Q + 1 < P) {
+            if (q == Q) {
+                W* buf = sm + ((NBUF == 2 && (Q & 1)) ? SMEM_WORDS : 0);
+                if constexpr (FWD) {
+                    scatter<Q, NP>(x, buf, tid);
+                    __syncthreads();
+                    gather<Q + 1, NP>(x, buf, tid);
+                } else {
+                    scatter<Q + 1, NP>(x, buf, tid);
+                    __syncthreads();
+                    gather<Q, NP>(x, buf, tid);
+                }
+                if constexpr (NBUF == 1 && P >= 3) __syncthreads();
+            } else {
+                xchg_rt<Q + 1, NP, FWD>(q, x, sm, tid);
+            }
+        }
+    }
+    template <int NP>
+    static __device__ __forceinline__ void levels_fwd(W (&x)[NP][R], const Tw* __restrict__ tw, unsigned nu, int L, const Mod& m)
+    {
+#pragma unroll
+        for (int j = 0; j < LOGR; j++) {
+            if (G::R1 == LOGR || j < L) {
+                const int half = R >> (j + 1);
+#pragma unroll
+                for (int g = 0; g < (1 << j); g++) {
+                    const Tw t = ldtw(tw, (nu << j) + g);
+#pragma unroll
+                    for (int u = 0; u < half; u++)
+#pragma unroll
+                        for (int np = 0; np < NP; np++) A::fwd_bf(x[np][2 * half * g + u], x[np][2 * half * g + u + half], t, m);
+                }
+            }
+        }
+    }
+    template <int NP>
+    static __device__ __forceinline__ void levels_inv(W (&x)[NP][R], const Tw* __restrict__ tw, unsigned nu, int L, const Mod& m)
+    {
+#pragma unroll
+        for (int j = LOGR - 1; j >= 0; j--) {
+            if (G::R1 == LOGR || j < L) {
+                const int half = R >> (j + 1);
+#pragma unroll
+                for (int g = 0; g < (1 << j); g++) {
+                    const Tw t = ldtw(tw, (nu << j) + g);
+#pragma unroll
+                    for (int u = 0; u < half; u++)
+#pragma unroll
+                        for (int np = 0; np < NP; np++) A::inv_bf(x[np][2 * half * g + u], x[np][2 * half * g + u + half], t, m);
+                }
+            }
+        }
+    }
+    template <int NP>
+    static __device__ __forceinline__ void fwd_loop(W (&x)[NP][R], W* sm, const Tw* __restrict__ tw, unsigned nu0, int tid, const Mod& m)
+    {
+#pragma unroll 1
+        for (int q = 0; q < P; q++) {
+            levels_fwd<NP>(x, tw, node_rt<0>(q, tid, nu0), q == 0 ? G::R1 : LOGR, m);
+            xchg_rt<0, NP, true>(q, x, sm, tid);
+        }
+    }
+    template <int NP>
+    static __device__ __forceinline__ void inv_loop(W (&x)[NP][R], W* sm, const Tw* __restrict__ tw, unsigned nu0, int tid, const Mod& m)
+    {
+#pragma unroll 1
+        for (int q = P - 1; q >= 0; q--) {
+            levels_inv<NP>(x, tw, node_rt<0>(q, tid, nu0), q == 0 ? G::R1 : LOGR, m);
+            xchg_rt<0, NP, false>(q - 1, x, sm, tid);
+        }
     }
 
     // element index held in slot k after fwd / expected before inv

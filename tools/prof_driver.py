@@ -1,0 +1,50 @@
+"""Small driver for ncu captures: launches one hot-path kernel a few times on a device-resident batch.
+usage: python tools/prof_driver.py {ntt64|ntt32|polymul64|polymul128|polymulb64|polymul32} [batch] [n]"""
+import importlib
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+cntt = importlib.import_module("concrete-ntt_b200")
+
+which = sys.argv[1]
+batch = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 2048
+g = torch.Generator(device="cuda").manual_seed(1)
+reps = 4
+if which == "ntt64":
+    plan = cntt.prime64.Plan.try_new(n, cntt.prime64.Solinas.P)
+    d = torch.randint(0, 2**62, (batch, n), dtype=torch.int64, device="cuda", generator=g)
+    for _ in range(reps):
+        plan.fwd(d)
+        plan.inv(d)
+elif which == "ntt32":
+    plan = cntt.prime32.Plan.try_new(n, 1062862849)
+    d = torch.randint(0, 1062862849, (batch, n), dtype=torch.int32, device="cuda", generator=g)
+    for _ in range(reps):
+        plan.fwd(d)
+        plan.inv(d)
+elif which in ("polymul64", "polymulb64", "polymul32"):
+    mod = {"polymul64": cntt.native64, "polymulb64": cntt.native_binary64, "polymul32": cntt.native32}[which]
+    plan = mod.Plan32.try_new(n)
+    dt = torch.int32 if which == "polymul32" else torch.int64
+    hi = 2**31 - 1 if which == "polymul32" else 2**63 - 1
+    lhs = torch.randint(-hi - 1, hi, (batch, n), dtype=dt, device="cuda", generator=g)
+    rhs = torch.randint(-hi - 1, hi, (batch, n), dtype=dt, device="cuda", generator=g)
+    if which == "polymulb64":
+        rhs &= 1
+    prod = torch.empty_like(lhs)
+    for _ in range(reps):
+        plan.negacyclic_polymul(prod, lhs, rhs)
+elif which == "polymul128":
+    plan = cntt.native128.Plan32.try_new(n)
+    lhs = torch.randint(-2**63, 2**63 - 1, (batch, n, 2), dtype=torch.int64, device="cuda", generator=g)
+    rhs = torch.randint(-2**63, 2**63 - 1, (batch, n, 2), dtype=torch.int64, device="cuda", generator=g)
+    prod = torch.empty_like(lhs)
+    for _ in range(reps):
+        plan.negacyclic_polymul(prod, lhs, rhs)
+torch.cuda.synchronize()
+print("done", which, batch, n)
