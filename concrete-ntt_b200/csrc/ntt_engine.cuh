@@ -50,49 +50,83 @@ struct Engine {
     typedef typename A::Mod Mod;
     static constexpr int N = G::N, R = G::R, T = G::T, P = G::P;
     static constexpr int LOGROW = PadCfg<W>::LOGROW;
-    static constexpr int SMEM_WORDS = padded_words<W>(N);      // per polynomial, per buffer
-    static constexpr int NBUF = (P >= 3) ? 2 : 1;              // ping-pong when >1 exchange
+    static constexpr int PH = 1 << LOGROW;                      // lanes served by one shared-memory phase
 
     // ---- layouts ------------------------------------------------------------------------
+    // Pass q >= 1 works on blocks of B = N >> s0(q) words, S = B / R apart inside a thread.  When S is
+    // smaller than a phase, one phase touches PH / S different blocks; with the padded layout those
+    // blocks must be D = PH / R apart to land on distinct banks, so the thread -> block map is permuted
+    // (blocks {b0, b0 + D, ...} share a phase).  Verified conflict-free by enumeration for every
+    // (LOGN, LOGR, word size) the library instantiates.  When a polynomial has too
+    // few phases for that permutation (small N) the engine switches to an XOR swizzle
+    // i ^ ((i >> LOGR) & (PH - 1)) of the unpadded index, which is conflict-free for every pass.
+    template <int Q> static __host__ __device__ constexpr int blk_words() { return Q == 0 ? N : (N >> G::s0(Q)); }
+    template <int Q> static __host__ __device__ constexpr int stride() { return Q == 0 ? T : (blk_words<Q>() >> LOGR); }
+    template <int Q> static __host__ __device__ constexpr bool wants_perm()
+    {
+        return Q >= 1 && stride<Q>() < PH && blk_words<Q>() >= PH && R < PH;
+    }
+    static constexpr int D = (R < PH) ? PH / R : 1;
+    static constexpr bool kPermFeasible = (T / PH) >= D && ((T / PH) % D) == 0;
+    template <int Q> static __host__ __device__ constexpr bool any_wants_perm()
+    {
+        if constexpr (Q >= P) return false;
+        else return wants_perm<Q>() || any_wants_perm<Q + 1>();
+    }
+    static constexpr bool kXor = any_wants_perm<0>() && !kPermFeasible;
+    static constexpr int SMEM_WORDS = kXor ? N : padded_words<W>(N); // per polynomial, per buffer
+    static constexpr int NBUF = (P >= 3) ? 2 : 1;                    // ping-pong when >1 exchange
+
+    template <int Q> static __device__ __forceinline__ void decomp(int tid, int& blk, int& o)
+    {
+        constexpr int S = stride<Q>();
+        if constexpr (Q == 0) {
+            blk = 0; o = tid;
+        } else if constexpr (wants_perm<Q>() && !kXor) {
+            const int w = tid / PH, l = tid % PH;
+            blk = (w / D) * (D * (PH / S)) + (w % D) + D * (l / S);
+            o = l % S;
+        } else {
+            blk = tid / S; o = tid % S;
+        }
+    }
     // element index of register slot k of thread `tid` in pass q
     template <int Q> static __device__ __forceinline__ int elem(int tid, int k)
     {
-        if constexpr (Q == 0) {
-            return tid + k * T;
-        } else {
-            constexpr int B = N >> G::s0(Q);
-            constexpr int S = B >> LOGR;
-            return (tid & ~(S - 1)) * R + (tid & (S - 1)) + k * S;
-        }
+        int blk, o;
+        decomp<Q>(tid, blk, o);
+        return blk * blk_words<Q>() + o + k * stride<Q>();
     }
     template <int Q> static __device__ __forceinline__ unsigned node(int tid, unsigned nu0)
     {
         if constexpr (Q == 0) {
             return nu0;
         } else {
-            constexpr int s0 = G::s0(Q);
-            constexpr int B = N >> s0;
-            constexpr int S = B >> LOGR;
-            return (nu0 << s0) + (unsigned)(tid / S);
+            int blk, o;
+            decomp<Q>(tid, blk, o);
+            return (nu0 << G::s0(Q)) + (unsigned)blk;
         }
     }
-    // padded shared-memory index of slot k: base computed once, per-k offsets are compile-time
-    // whenever the split (base + kS) >> LOGROW == (base >> LOGROW) + (kS >> LOGROW) is exact.
-    template <int Q> static __host__ __device__ constexpr int stride()
-    {
-        if constexpr (Q == 0) return T;
-        else return (N >> G::s0(Q)) >> LOGR;
-    }
+    // shared-memory index of slot k.  Padded mode: base computed once, per-k offsets are compile-time
+    // whenever the split (base + kS) >> LOGROW == (base >> LOGROW) + (kS >> LOGROW) is exact (always for
+    // Q >= 1; for Q == 0 iff T is a multiple of the row).  XOR mode: the fields (block | slot | offset) of
+    // the element index are bit-disjoint, so swz(base + kS) = swz(base) ^ swz(kS).
+    static __host__ __device__ constexpr int swz(int i) { return i ^ ((i >> LOGR) & (PH - 1)); }
     template <int Q> static __host__ __device__ constexpr bool split_ok()
     {
-        // Q == 0: exact iff T is a multiple of the row; Q >= 1: always exact
-        if constexpr (Q == 0) return (T % (1 << LOGROW)) == 0;
+        if constexpr (Q == 0) return (T % PH) == 0;
         else return true;
     }
-    template <int Q> static __device__ __forceinline__ int sidx(int base_elem, int base_pad, int k)
+    template <int Q> static __device__ __forceinline__ int sbase(int base_elem)
+    {
+        if constexpr (kXor) return swz(base_elem);
+        else return pad_idx<W>(base_elem);
+    }
+    template <int Q> static __device__ __forceinline__ int sidx(int base_elem, int base_s, int k)
     {
         constexpr int S = stride<Q>();
-        if constexpr (split_ok<Q>()) return base_pad + k * S + ((k * S) >> LOGROW);
+        if constexpr (kXor) return base_s ^ swz(k * S);
+        else if constexpr (split_ok<Q>()) return base_s + k * S + ((k * S) >> LOGROW);
         else return pad_idx<W>(base_elem + k * S);
     }
 
@@ -100,21 +134,21 @@ struct Engine {
     static __device__ __forceinline__ void scatter(W (&x)[NP][R], W* sm, int tid)
     {
         const int be = elem<Q>(tid, 0);
-        const int bp = pad_idx<W>(be);
+        const int bs = sbase<Q>(be);
 #pragma unroll
         for (int np = 0; np < NP; np++)
 #pragma unroll
-            for (int k = 0; k < R; k++) sm[np * SMEM_WORDS * NBUF + sidx<Q>(be, bp, k)] = x[np][k];
+            for (int k = 0; k < R; k++) sm[np * SMEM_WORDS * NBUF + sidx<Q>(be, bs, k)] = x[np][k];
     }
     template <int Q, int NP>
     static __device__ __forceinline__ void gather(W (&x)[NP][R], const W* sm, int tid)
     {
         const int be = elem<Q>(tid, 0);
-        const int bp = pad_idx<W>(be);
+        const int bs = sbase<Q>(be);
 #pragma unroll
         for (int np = 0; np < NP; np++)
 #pragma unroll
-            for (int k = 0; k < R; k++) x[np][k] = sm[np * SMEM_WORDS * NBUF + sidx<Q>(be, bp, k)];
+            for (int k = 0; k < R; k++) x[np][k] = sm[np * SMEM_WORDS * NBUF + sidx<Q>(be, bs, k)];
     }
 
     static __device__ __forceinline__ Tw ldtw(const Tw* __restrict__ tw, unsigned idx) { return __ldg(tw + idx); }
