@@ -15,6 +15,7 @@ import types as _types
 from . import _lib
 from ._lib import CnttError, LibraryMissing, ReferencePanic  # noqa: F401
 from . import plans as _plans
+from . import shard  # noqa: F401  (batch sharding across GPUs; no collective on the data path)
 
 
 def _module(name, **attrs):

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcntt_b200.so")
+LIB_PATH = os.environ.get("CNTT_B200_LIB", os.path.join(_HERE, "libcntt_b200.so"))  # override: experiments only
 
 OK, INVALID_SIZE, INVALID_MODULUS, NO_ROOT, LENGTH_MISMATCH, CUDA_ERROR, NULL_POINTER, UNSUPPORTED, PANIC_MODULUS = range(9)
 

@@ -117,7 +117,10 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
 template <int KIND, int LOGN>
 static cudaError_t launch_fused_one(const NativePlanDev& pl, void* prod, const void* lhs, const void* rhs, size_t batch, cudaStream_t st)
 {
-    constexpr int LOGR = LOGN < 3 ? LOGN : 3;
+#ifndef CNTT_FUSED_LOGR
+#define CNTT_FUSED_LOGR 3
+#endif
+    constexpr int LOGR = LOGN < CNTT_FUSED_LOGR ? LOGN : CNTT_FUSED_LOGR;
     typedef FusedCfg<KIND, LOGN, LOGR> Cfg;
     FusedParams fp;
     for (int k = 0; k < Cfg::NP; k++) {

@@ -1,0 +1,44 @@
+"""Times device-resident polymul / NTT launches with CUDA events (quick A/B experiments)."""
+import importlib, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+cntt = importlib.import_module("concrete-ntt_b200")
+def bench(fn, reps=10):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+g = torch.Generator(device="cuda").manual_seed(1)
+cases = sys.argv[1:] or ["native64:2048:65536"]
+for c in cases:
+    kind, n, batch = c.split(":"); n = int(n); batch = int(batch)
+    if kind.startswith("native") or kind.startswith("binary"):
+        bits = int(kind.replace("native", "").replace("binary", ""))
+        mod = getattr(cntt, ("native_binary%d" if kind.startswith("binary") else "native%d") % bits)
+        plan = mod.Plan32.try_new(n)
+        shape = (batch, n, 2) if bits == 128 else (batch, n)
+        dt = torch.int32 if bits == 32 else torch.int64
+        hi = 2**31 - 1 if bits == 32 else 2**63 - 1
+        lhs = torch.randint(-hi - 1, hi, shape, dtype=dt, device="cuda", generator=g)
+        rhs = torch.randint(-hi - 1, hi, shape, dtype=dt, device="cuda", generator=g)
+        if kind.startswith("binary"):
+            rhs &= 1
+            if bits == 128: rhs[..., 1] = 0
+        prod = torch.empty_like(lhs)
+        ms = bench(lambda: plan.negacyclic_polymul(prod, lhs, rhs))
+        print("%s n=%d batch=%d: %.3f ms  %.2f M polymul/s" % (kind, n, batch, ms, batch / ms / 1e3))
+    else:
+        if kind == "p32":
+            plan = cntt.prime32.Plan.try_new(n, 1062862849); d = torch.randint(0, 1062862849, (batch, n), dtype=torch.int32, device="cuda", generator=g)
+        elif kind == "p64s":
+            plan = cntt.prime64.Plan.try_new(n, cntt.prime64.Solinas.P); d = torch.randint(0, 2**62, (batch, n), dtype=torch.int64, device="cuda", generator=g)
+        else:
+            p = cntt.prime.largest_prime_in_arithmetic_progression64(1 << 17, 1, 1 << 61, 1 << 62)
+            plan = cntt.prime64.Plan.try_new(n, p); d = torch.randint(0, 2**61, (batch, n), dtype=torch.int64, device="cuda", generator=g)
+        f = bench(lambda: plan.fwd(d)); i = bench(lambda: plan.inv(d))
+        wb = 4 if kind == "p32" else 8
+        print("%s n=%d batch=%d: fwd %.3f ms (%.1f M NTT/s, %.0f GB/s)  inv %.3f ms (%.1f M NTT/s)" % (kind, n, batch, f, batch / f / 1e3, 2 * n * wb * batch / f / 1e6, i, batch / i / 1e3))
