@@ -584,6 +584,7 @@ CNTT_API int cntt_native_plan_new(size_t n, int word_bits, int binary, int devic
     pl->dev.logn = pl->sub[0]->logn;
     pl->dev.nprimes = pl->nprimes;
     for (int k = 0; k < pl->nprimes; k++) pl->dev.sub[k] = dev32<A32L4>(pl->sub[k]);
+    native_lhs_scale(pl->dev.logn, pl->dev.lscale);
     *out = pl;
     return CNTT_OK;
 }

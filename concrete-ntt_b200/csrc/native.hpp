@@ -6,26 +6,28 @@
 
 namespace cntt {
 
-// Built-in primes P0..P9 (src/lib.rs:453-462) and everything Garner reconstruction needs
-// (src/lib.rs:512-594).  Filled on the host by native_consts() with the reference's formulas and
-// passed to kernels by value.
+// Everything the native kernels need about the built-in primes P0..P9 (src/lib.rs:453-462), derived on
+// the host by native_consts() and passed to kernels by value (constant bank, compile-time indices).
+//
+// Garner reconstruction works on 32-bit mixed-radix digits d_0..d_{np-1} of the unique x in [0, prod P_k)
+// with x = r_k (mod P_k):   x = d_0 + d_1 P_0 + d_2 P_0 P_1 + ...
+//   d_k = (..((r_k - d_0) P_0^-1 - d_1) P_1^-1 - ...) P_{k-1}^-1  mod P_k
+// These are the digits the reference's reconstruct_* functions compute (their v_i, or pairs of them:
+// v12 = d_1 + d_2 P_1, v34 = d_3 + d_4 P_3 in src/native64.rs:90-141), so the lifted word and the sign
+// rule (top digit / top digit pair > half) are identical; only the evaluation order differs.
 struct NativeConsts {
     uint32_t P[10];
-    uint64_t barrett[10];  // floor(2^64 / P[k]) : value % P[k] without a divide
-    uint32_t c64[10];      // 2^64 mod P[k]      : folds the high limb of a 128-bit word
-    uint32_t P0_INV_MOD_P1, P01_INV_MOD_P2, P1_INV_MOD_P2, P3_INV_MOD_P4;
-    uint32_t P2_INV_MOD_P3, P4_INV_MOD_P5, P6_INV_MOD_P7, P8_INV_MOD_P9;
-    uint64_t P12, P34, P0_INV_MOD_P12, P0_INV_MOD_P12_SHOUP, P0_MOD_P34_SHOUP, P012_INV_MOD_P34, P012_INV_MOD_P34_SHOUP;
-    uint64_t P01, P23, P45, P67, P89;
-    uint64_t P01_MOD_P45_SHOUP, P01_MOD_P67_SHOUP, P01_MOD_P89_SHOUP, P23_MOD_P67_SHOUP, P23_MOD_P89_SHOUP, P45_MOD_P89_SHOUP;
-    uint64_t P01_INV_MOD_P23, P01_INV_MOD_P23_SHOUP, P0123_INV_MOD_P45, P0123_INV_MOD_P45_SHOUP;
-    uint64_t P012345_INV_MOD_P67, P012345_INV_MOD_P67_SHOUP, P01234567_INV_MOD_P89, P01234567_INV_MOD_P89_SHOUP;
-    uint64_t P0123[2], P012345[2], P01234567[2], P0123456789[2]; // wrapping u128 products, {lo, hi}
+    uint32_t pinv[10];      // P[k]^-1 mod 2^32 (Montgomery)
+    uint2 red[10][4];       // red[k][j] = {2^(32 j) mod P[k], its Shoup companion}, j = 1..3  (j = 0 unused)
+    uint2 ginv[10][10];     // ginv[j][k] = {P[j]^-1 mod P[k], Shoup companion}, j < k
+    uint64_t gm[11][2];     // gm[j] = P_0 ... P_{j-1} mod 2^128 as {lo, hi}; gm[0] = 1
+    uint32_t half_single[10]; // floor(P[k] / 2): sign threshold when the top digit decides (np = 2, 3)
+    uint32_t half_pair_lo[10], half_pair_hi[10]; // floor(P[k-1] P[k] / 2) = lo + hi * P[k-1] (np = 5, 10)
 };
 
 const NativeConsts& native_consts();
 
-enum NativeKind {            // word_bits / binary            reconstruction
+enum NativeKind {            // word_bits / binary            reference reconstruction
     NK_NATIVE32 = 0,         // 32 / 0   3 primes              native32.rs:27-56
     NK_NATIVE64 = 1,         // 64 / 0   5 primes              native64.rs:90-141
     NK_NATIVE128 = 2,        // 128 / 0  10 primes             native128.rs:19-118
@@ -41,10 +43,14 @@ struct NativePlanDev {
     int logn;
     int nprimes;
     PlanDev<A32L4> sub[10]; // prime32 sub-plans on P0.. (all < 2^30)
+    uint2 lscale[10][4];    // 2^(32 j) * 2^32 / N mod P[k] (Shoup pairs): lhs scaling of the fused polymul
 };
 
+void native_lhs_scale(int logn, uint2 (*out)[4]);
+
 // value (batch*n words) -> nprimes residue planes of batch*n u32, plane k at planes + k*plane_stride.
-// copy_low32: fwd_binary's `*value as u32` (no reduction).
+// copy_low32: fwd_binary's `*value as u32` (no reduction).  Residues are written in the lazy range
+// [0, 4p) accepted by the forward NTT kernels (the planes are only ever consumed by them).
 cudaError_t native_reduce(const NativePlanDev& pl, const void* value, uint32_t* planes, size_t plane_stride, size_t nwords,
                           bool copy_low32, cudaStream_t st);
 // residue planes -> words (Garner, centred lift, wrapping)

@@ -1,8 +1,10 @@
-// native_device.cuh -- per-coefficient device code of the native plans: word % P_k and the six Garner
-// reconstructions.  The reconstructions evaluate the reference's formulas term by term so that even
-// arbitrary (not polymul-generated) residues lift to the same word, including the sign rule
-// (src/native32.rs:39, native64.rs:125, native128.rs:105, native_binary32.rs:27,
-// native_binary64.rs:42, native_binary128.rs:47).
+// native_device.cuh -- per-coefficient device code of the native plans: word -> residue (lazy) and the
+// Garner reconstruction on 32-bit mixed-radix digits (see native.hpp for why this equals the reference's
+// reconstruct_* functions, including the sign rule: src/native32.rs:39, native64.rs:125,
+// native128.rs:105, native_binary32.rs:27, native_binary64.rs:42, native_binary128.rs:47).
+//
+// The native kernels are bound by the FMA-heavy pipe (IMAD 1 slot, IMAD.HI 2, IMAD.WIDE 2.6 -- measured,
+// profiles/r01_ubench_int_pipes.txt), so everything here is 32-bit Shoup arithmetic: no 64-bit multiplies.
 #pragma once
 #include "native.hpp"
 
@@ -11,43 +13,60 @@ namespace dev {
 
 typedef unsigned __int128 u128;
 
-// v mod p with M = floor(2^64 / p): the quotient estimate is off by at most one.
-__device__ __forceinline__ uint32_t mod_u64(uint64_t v, uint32_t p, uint64_t M)
+// a * c mod p in [0, 2p) for any 32-bit a; cc = {c, floor(c 2^32 / p)}
+__device__ __forceinline__ uint32_t mulc(uint32_t a, uint2 cc, uint32_t p)
 {
-    const uint64_t q = __umul64hi(v, M);
-    uint64_t r = v - q * p;
-    if (r >= p) r -= p;
-    return (uint32_t)r;
+    const uint32_t q = __umulhi(a, cc.y);
+    return a * cc.x - q * p;
 }
-__device__ __forceinline__ uint32_t mod_u128(uint64_t lo, uint64_t hi, const NativeConsts& c, int k)
+__device__ __forceinline__ uint32_t red2p(uint32_t x, uint32_t p) { return umin32(x, x - 2u * p); } // [0,4p) -> [0,2p)
+__device__ __forceinline__ uint32_t red1p(uint32_t x, uint32_t p) { return umin32(x, x - p); }      // [0,2p) -> [0,p)
+// any 32-bit w -> [0, 2p):  w - (w >> 30) p   (2^30 - p < 2^24 for every built-in prime)
+__device__ __forceinline__ uint32_t fold32(uint32_t w, uint32_t p) { return w - (w >> 30) * p; }
+
+// word -> residue mod P[k] in [0, 4p).  Limb j (weight 2^(32 j)) is multiplied by scale[j] (Shoup pair);
+// limb 0 is multiplied by scale[0] when SCALE0, else folded.  With scale = red[k] this is plain reduction;
+// the fused polymul passes scale = red * (2^32 / N) for the lhs operand (see native_fused.cuh).
+template <int NLIMBS, bool SCALE0>
+__device__ __forceinline__ uint32_t residue(uint64_t lo, uint64_t hi, const uint2* scale, uint32_t p)
 {
-    const uint32_t h = mod_u64(hi, c.P[k], c.barrett[k]);
-    const uint32_t l = mod_u64(lo, c.P[k], c.barrett[k]);
-    return mod_u64((uint64_t)h * c.c64[k] + l, c.P[k], c.barrett[k]);
+    uint32_t x = SCALE0 ? mulc((uint32_t)lo, scale[0], p) : fold32((uint32_t)lo, p); // [0,2p)
+    if constexpr (NLIMBS >= 2) x += mulc((uint32_t)(lo >> 32), scale[1], p);           // [0,4p)
+    if constexpr (NLIMBS >= 4) {
+        x = red2p(x, p) + mulc((uint32_t)hi, scale[2], p);
+        x = red2p(x, p) + mulc((uint32_t)(hi >> 32), scale[3], p);
+    }
+    return x;
 }
-// native32::mul_mod32 (src/native32.rs:21-25): (a * b) % P[k]
-__device__ __forceinline__ uint32_t mul_mod32(const NativeConsts& c, int k, uint32_t a, uint32_t b)
+
+// Montgomery product a b 2^-32 mod p in (0, 2p) for a b < 2^32 p
+__device__ __forceinline__ uint32_t mont(uint32_t a, uint32_t b, uint32_t p, uint32_t pinv)
 {
-    return mod_u64((uint64_t)a * b, c.P[k], c.barrett[k]);
+    const uint64_t t = (uint64_t)a * b;
+    const uint32_t m = (uint32_t)t * pinv;
+    return (uint32_t)(t >> 32) - __umulhi(m, p) + p;
 }
-// native64::mul_mod64 (src/native64.rs:36-41)
-__device__ __forceinline__ uint64_t mul_mod64(uint64_t p_neg, uint64_t a, uint64_t b, uint64_t b_shoup)
-{
-    const uint64_t q = __umul64hi(a, b_shoup);
-    const uint64_t r = a * b + p_neg * q;
-    const uint64_t r2 = r + p_neg;
-    return r < r2 ? r : r2;
-}
-__device__ __forceinline__ u128 mk128(const uint64_t w[2]) { return ((u128)w[1] << 64) | w[0]; }
 
 template <int KIND> struct KindInfo;
-template <> struct KindInfo<NK_NATIVE32> { static constexpr int NP = 3; typedef uint32_t Word; };
-template <> struct KindInfo<NK_NATIVE64> { static constexpr int NP = 5; typedef uint64_t Word; };
-template <> struct KindInfo<NK_NATIVE128> { static constexpr int NP = 10; typedef u128 Word; };
-template <> struct KindInfo<NK_BINARY32> { static constexpr int NP = 2; typedef uint32_t Word; };
-template <> struct KindInfo<NK_BINARY64> { static constexpr int NP = 3; typedef uint64_t Word; };
-template <> struct KindInfo<NK_BINARY128> { static constexpr int NP = 5; typedef u128 Word; };
+template <> struct KindInfo<NK_NATIVE32> { static constexpr int NP = 3, LIMBS = 1; typedef uint32_t Word; };
+template <> struct KindInfo<NK_NATIVE64> { static constexpr int NP = 5, LIMBS = 2; typedef uint64_t Word; };
+template <> struct KindInfo<NK_NATIVE128> { static constexpr int NP = 10, LIMBS = 4; typedef u128 Word; };
+template <> struct KindInfo<NK_BINARY32> { static constexpr int NP = 2, LIMBS = 1; typedef uint32_t Word; };
+template <> struct KindInfo<NK_BINARY64> { static constexpr int NP = 3, LIMBS = 2; typedef uint64_t Word; };
+template <> struct KindInfo<NK_BINARY128> { static constexpr int NP = 5, LIMBS = 4; typedef u128 Word; };
 
+template <int KIND>
+__device__ __forceinline__ void load_word(const void* p, size_t i, uint64_t& lo, uint64_t& hi)
+{
+    typedef typename KindInfo<KIND>::Word Word;
+    if constexpr (sizeof(Word) == 4) { lo = reinterpret_cast<const uint32_t*>(p)[i]; hi = 0; }
+    else if constexpr (sizeof(Word) == 8) { lo = reinterpret_cast<const uint64_t*>(p)[i]; hi = 0; }
+    else {
+        const uint4 q = reinterpret_cast<const uint4*>(p)[i];
+        lo = (uint64_t)q.x | ((uint64_t)q.y << 32);
+        hi = (uint64_t)q.z | ((uint64_t)q.w << 32);
+    }
+}
 template <int KIND>
 __device__ __forceinline__ void store_word(void* value, unsigned long long i, typename KindInfo<KIND>::Word w)
 {
@@ -60,84 +79,43 @@ __device__ __forceinline__ void store_word(void* value, unsigned long long i, ty
     }
 }
 
-// mixed-radix digits shared by native64 / native_binary128: (v0, v12, v34)
-__device__ __forceinline__ void garner_01234(const uint32_t* r, const NativeConsts& c, uint64_t& v0, uint64_t& v12, uint64_t& v34)
-{
-    const uint32_t v2 = mul_mod32(c, 2, c.P1_INV_MOD_P2, 2 * c.P[2] + r[2] - r[1]);
-    const uint64_t mod_p12 = (uint64_t)r[1] + (uint64_t)v2 * c.P[1];
-    const uint32_t v4 = mul_mod32(c, 4, c.P3_INV_MOD_P4, 2 * c.P[4] + r[4] - r[3]);
-    const uint64_t mod_p34 = (uint64_t)r[3] + (uint64_t)v4 * c.P[3];
-    v0 = r[0];
-    v12 = mul_mod64(0 - c.P12, 2 * c.P12 + mod_p12 - v0, c.P0_INV_MOD_P12, c.P0_INV_MOD_P12_SHOUP);
-    v34 = mul_mod64(0 - c.P34, 2 * c.P34 + mod_p34 - (v0 + mul_mod64(0 - c.P34, v12, (uint64_t)c.P[0], c.P0_MOD_P34_SHOUP)),
-                    c.P012_INV_MOD_P34, c.P012_INV_MOD_P34_SHOUP);
-}
-
+// canonical residues r[0..NP) -> centred lift wrapped to the word
 template <int KIND>
 __device__ __forceinline__ typename KindInfo<KIND>::Word reconstruct(const uint32_t* r, const NativeConsts& c)
 {
-    if constexpr (KIND == NK_BINARY32) {
-        const uint32_t v0 = r[0];
-        const uint32_t v1 = mul_mod32(c, 1, c.P0_INV_MOD_P1, 2 * c.P[1] + r[1] - v0);
-        const uint32_t pos = v0 + v1 * c.P[0];
-        return v1 > (c.P[1] / 2) ? pos - c.P[0] * c.P[1] : pos;
-    } else if constexpr (KIND == NK_NATIVE32 || KIND == NK_BINARY64) {
-        const uint32_t v0 = r[0];
-        const uint32_t v1 = mul_mod32(c, 1, c.P0_INV_MOD_P1, 2 * c.P[1] + r[1] - v0);
-        const uint32_t v2 = mul_mod32(c, 2, c.P01_INV_MOD_P2, 2 * c.P[2] + r[2] - (v0 + mul_mod32(c, 2, c.P[0], v1)));
-        const bool sign = v2 > (c.P[2] / 2);
-        if constexpr (KIND == NK_NATIVE32) {
-            const uint32_t _01 = c.P[0] * c.P[1];
-            const uint32_t pos = v0 + v1 * c.P[0] + v2 * _01;
-            return sign ? pos - _01 * c.P[2] : pos;
-        } else {
-            const uint64_t _01 = (uint64_t)c.P[0] * c.P[1];
-            const uint64_t pos = (uint64_t)v0 + (uint64_t)v1 * c.P[0] + (uint64_t)v2 * _01;
-            return sign ? pos - _01 * c.P[2] : pos;
-        }
-    } else if constexpr (KIND == NK_NATIVE64) {
-        uint64_t v0, v12, v34;
-        garner_01234(r, c, v0, v12, v34);
-        const uint64_t _0 = c.P[0], _012 = _0 * c.P12;
-        const uint64_t pos = v0 + v12 * _0 + v34 * _012;
-        return v34 > (c.P34 / 2) ? pos - _012 * c.P34 : pos;
-    } else if constexpr (KIND == NK_BINARY128) {
-        uint64_t v0, v12, v34;
-        garner_01234(r, c, v0, v12, v34);
-        const u128 _0 = c.P[0], _012 = _0 * (u128)c.P12;
-        const u128 pos = (u128)v0 + (u128)v12 * _0 + (u128)v34 * _012;
-        return v34 > (c.P34 / 2) ? pos - _012 * (u128)c.P34 : pos;
-    } else { // NK_NATIVE128
-        uint64_t mp[5];
+    typedef typename KindInfo<KIND>::Word Word;
+    constexpr int NP = KindInfo<KIND>::NP;
+    uint32_t d[NP];
+    d[0] = r[0];
 #pragma unroll
-        for (int t = 0; t < 5; t++) {
-            const uint32_t inv = t == 0 ? c.P0_INV_MOD_P1 : t == 1 ? c.P2_INV_MOD_P3 : t == 2 ? c.P4_INV_MOD_P5
-                                 : t == 3 ? c.P6_INV_MOD_P7 : c.P8_INV_MOD_P9;
-            const uint32_t a = r[2 * t];
-            const uint32_t b = mul_mod32(c, 2 * t + 1, inv, 2 * c.P[2 * t + 1] + r[2 * t + 1] - a);
-            mp[t] = (uint64_t)a + (uint64_t)b * c.P[2 * t];
-        }
-        const uint64_t n23 = 0 - c.P23, n45 = 0 - c.P45, n67 = 0 - c.P67, n89 = 0 - c.P89;
-        const uint64_t v01 = mp[0];
-        const uint64_t v23 = mul_mod64(n23, 2 * c.P23 + mp[1] - v01, c.P01_INV_MOD_P23, c.P01_INV_MOD_P23_SHOUP);
-        const uint64_t v45 = mul_mod64(n45, 2 * c.P45 + mp[2] - (v01 + mul_mod64(n45, v23, c.P01, c.P01_MOD_P45_SHOUP)),
-                                       c.P0123_INV_MOD_P45, c.P0123_INV_MOD_P45_SHOUP);
-        const uint64_t v67 = mul_mod64(
-            n67,
-            2 * c.P67 + mp[3] -
-                (v01 + mul_mod64(n67, v23 + mul_mod64(n67, v45, c.P23, c.P23_MOD_P67_SHOUP), c.P01, c.P01_MOD_P67_SHOUP)),
-            c.P012345_INV_MOD_P67, c.P012345_INV_MOD_P67_SHOUP);
-        const uint64_t v89 = mul_mod64(
-            n89,
-            2 * c.P89 + mp[4] -
-                (v01 + mul_mod64(n89,
-                                 v23 + mul_mod64(n89, v45 + mul_mod64(n89, v67, c.P45, c.P45_MOD_P89_SHOUP), c.P23,
-                                                 c.P23_MOD_P89_SHOUP),
-                                 c.P01, c.P01_MOD_P89_SHOUP)),
-            c.P01234567_INV_MOD_P89, c.P01234567_INV_MOD_P89_SHOUP);
-        const u128 pos = (u128)v01 + (u128)v23 * (u128)c.P01 + (u128)v45 * mk128(c.P0123) + (u128)v67 * mk128(c.P012345) +
-                         (u128)v89 * mk128(c.P01234567);
-        return v89 > (c.P89 / 2) ? pos - mk128(c.P0123456789) : pos;
+    for (int k = 1; k < NP; k++) {
+        const uint32_t p = c.P[k];
+        uint32_t x = r[k];
+#pragma unroll
+        for (int j = 0; j < k; j++) x = mulc(x - d[j] + p, c.ginv[j][k], p); // d[j] < P[j] < P[k]; x < 2p
+        d[k] = red1p(x, p);
+    }
+    bool neg;
+    if constexpr (NP <= 3) {
+        neg = d[NP - 1] > c.half_single[NP - 1];
+    } else {
+        neg = d[NP - 1] > c.half_pair_hi[NP - 1] || (d[NP - 1] == c.half_pair_hi[NP - 1] && d[NP - 2] > c.half_pair_lo[NP - 1]);
+    }
+    if constexpr (sizeof(Word) == 4) {
+        uint32_t pos = d[0];
+#pragma unroll
+        for (int j = 1; j < NP; j++) pos += d[j] * (uint32_t)c.gm[j][0];
+        return neg ? pos - (uint32_t)c.gm[NP][0] : pos;
+    } else if constexpr (sizeof(Word) == 8) {
+        uint64_t pos = d[0];
+#pragma unroll
+        for (int j = 1; j < NP; j++) pos += (uint64_t)d[j] * c.gm[j][0];
+        return neg ? pos - c.gm[NP][0] : pos;
+    } else {
+        u128 pos = d[0];
+#pragma unroll
+        for (int j = 1; j < NP; j++) pos += (u128)d[j] * (((u128)c.gm[j][1] << 64) | c.gm[j][0]);
+        return neg ? pos - (((u128)c.gm[NP][1] << 64) | c.gm[NP][0]) : pos;
     }
 }
 

@@ -15,6 +15,7 @@ struct FusedParams {
     const uint2* tw_fwd[10];
     const uint2* tw_inv[10];
     Mod32 mod[10];
+    uint2 lscale[10][4];
 };
 
 template <int KIND, int LOGN, int LOGR>
@@ -28,19 +29,12 @@ struct FusedCfg {
     static constexpr size_t SMEM_BYTES = (size_t)GP * (XCHG_WORDS + STASH_WORDS) * sizeof(uint32_t);
 };
 
-template <int KIND>
-__device__ __forceinline__ void load_word(const void* p, size_t i, uint64_t& lo, uint64_t& hi)
-{
-    typedef typename dev::KindInfo<KIND>::Word Word;
-    if constexpr (sizeof(Word) == 4) { lo = reinterpret_cast<const uint32_t*>(p)[i]; hi = 0; }
-    else if constexpr (sizeof(Word) == 8) { lo = reinterpret_cast<const uint64_t*>(p)[i]; hi = 0; }
-    else {
-        const uint4 q = reinterpret_cast<const uint4*>(p)[i];
-        lo = (uint64_t)q.x | ((uint64_t)q.y << 32);
-        hi = (uint64_t)q.z | ((uint64_t)q.w << 32);
-    }
-}
-
+// Per prime p_k (all arithmetic 32-bit, lazy ranges of policy A32L4):
+//   lhs residue * (2^32 / N)   [0,4p)    Shoup multiplies by per-limb constants
+//   rhs residue                [0,4p)    (binary plans: the low 32 bits, src/native_binary64.rs:372-389)
+//   two forward NTTs, twiddle loads shared
+//   pointwise Montgomery product  A B 2^-32 = a b / N   in (0,2p)    (replaces mul_assign_normalize)
+//   inverse NTT, canonical residue parked in shared memory
 template <int KIND, int LOGN, int LOGR>
 __global__ void __launch_bounds__(FusedCfg<KIND, LOGN, LOGR>::GP * FusedCfg<KIND, LOGN, LOGR>::T)
 k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ prod, const void* __restrict__ lhs,
@@ -50,6 +44,7 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
     typedef typename Cfg::E E;
     typedef typename dev::KindInfo<KIND>::Word Word;
     constexpr int T = Cfg::T, R = E::R, N = E::N, NP = Cfg::NP, GP = Cfg::GP;
+    constexpr int LIMBS = dev::KindInfo<KIND>::LIMBS;
     constexpr bool BINARY = KIND >= NK_BINARY32;
     constexpr int WB = (int)sizeof(Word);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -70,32 +65,26 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
 #pragma unroll
     for (int k = 0; k < R; k++) {
         uint64_t h0, h1;
-        load_word<KIND>(lhs, base + tid + k * T, llo[k], h0);
-        load_word<KIND>(rhs, base + tid + k * T, rlo[k], h1);
+        dev::load_word<KIND>(lhs, base + tid + k * T, llo[k], h0);
+        dev::load_word<KIND>(rhs, base + tid + k * T, rlo[k], h1);
         if constexpr (WB == 16) { lhi[k] = h0; rhi[k] = h1; }
     }
 
 #pragma unroll 1
     for (int pk = 0; pk < NP; pk++) {
         const Mod32 m = fp.mod[pk];
-        const uint32_t p = c.P[pk];
-        const uint64_t bar = c.barrett[pk];
+        const uint32_t p = m.p;
         uint32_t x[2][R];
 #pragma unroll
         for (int k = 0; k < R; k++) {
-            if constexpr (WB == 16) {
-                x[0][k] = dev::mod_u128(llo[k], lhi[k], c, pk);
-                x[1][k] = BINARY ? (uint32_t)rlo[k] : dev::mod_u128(rlo[k], rhi[k], c, pk);
-            } else {
-                x[0][k] = dev::mod_u64(llo[k], p, bar);
-                x[1][k] = BINARY ? (uint32_t)rlo[k] : dev::mod_u64(rlo[k], p, bar);
-            }
+            x[0][k] = dev::residue<LIMBS, true>(llo[k], WB == 16 ? lhi[k] : 0ull, fp.lscale[pk], p);
+            x[1][k] = BINARY ? (uint32_t)rlo[k] : dev::residue<LIMBS, false>(rlo[k], WB == 16 ? rhi[k] : 0ull, c.red[pk], p);
         }
         E::template fwd<2>(x, sm, fp.tw_fwd[pk], 1u, tid, m);
         uint32_t y[1][R];
+        const uint32_t pinv = c.pinv[pk];
 #pragma unroll
-        for (int k = 0; k < R; k++)
-            y[0][k] = A32L4::mul_norm(A32L4::canon_fwd(x[0][k], m), A32L4::canon_fwd(x[1][k], m), m);
+        for (int k = 0; k < R; k++) y[0][k] = dev::mont(dev::red2p(x[0][k], p), dev::red2p(x[1][k], p), p, pinv);
         if constexpr (E::NBUF == 1 && E::P >= 2) __syncthreads(); // single exchange buffer: fwd gather vs inv scatter
         E::template inv<1>(y, sm, fp.tw_inv[pk], 1u, tid, m);
 #pragma unroll
@@ -127,6 +116,7 @@ static cudaError_t launch_fused_one(const NativePlanDev& pl, void* prod, const v
         fp.tw_fwd[k] = pl.sub[k].tw_fwd;
         fp.tw_inv[k] = pl.sub[k].tw_inv;
         fp.mod[k] = pl.sub[k].mod;
+        for (int j = 0; j < 4; j++) fp.lscale[k][j] = pl.lscale[k][j];
     }
     auto kern = k_polymul_fused<KIND, LOGN, LOGR>;
     if (Cfg::SMEM_BYTES > 227 * 1024) return cudaErrorNotSupported;

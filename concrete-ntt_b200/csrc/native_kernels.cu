@@ -7,7 +7,7 @@
 
 namespace cntt {
 
-// ---- host: constants (same formulas as src/lib.rs:512-594) ---------------------------------------
+// ---- host: constants -----------------------------------------------------------------------------
 static NativeConsts g_consts;
 static std::once_flag g_consts_once;
 
@@ -17,69 +17,36 @@ static void fill_consts()
     typedef unsigned __int128 u128;
     NativeConsts& c = g_consts;
     static const uint32_t P[10] = {0x3F5A0001u, 0x3F5D0001u, 0x3F760001u, 0x3F820001u, 0x3FAC0001u,
-                                   0x3FAF0001u, 0x3FB10001u, 0x3FBB0001u, 0x3FDE0001u, 0x3FFC0001u};
+                                   0x3FAF0001u, 0x3FB10001u, 0x3FBB0001u, 0x3FDE0001u, 0x3FFC0001u}; // src/lib.rs:453-462
+    auto shoup = [](uint64_t w, uint32_t p) { return make_uint2((uint32_t)w, (uint32_t)((w << 32) / p)); };
     for (int k = 0; k < 10; k++) {
-        c.P[k] = P[k];
-        c.barrett[k] = (uint64_t)((((u128)1) << 64) / P[k]);
-        c.c64[k] = (uint32_t)((((u128)1) << 64) % P[k]);
+        const uint32_t p = P[k];
+        c.P[k] = p;
+        uint32_t inv = 1; // Newton iteration for p^-1 mod 2^32 (p odd)
+        for (int it = 0; it < 5; it++) inv *= 2u - p * inv;
+        c.pinv[k] = inv;
+        Fp f(p);
+        uint64_t w = 1;
+        for (int j = 0; j < 4; j++) {
+            c.red[k][j] = shoup(w, p);
+            w = f.mul(w, ((uint64_t)1 << 32) % p);
+        }
+        for (int j = 0; j < 10; j++) c.ginv[j][k] = j < k ? shoup(f.inv(P[j] % p), p) : make_uint2(0, 0);
+        c.half_single[k] = p / 2;
+        if (k >= 1) {
+            const uint64_t h = ((uint64_t)P[k - 1] * p) / 2;
+            c.half_pair_lo[k] = (uint32_t)(h % P[k - 1]);
+            c.half_pair_hi[k] = (uint32_t)(h / P[k - 1]);
+        } else {
+            c.half_pair_lo[k] = c.half_pair_hi[k] = 0;
+        }
     }
-    auto inv32 = [](uint32_t m, uint64_t x) { return (uint32_t)Fp(m).inv(x % m); };
-    auto shoup64 = [](uint64_t m, uint64_t w) { return (uint64_t)((((u128)w) << 64) / m); };
-    // inverse modulo a product of two primes a*b via Euler: x^(phi - 1)
-    auto inv_pair = [](uint64_t m, uint64_t x, uint32_t a, uint32_t b) { return Fp(m).pow(x, ((uint64_t)a - 1) * ((uint64_t)b - 1) - 1); };
-    c.P0_INV_MOD_P1 = inv32(P[1], P[0]);
-    c.P01_INV_MOD_P2 = inv32(P[2], (uint64_t)P[0] * P[1]);
-    c.P1_INV_MOD_P2 = inv32(P[2], P[1]);
-    c.P3_INV_MOD_P4 = inv32(P[4], P[3]);
-    c.P2_INV_MOD_P3 = inv32(P[3], P[2]);
-    c.P4_INV_MOD_P5 = inv32(P[5], P[4]);
-    c.P6_INV_MOD_P7 = inv32(P[7], P[6]);
-    c.P8_INV_MOD_P9 = inv32(P[9], P[8]);
-    c.P12 = (uint64_t)P[1] * P[2];
-    c.P34 = (uint64_t)P[3] * P[4];
-    c.P0_INV_MOD_P12 = inv_pair(c.P12, P[0], P[1], P[2]);
-    c.P0_INV_MOD_P12_SHOUP = shoup64(c.P12, c.P0_INV_MOD_P12);
-    c.P0_MOD_P34_SHOUP = shoup64(c.P34, P[0]);
-    c.P012_INV_MOD_P34 = inv_pair(c.P34, Fp(c.P34).mul(P[0], c.P12), P[3], P[4]);
-    c.P012_INV_MOD_P34_SHOUP = shoup64(c.P34, c.P012_INV_MOD_P34);
-    c.P01 = (uint64_t)P[0] * P[1];
-    c.P23 = (uint64_t)P[2] * P[3];
-    c.P45 = (uint64_t)P[4] * P[5];
-    c.P67 = (uint64_t)P[6] * P[7];
-    c.P89 = (uint64_t)P[8] * P[9];
-    c.P01_MOD_P45_SHOUP = shoup64(c.P45, c.P01);
-    c.P01_MOD_P67_SHOUP = shoup64(c.P67, c.P01);
-    c.P01_MOD_P89_SHOUP = shoup64(c.P89, c.P01);
-    c.P23_MOD_P67_SHOUP = shoup64(c.P67, c.P23);
-    c.P23_MOD_P89_SHOUP = shoup64(c.P89, c.P23);
-    c.P45_MOD_P89_SHOUP = shoup64(c.P89, c.P45);
-    c.P01_INV_MOD_P23 = inv_pair(c.P23, c.P01, P[2], P[3]);
-    c.P01_INV_MOD_P23_SHOUP = shoup64(c.P23, c.P01_INV_MOD_P23);
-    {
-        Fp f(c.P45);
-        c.P0123_INV_MOD_P45 = inv_pair(c.P45, f.mul(c.P01 % c.P45, c.P23 % c.P45), P[4], P[5]);
-        c.P0123_INV_MOD_P45_SHOUP = shoup64(c.P45, c.P0123_INV_MOD_P45);
+    u128 m = 1;
+    for (int j = 0; j <= 10; j++) {
+        c.gm[j][0] = (uint64_t)m;
+        c.gm[j][1] = (uint64_t)(m >> 64);
+        if (j < 10) m *= (u128)P[j]; // wrapping, like the reference's u128::wrapping_mul (src/lib.rs:591-594)
     }
-    {
-        Fp f(c.P67);
-        c.P012345_INV_MOD_P67 = inv_pair(c.P67, f.mul(f.mul(c.P01 % c.P67, c.P23 % c.P67), c.P45 % c.P67), P[6], P[7]);
-        c.P012345_INV_MOD_P67_SHOUP = shoup64(c.P67, c.P012345_INV_MOD_P67);
-    }
-    {
-        Fp f(c.P89);
-        c.P01234567_INV_MOD_P89 =
-            inv_pair(c.P89, f.mul(f.mul(f.mul(c.P01 % c.P89, c.P23 % c.P89), c.P45 % c.P89), c.P67 % c.P89), P[8], P[9]);
-        c.P01234567_INV_MOD_P89_SHOUP = shoup64(c.P89, c.P01234567_INV_MOD_P89);
-    }
-    u128 p0123 = (u128)c.P01 * (u128)c.P23;
-    u128 p012345 = p0123 * (u128)c.P45;
-    u128 p01234567 = p012345 * (u128)c.P67;
-    u128 p0123456789 = p01234567 * (u128)c.P89;
-    auto split = [](u128 x, uint64_t out[2]) { out[0] = (uint64_t)x; out[1] = (uint64_t)(x >> 64); };
-    split(p0123, c.P0123);
-    split(p012345, c.P012345);
-    split(p01234567, c.P01234567);
-    split(p0123456789, c.P0123456789);
 }
 
 const NativeConsts& native_consts()
@@ -88,12 +55,28 @@ const NativeConsts& native_consts()
     return g_consts;
 }
 
+// lhs scale constants of the fused polymul: 2^(32 j) * 2^32 * N^-1 mod P[k] (Shoup pairs)
+void native_lhs_scale(int logn, uint2 (*out)[4])
+{
+    const NativeConsts& c = native_consts();
+    for (int k = 0; k < 10; k++) {
+        host::Fp f(c.P[k]);
+        const uint64_t ninv = f.inv(((uint64_t)1 << logn) % c.P[k]);
+        uint64_t w = f.mul(((uint64_t)1 << 32) % c.P[k], ninv);
+        for (int j = 0; j < 4; j++) {
+            out[k][j] = make_uint2((uint32_t)w, (uint32_t)((w << 32) / c.P[k]));
+            w = f.mul(w, ((uint64_t)1 << 32) % c.P[k]);
+        }
+    }
+}
+
 // ---- kernels -------------------------------------------------------------------------------------
 template <int WORD_BYTES, int NP, bool COPY_LOW32>
 __global__ void __launch_bounds__(256)
 k_native_reduce(const NativeConsts c, const void* __restrict__ value, uint32_t* __restrict__ planes, size_t plane_stride,
                 unsigned long long nwords)
 {
+    constexpr int LIMBS = WORD_BYTES / 4;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride) {
         uint64_t lo, hi = 0;
@@ -108,8 +91,7 @@ k_native_reduce(const NativeConsts c, const void* __restrict__ value, uint32_t* 
         for (int k = 0; k < NP; k++) {
             uint32_t r;
             if constexpr (COPY_LOW32) r = (uint32_t)lo;
-            else if constexpr (WORD_BYTES == 16) r = dev::mod_u128(lo, hi, c, k);
-            else r = dev::mod_u64(lo, c.P[k], c.barrett[k]);
+            else r = dev::residue<LIMBS, false>(lo, hi, c.red[k], c.P[k]); // lazy [0,4p): consumed by the forward NTT only
             planes[(size_t)k * plane_stride + i] = r;
         }
     }

@@ -178,7 +178,14 @@ k_pointwise(const typename A::Mod m, typename A::W* __restrict__ dst, const type
 template <class A, int LOGN, bool FWD>
 cudaError_t launch_cta_one(const PlanDev<A>& pl, typename A::W* data, unsigned long long nvpoly, int log_sub, cudaStream_t st)
 {
-    constexpr int LOGR = LOGN < 4 ? LOGN : 4;
+#ifndef CNTT_LOGR64
+#define CNTT_LOGR64 4
+#endif
+#ifndef CNTT_LOGR32
+#define CNTT_LOGR32 4
+#endif
+    constexpr int LOGR_MAX = sizeof(typename A::W) == 8 ? CNTT_LOGR64 : CNTT_LOGR32;
+    constexpr int LOGR = LOGN < LOGR_MAX ? LOGN : LOGR_MAX;
     typedef Engine<A, LOGN, LOGR> E;
     constexpr int T = E::T;
     constexpr int GP = T >= 128 ? 1 : 128 / T;
