@@ -148,6 +148,8 @@ struct cntt_prime32_plan {
     Mod32 mod;
     uint2* d_fwd;
     uint2* d_inv;
+    uint2* d_fwd_last; // last-pass layouts of the CTA kernel (ntt_engine.cuh, TwSrc); nullptr when unused
+    uint2* d_inv_last;
     Staging stg;
 };
 struct cntt_prime64_plan {
@@ -159,6 +161,8 @@ struct cntt_prime64_plan {
     Mod64 mod;
     void* d_fwd; // ulonglong2[n] (Shoup classes) or uint64_t[n] (Solinas)
     void* d_inv;
+    void* d_fwd_last; // as in cntt_prime32_plan
+    void* d_inv_last;
     Staging stg;
 };
 
@@ -173,6 +177,34 @@ static int validate(size_t n, uint64_t p, size_t min_n, uint64_t* psi, int* logn
     if (!host::primitive_root_pow2(p, 2 * (uint64_t)n, psi)) return CNTT_NO_ROOT;
     *logn = lg;
     return CNTT_OK;
+}
+
+static void free_tables32(cntt_prime32_plan* pl)
+{
+    if (pl->d_fwd) cudaFree(pl->d_fwd);
+    if (pl->d_inv) cudaFree(pl->d_inv);
+    if (pl->d_fwd_last) cudaFree(pl->d_fwd_last);
+    if (pl->d_inv_last) cudaFree(pl->d_inv_last);
+}
+// device-side re-layout of the heap tables for the last pass of the CTA kernel (synchronous: plan time)
+static cudaError_t build_last32(cntt_prime32_plan* pl)
+{
+    const bool uses = pl->cls == C32_L4 ? uses_last_A32L4(pl->logn) : pl->cls == C32_L2 ? uses_last_A32L2(pl->logn) : uses_last_A32G(pl->logn);
+    if (!uses) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaMalloc(&pl->d_fwd_last, pl->n * sizeof(uint2))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&pl->d_inv_last, pl->n * sizeof(uint2))) != cudaSuccess) return e;
+    for (int dir = 0; dir < 2; dir++) {
+        const uint2* heap = dir ? pl->d_inv : pl->d_fwd;
+        uint2* o = dir ? pl->d_inv_last : pl->d_fwd_last;
+        switch (pl->cls) {
+        case C32_L4: e = build_last_A32L4(pl->logn, heap, o, nullptr); break;
+        case C32_L2: e = build_last_A32L2(pl->logn, heap, o, nullptr); break;
+        default: e = build_last_A32G(pl->logn, heap, o, nullptr); break;
+        }
+        if (e != cudaSuccess) return e;
+    }
+    return cudaStreamSynchronize(nullptr);
 }
 
 static int build_prime32(size_t n, uint32_t p, int device, cntt_prime32_plan** out)
@@ -200,13 +232,13 @@ static int build_prime32(size_t n, uint32_t p, int device, cntt_prime32_plan** o
     const int big_q = host::ilog2(p) + 1;                       // prime32.rs:669
     m.big_q_m1 = (uint32_t)(big_q - 1);
     m.p_barrett = (uint32_t)((((uint64_t)1) << (big_q + 31)) / p); // prime32.rs:670-671
-    pl->d_fwd = pl->d_inv = nullptr;
+    pl->d_fwd = pl->d_inv = pl->d_fwd_last = pl->d_inv_last = nullptr;
     cudaError_t e;
     if ((e = cudaMalloc(&pl->d_fwd, n * sizeof(uint2))) != cudaSuccess || (e = cudaMalloc(&pl->d_inv, n * sizeof(uint2))) != cudaSuccess ||
         (e = cudaMemcpy(pl->d_fwd, hf.data(), n * sizeof(uint2), cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (e = cudaMemcpy(pl->d_inv, hi.data(), n * sizeof(uint2), cudaMemcpyHostToDevice)) != cudaSuccess) {
-        if (pl->d_fwd) cudaFree(pl->d_fwd);
-        if (pl->d_inv) cudaFree(pl->d_inv);
+        (e = cudaMemcpy(pl->d_inv, hi.data(), n * sizeof(uint2), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = build_last32(pl)) != cudaSuccess) {
+        free_tables32(pl);
         delete pl;
         return cuda_fail(e, "prime32 plan upload");
     }
@@ -225,8 +257,7 @@ CNTT_API void cntt_prime32_plan_free(cntt_prime32_plan* pl)
     if (!pl) return;
     DeviceGuard g(pl->device);
     pl->stg.release();
-    cudaFree(pl->d_fwd);
-    cudaFree(pl->d_inv);
+    free_tables32(pl);
     delete pl;
 }
 CNTT_API size_t cntt_prime32_ntt_size(const cntt_prime32_plan* pl) { return pl ? pl->n : 0; }
@@ -236,6 +267,7 @@ template <class A> static PlanDev<A> dev32(const cntt_prime32_plan* pl)
 {
     PlanDev<A> d;
     d.logn = pl->logn; d.mod = pl->mod; d.tw_fwd = pl->d_fwd; d.tw_inv = pl->d_inv;
+    d.tw_fwd_last = pl->d_fwd_last; d.tw_inv_last = pl->d_inv_last;
     return d;
 }
 static cudaError_t run_ntt32(const cntt_prime32_plan* pl, uint32_t* d, size_t batch, bool fwd, cudaStream_t st)
@@ -298,6 +330,40 @@ CNTT_API int cntt_prime32_mul_accumulate(const cntt_prime32_plan* pl, uint32_t* 
 }
 
 // ---- prime64 ------------------------------------------------------------------------------------------------
+static void free_tables64(cntt_prime64_plan* pl)
+{
+    if (pl->d_fwd) cudaFree(pl->d_fwd);
+    if (pl->d_inv) cudaFree(pl->d_inv);
+    if (pl->d_fwd_last) cudaFree(pl->d_fwd_last);
+    if (pl->d_inv_last) cudaFree(pl->d_inv_last);
+}
+static cudaError_t build_last64(cntt_prime64_plan* pl, size_t bytes)
+{
+    bool uses;
+    switch (pl->cls) {
+    case C64_L4: uses = uses_last_A64L4(pl->logn); break;
+    case C64_L2: uses = uses_last_A64L2(pl->logn); break;
+    case C64_S: uses = uses_last_A64S(pl->logn); break;
+    default: uses = uses_last_A64G(pl->logn); break;
+    }
+    if (!uses) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaMalloc(&pl->d_fwd_last, bytes)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&pl->d_inv_last, bytes)) != cudaSuccess) return e;
+    for (int dir = 0; dir < 2; dir++) {
+        const void* heap = dir ? pl->d_inv : pl->d_fwd;
+        void* o = dir ? pl->d_inv_last : pl->d_fwd_last;
+        switch (pl->cls) {
+        case C64_L4: e = build_last_A64L4(pl->logn, (const ulonglong2*)heap, (ulonglong2*)o, nullptr); break;
+        case C64_L2: e = build_last_A64L2(pl->logn, (const ulonglong2*)heap, (ulonglong2*)o, nullptr); break;
+        case C64_S: e = build_last_A64S(pl->logn, (const uint64_t*)heap, (uint64_t*)o, nullptr); break;
+        default: e = build_last_A64G(pl->logn, (const ulonglong2*)heap, (ulonglong2*)o, nullptr); break;
+        }
+        if (e != cudaSuccess) return e;
+    }
+    return cudaStreamSynchronize(nullptr);
+}
+
 static int build_prime64(size_t n, uint64_t p, int device, cntt_prime64_plan** out)
 {
     typedef unsigned __int128 u128;
@@ -319,7 +385,7 @@ static int build_prime64(size_t n, uint64_t p, int device, cntt_prime64_plan** o
     const int big_q = host::ilog2(p) + 1;                           // prime64.rs:754
     m.big_q_m1 = (uint32_t)(big_q - 1);
     m.p_barrett = (uint64_t)((((u128)1) << (big_q + 63)) / p);      // prime64.rs:755-756 (unused when p >= 2^63)
-    pl->d_fwd = pl->d_inv = nullptr;
+    pl->d_fwd = pl->d_inv = pl->d_fwd_last = pl->d_inv_last = nullptr;
     cudaError_t e;
     size_t bytes;
     std::vector<ulonglong2> sf, si;
@@ -338,9 +404,9 @@ static int build_prime64(size_t n, uint64_t p, int device, cntt_prime64_plan** o
     }
     if ((e = cudaMalloc(&pl->d_fwd, bytes)) != cudaSuccess || (e = cudaMalloc(&pl->d_inv, bytes)) != cudaSuccess ||
         (e = cudaMemcpy(pl->d_fwd, hf, bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (e = cudaMemcpy(pl->d_inv, hi, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) {
-        if (pl->d_fwd) cudaFree(pl->d_fwd);
-        if (pl->d_inv) cudaFree(pl->d_inv);
+        (e = cudaMemcpy(pl->d_inv, hi, bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = build_last64(pl, bytes)) != cudaSuccess) {
+        free_tables64(pl);
         delete pl;
         return cuda_fail(e, "prime64 plan upload");
     }
@@ -358,8 +424,7 @@ CNTT_API void cntt_prime64_plan_free(cntt_prime64_plan* pl)
     if (!pl) return;
     DeviceGuard g(pl->device);
     pl->stg.release();
-    cudaFree(pl->d_fwd);
-    cudaFree(pl->d_inv);
+    free_tables64(pl);
     delete pl;
 }
 CNTT_API size_t cntt_prime64_ntt_size(const cntt_prime64_plan* pl) { return pl ? pl->n : 0; }
@@ -371,6 +436,8 @@ template <class A> static PlanDev<A> dev64(const cntt_prime64_plan* pl)
     d.logn = pl->logn; d.mod = pl->mod;
     d.tw_fwd = reinterpret_cast<const typename A::Tw*>(pl->d_fwd);
     d.tw_inv = reinterpret_cast<const typename A::Tw*>(pl->d_inv);
+    d.tw_fwd_last = reinterpret_cast<const typename A::Tw*>(pl->d_fwd_last);
+    d.tw_inv_last = reinterpret_cast<const typename A::Tw*>(pl->d_inv_last);
     return d;
 }
 static cudaError_t run_ntt64(const cntt_prime64_plan* pl, uint64_t* d, size_t batch, bool fwd, cudaStream_t st)
@@ -544,6 +611,7 @@ struct cntt_native_plan {
     int device;
     int nprimes;
     cntt_prime32_plan* sub[10];
+    uint2* d_fused_last; // fwd/inv last-pass tables of the fused kernel's engine for every prime (2 * nprimes * n entries)
     NativePlanDev dev;
     Staging stg;
 };
@@ -561,6 +629,7 @@ CNTT_API int cntt_native_plan_new(size_t n, int word_bits, int binary, int devic
     cntt_native_plan* pl = new cntt_native_plan();
     pl->n = n; pl->kind = kind; pl->device = device; pl->nprimes = native_num_primes(kind);
     for (int k = 0; k < 10; k++) pl->sub[k] = nullptr;
+    pl->d_fused_last = nullptr;
     // decide Some/None on the host for every prime before touching the device
     for (int k = 0; k < pl->nprimes; k++) {
         uint64_t psi;
@@ -585,6 +654,24 @@ CNTT_API int cntt_native_plan_new(size_t n, int word_bits, int binary, int devic
     pl->dev.nprimes = pl->nprimes;
     for (int k = 0; k < pl->nprimes; k++) pl->dev.sub[k] = dev32<A32L4>(pl->sub[k]);
     native_lhs_scale(pl->dev.logn, pl->dev.lscale);
+    for (int k = 0; k < 10; k++) pl->dev.fused_fwd_last[k] = pl->dev.fused_inv_last[k] = nullptr;
+    if (native_fused_supported(pl->dev.logn)) {
+        DeviceGuard g(device);
+        cudaError_t e = g.ok ? cudaMalloc(&pl->d_fused_last, 2 * (size_t)pl->nprimes * n * sizeof(uint2)) : cudaErrorInvalidDevice;
+        for (int k = 0; k < pl->nprimes && e == cudaSuccess; k++) {
+            uint2* f = pl->d_fused_last + (size_t)(2 * k) * n;
+            uint2* i = f + n;
+            if ((e = native_fused_build_last(pl->dev.logn, pl->sub[k]->d_fwd, f, nullptr)) != cudaSuccess) break;
+            if ((e = native_fused_build_last(pl->dev.logn, pl->sub[k]->d_inv, i, nullptr)) != cudaSuccess) break;
+            pl->dev.fused_fwd_last[k] = f;
+            pl->dev.fused_inv_last[k] = i;
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+        if (e != cudaSuccess) {
+            cntt_native_plan_free(pl);
+            return cuda_fail(e, "native plan upload");
+        }
+    }
     *out = pl;
     return CNTT_OK;
 }
@@ -594,6 +681,7 @@ CNTT_API void cntt_native_plan_free(cntt_native_plan* pl)
     {
         DeviceGuard g(pl->device);
         pl->stg.release();
+        if (pl->d_fused_last) cudaFree(pl->d_fused_last);
     }
     for (int k = 0; k < pl->nprimes; k++) cntt_prime32_plan_free(pl->sub[k]);
     delete pl;

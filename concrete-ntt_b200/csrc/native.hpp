@@ -44,6 +44,8 @@ struct NativePlanDev {
     int nprimes;
     PlanDev<A32L4> sub[10]; // prime32 sub-plans on P0.. (all < 2^30)
     uint2 lscale[10][4];    // 2^(32 j) * 2^32 / N mod P[k] (Shoup pairs): lhs scaling of the fused polymul
+    const uint2* fused_fwd_last[10]; // last-pass twiddle layouts of the fused kernel's engine (Engine::TwSrc::last)
+    const uint2* fused_inv_last[10];
 };
 
 void native_lhs_scale(int logn, uint2 (*out)[4]);
@@ -56,6 +58,9 @@ cudaError_t native_reduce(const NativePlanDev& pl, const void* value, uint32_t* 
 // residue planes -> words (Garner, centred lift, wrapping)
 cudaError_t native_crt(const NativePlanDev& pl, void* value, const uint32_t* planes, size_t plane_stride, size_t nwords,
                        cudaStream_t st);
+// fused kernel: is there a variant for this size, and its engine's last-pass table builder (heap -> out, n entries)
+bool native_fused_supported(int logn);
+cudaError_t native_fused_build_last(int logn, const uint2* heap, uint2* out, cudaStream_t st);
 // fused single-kernel polymul; returns cudaErrorNotSupported when no fused variant exists for (kind, logn)
 cudaError_t native_polymul_fused(const NativePlanDev& pl, void* prod, const void* lhs, const void* rhs, size_t batch,
                                  cudaStream_t st);

@@ -11,9 +11,16 @@
 
 namespace cntt {
 
+#ifndef CNTT_FUSED_LOGR
+#define CNTT_FUSED_LOGR 3
+#endif
+constexpr int kFusedMinLogN = 5, kFusedMaxLogN = 12;
+
 struct FusedParams {
     const uint2* tw_fwd[10];
     const uint2* tw_inv[10];
+    const uint2* tw_fwd_last[10];
+    const uint2* tw_inv_last[10];
     Mod32 mod[10];
     uint2 lscale[10][4];
 };
@@ -80,13 +87,13 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
             x[0][k] = dev::residue<LIMBS, true>(llo[k], WB == 16 ? lhi[k] : 0ull, fp.lscale[pk], p);
             x[1][k] = BINARY ? (uint32_t)rlo[k] : dev::residue<LIMBS, false>(rlo[k], WB == 16 ? rhi[k] : 0ull, c.red[pk], p);
         }
-        E::template fwd<2>(x, sm, fp.tw_fwd[pk], 1u, tid, m);
+        E::template fwd<2>(x, sm, typename E::TwSrc{fp.tw_fwd[pk], fp.tw_fwd_last[pk]}, 1u, tid, m);
         uint32_t y[1][R];
         const uint32_t pinv = c.pinv[pk];
 #pragma unroll
         for (int k = 0; k < R; k++) y[0][k] = dev::mont(dev::red2p(x[0][k], p), dev::red2p(x[1][k], p), p, pinv);
         if constexpr (E::NBUF == 1 && E::P >= 2) __syncthreads(); // single exchange buffer: fwd gather vs inv scatter
-        E::template inv<1>(y, sm, fp.tw_inv[pk], 1u, tid, m);
+        E::template inv<1>(y, sm, typename E::TwSrc{fp.tw_inv[pk], fp.tw_inv_last[pk]}, 1u, tid, m);
 #pragma unroll
         for (int k = 0; k < R; k++) stash[pk * N + tid + k * T] = A32L4::canon_inv(y[0][k], m);
         if constexpr (E::NBUF == 1 && E::P >= 2) __syncthreads(); // inv gather vs next prime's fwd scatter
@@ -106,15 +113,15 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
 template <int KIND, int LOGN>
 static cudaError_t launch_fused_one(const NativePlanDev& pl, void* prod, const void* lhs, const void* rhs, size_t batch, cudaStream_t st)
 {
-#ifndef CNTT_FUSED_LOGR
-#define CNTT_FUSED_LOGR 3
-#endif
     constexpr int LOGR = LOGN < CNTT_FUSED_LOGR ? LOGN : CNTT_FUSED_LOGR;
     typedef FusedCfg<KIND, LOGN, LOGR> Cfg;
     FusedParams fp;
     for (int k = 0; k < Cfg::NP; k++) {
         fp.tw_fwd[k] = pl.sub[k].tw_fwd;
         fp.tw_inv[k] = pl.sub[k].tw_inv;
+        fp.tw_fwd_last[k] = pl.fused_fwd_last[k];
+        fp.tw_inv_last[k] = pl.fused_inv_last[k];
+        if (Cfg::E::kLastXp && (!fp.tw_fwd_last[k] || !fp.tw_inv_last[k])) return cudaErrorInvalidValue;
         fp.mod[k] = pl.sub[k].mod;
         for (int j = 0; j < 4; j++) fp.lscale[k][j] = pl.lscale[k][j];
     }
@@ -144,6 +151,13 @@ static cudaError_t launch_fused_kind(const NativePlanDev& pl, void* prod, const 
     case 12: return launch_fused_one<KIND, 12>(pl, prod, lhs, rhs, batch, st);
     default: return cudaErrorNotSupported; // larger N: unfused two-level pipeline (capi.cu)
     }
+}
+
+template <int LOGN>
+static cudaError_t fused_build_last_one(const uint2* heap, uint2* out, cudaStream_t st)
+{
+    constexpr int LOGR = LOGN < CNTT_FUSED_LOGR ? LOGN : CNTT_FUSED_LOGR;
+    return launch_build_last_e<Engine<A32L4, LOGN, LOGR>>(heap, out, 0, st);
 }
 
 } // namespace cntt

@@ -166,6 +166,21 @@ cudaError_t native_crt(const NativePlanDev& pl, void* value, const uint32_t* pla
 #include "native_fused.cuh"
 
 namespace cntt {
+bool native_fused_supported(int logn) { return logn >= kFusedMinLogN && logn <= kFusedMaxLogN; }
+cudaError_t native_fused_build_last(int logn, const uint2* heap, uint2* out, cudaStream_t st)
+{
+    switch (logn) {
+    case 5: return fused_build_last_one<5>(heap, out, st);
+    case 6: return fused_build_last_one<6>(heap, out, st);
+    case 7: return fused_build_last_one<7>(heap, out, st);
+    case 8: return fused_build_last_one<8>(heap, out, st);
+    case 9: return fused_build_last_one<9>(heap, out, st);
+    case 10: return fused_build_last_one<10>(heap, out, st);
+    case 11: return fused_build_last_one<11>(heap, out, st);
+    case 12: return fused_build_last_one<12>(heap, out, st);
+    default: return cudaErrorNotSupported;
+    }
+}
 cudaError_t native_polymul_fused(const NativePlanDev& pl, void* prod, const void* lhs, const void* rhs, size_t batch,
                                  cudaStream_t st)
 {

@@ -151,20 +151,35 @@ struct Engine {
             for (int k = 0; k < R; k++) x[np][k] = sm[np * SMEM_WORDS * NBUF + sidx<Q>(be, bs, k)];
     }
 
+    // ---- twiddle sources ------------------------------------------------------------------
+    // `heap` is the plan's heap-ordered table.  In the last pass every thread owns a different sub-tree, so
+    // heap reads are strided by 2^j entries across a warp (ncu: the L1 tag stage was the limiter of the
+    // u32 kernels, 4.4x more global-load wavefronts than shared-memory wavefronts).  `last` is the same
+    // data re-laid per (level, g) with the thread index innermost, last[((1 << j) - 1 + g) * T + tid],
+    // built on the device by k_build_last with this very engine's thread map: one coalesced request per load.
+    struct TwSrc {
+        const Tw* __restrict__ heap;
+        const Tw* __restrict__ last; // this polynomial's (sub-block's) slice; unused when !kLastXp
+    };
+    static constexpr int LAST_WORDS = (R - 1) * T;             // entries of one sub-block's last-pass table
+    template <int Q> static __device__ __forceinline__ Tw tw_at(const TwSrc& s, unsigned nu, int tid, int j, int g)
+    {
+        if constexpr (kLastXp && Q == P - 1) return __ldg(s.last + ((1 << j) - 1 + g) * T + tid);
+        else return __ldg(s.heap + (nu << j) + g);
+    }
     static __device__ __forceinline__ Tw ldtw(const Tw* __restrict__ tw, unsigned idx) { return __ldg(tw + idx); }
 
     // ---- register passes ------------------------------------------------------------------
     template <int Q, int NP>
-    static __device__ __forceinline__ void fwd_pass(W (&x)[NP][R], const Tw* __restrict__ tw, unsigned nu, const Mod& m)
+    static __device__ __forceinline__ void fwd_pass(W (&x)[NP][R], const TwSrc& tw, unsigned nu, int tid, const Mod& m)
     {
         constexpr int L = G::levels(Q);
 #pragma unroll
         for (int j = 0; j < L; j++) {
-            constexpr int dummy = 0; (void)dummy;
             const int half = R >> (j + 1);
 #pragma unroll
             for (int g = 0; g < (1 << j); g++) {
-                const Tw t = ldtw(tw, (nu << j) + g);
+                const Tw t = tw_at<Q>(tw, nu, tid, j, g);
 #pragma unroll
                 for (int u = 0; u < half; u++) {
 #pragma unroll
@@ -174,7 +189,7 @@ struct Engine {
         }
     }
     template <int Q, int NP>
-    static __device__ __forceinline__ void inv_pass(W (&x)[NP][R], const Tw* __restrict__ tw, unsigned nu, const Mod& m)
+    static __device__ __forceinline__ void inv_pass(W (&x)[NP][R], const TwSrc& tw, unsigned nu, int tid, const Mod& m)
     {
         constexpr int L = G::levels(Q);
 #pragma unroll
@@ -182,7 +197,7 @@ struct Engine {
             const int half = R >> (j + 1);
 #pragma unroll
             for (int g = 0; g < (1 << j); g++) {
-                const Tw t = ldtw(tw, (nu << j) + g);
+                const Tw t = tw_at<Q>(tw, nu, tid, j, g);
 #pragma unroll
                 for (int u = 0; u < half; u++) {
 #pragma unroll
@@ -198,9 +213,9 @@ struct Engine {
     // `sm` points at this polynomial group's shared memory (NP * NBUF * SMEM_WORDS words).
     // All threads of the CTA must call (uses __syncthreads()).
     template <int Q, int NP>
-    static __device__ __forceinline__ void fwd_from(W (&x)[NP][R], W* sm, const Tw* __restrict__ tw, unsigned nu0, int tid, const Mod& m)
+    static __device__ __forceinline__ void fwd_from(W (&x)[NP][R], W* sm, const TwSrc& tw, unsigned nu0, int tid, const Mod& m)
     {
-        fwd_pass<Q, NP>(x, tw, node<Q>(tid, nu0), m);
+        fwd_pass<Q, NP>(x, tw, node<Q>(tid, nu0), tid, m);
         if constexpr (Q + 1 < P) {
             W* buf = sm + ((NBUF == 2 && (Q & 1)) ? SMEM_WORDS : 0);
             scatter<Q, NP>(x, buf, tid);
@@ -211,17 +226,17 @@ struct Engine {
         }
     }
     template <int NP>
-    static __device__ __forceinline__ void fwd(W (&x)[NP][R], W* sm, const Tw* __restrict__ tw, unsigned nu0, int tid, const Mod& m)
+    static __device__ __forceinline__ void fwd(W (&x)[NP][R], W* sm, const TwSrc& tw, unsigned nu0, int tid, const Mod& m)
     {
-        if constexpr (kLoopPasses) fwd_loop<NP>(x, sm, tw, nu0, tid, m);
+        if constexpr (kLoopPasses) fwd_loop<NP>(x, sm, tw.heap, nu0, tid, m);
         else fwd_from<0, NP>(x, sm, tw, nu0, tid, m);
     }
 
     // inv: x enters in pass-(P-1) layout, leaves in pass-0 layout, lazy range of the policy.
     template <int Q, int NP>
-    static __device__ __forceinline__ void inv_from(W (&x)[NP][R], W* sm, const Tw* __restrict__ tw, unsigned nu0, int tid, const Mod& m)
+    static __device__ __forceinline__ void inv_from(W (&x)[NP][R], W* sm, const TwSrc& tw, unsigned nu0, int tid, const Mod& m)
     {
-        inv_pass<Q, NP>(x, tw, node<Q>(tid, nu0), m);
+        inv_pass<Q, NP>(x, tw, node<Q>(tid, nu0), tid, m);
         if constexpr (Q > 0) {
             W* buf = sm + ((NBUF == 2 && (Q & 1)) ? SMEM_WORDS : 0);
             scatter<Q, NP>(x, buf, tid);
@@ -231,9 +246,9 @@ struct Engine {
         }
     }
     template <int NP>
-    static __device__ __forceinline__ void inv(W (&x)[NP][R], W* sm, const Tw* __restrict__ tw, unsigned nu0, int tid, const Mod& m)
+    static __device__ __forceinline__ void inv(W (&x)[NP][R], W* sm, const TwSrc& tw, unsigned nu0, int tid, const Mod& m)
     {
-        if constexpr (kLoopPasses) inv_loop<NP>(x, sm, tw, nu0, tid, m);
+        if constexpr (kLoopPasses) inv_loop<NP>(x, sm, tw.heap, nu0, tid, m);
         else inv_from<P - 1, NP>(x, sm, tw, nu0, tid, m);
     }
 
@@ -243,6 +258,7 @@ struct Engine {
     // stall_no_instruction was the top stall).  The butterfly levels are therefore emitted once and the
     // passes iterate at run time; only the (tiny) per-pass exchanges stay specialised at compile time.
     static constexpr bool kLoopPasses = (sizeof(W) == 8) && (P >= 2);
+    static constexpr bool kLastXp = (P >= 2) && !kLoopPasses;  // transposed last-pass twiddle table in use
 
     template <int Q> static __device__ __forceinline__ unsigned node_rt(int q, int tid, unsigned nu0)
     {

@@ -21,6 +21,23 @@ struct PlanDev {
     typename A::Mod mod;
     const typename A::Tw* tw_fwd; // heap order, N entries, entry 0 unused (= 1)
     const typename A::Tw* tw_inv;
+    // last-pass tables of the CTA kernel (Engine::TwSrc::last), N entries each, built by launch_build_last;
+    // nullptr when the class / size does not use them
+    const typename A::Tw* tw_fwd_last;
+    const typename A::Tw* tw_inv_last;
+};
+
+// LOGR of the CTA kernel per word size, and whether the last-pass table exists for a transform size
+#ifndef CNTT_LOGR64
+#define CNTT_LOGR64 4
+#endif
+#ifndef CNTT_LOGR32
+#define CNTT_LOGR32 4
+#endif
+template <class A, int LOGN> struct CtaCfg {
+    static constexpr int LOGR_MAX = sizeof(typename A::W) == 8 ? CNTT_LOGR64 : CNTT_LOGR32;
+    static constexpr int LOGR = LOGN < LOGR_MAX ? LOGN : LOGR_MAX;
+    typedef Engine<A, LOGN, LOGR> E;
 };
 
 // ---- vector helpers -------------------------------------------------------------------------
@@ -76,8 +93,8 @@ __device__ __forceinline__ void load_contig(const W* __restrict__ src, W (&x)[R]
 // sub-tree rooted at heap node (1 << log_sub) + (v mod 2^log_sub).
 template <class A, int LOGN, int LOGR, int GP, bool FWD>
 __global__ void __launch_bounds__(GP * Geo<LOGN, LOGR>::T)
-k_ntt_cta(const typename A::Tw* __restrict__ tw, const typename A::Mod m, typename A::W* __restrict__ data,
-          unsigned long long nvpoly, int log_sub)
+k_ntt_cta(const typename A::Tw* __restrict__ tw, const typename A::Tw* __restrict__ tw_last, const typename A::Mod m,
+          typename A::W* __restrict__ data, unsigned long long nvpoly, int log_sub)
 {
     typedef Engine<A, LOGN, LOGR> E;
     typedef typename A::W W;
@@ -91,24 +108,91 @@ k_ntt_cta(const typename A::Tw* __restrict__ tw, const typename A::Mod m, typena
     const bool active = vp < nvpoly;
     if (!active) vp = nvpoly - 1; // keep the group in lock-step (barriers), discard its result
     W* base = data + vp * (unsigned long long)N;
-    const unsigned nu0 = (1u << log_sub) + (unsigned)(vp & ((1ull << log_sub) - 1ull));
+    const unsigned sub = (unsigned)(vp & ((1ull << log_sub) - 1ull));
+    const unsigned nu0 = (1u << log_sub) + sub;
     W* sm = sm_all + (size_t)grp * E::SMEM_WORDS * E::NBUF;
+    const typename E::TwSrc tws = {tw, tw_last + (size_t)sub * E::LAST_WORDS};
 
     W x[1][R];
     if constexpr (FWD) {
 #pragma unroll
         for (int k = 0; k < R; k++) x[0][k] = base[tid + k * T];
-        E::template fwd<1>(x, sm, tw, nu0, tid, m);
+        E::template fwd<1>(x, sm, tws, nu0, tid, m);
 #pragma unroll
         for (int k = 0; k < R; k++) x[0][k] = A::canon_fwd(x[0][k], m);
         if (active) store_contig<W, R>(base + E::elem_last(tid, 0), x[0]);
     } else {
         load_contig<W, R>(base + E::elem_last(tid, 0), x[0]);
-        E::template inv<1>(x, sm, tw, nu0, tid, m);
+        E::template inv<1>(x, sm, tws, nu0, tid, m);
         if (active) {
 #pragma unroll
             for (int k = 0; k < R; k++) base[tid + k * T] = A::canon_inv(x[0][k], m);
         }
+    }
+}
+
+// ---- last-pass twiddle table builder (plan time) ---------------------------------------------------
+// One thread per (sub-block, engine thread): copies the R - 1 heap entries of its last-pass sub-tree into
+// the thread-innermost layout read by Engine::tw_at.  Uses the engine's own thread -> node map, so the
+// table cannot disagree with the kernel that consumes it.
+template <class E>
+__global__ void k_build_last(const typename E::Tw* __restrict__ heap, typename E::Tw* __restrict__ out, int log_sub)
+{
+    constexpr int T = E::T, R = E::R, LOGR = E::G::levels(E::P - 1);
+    const unsigned sub = blockIdx.x;
+    for (int tid = threadIdx.x; tid < T; tid += blockDim.x) {
+        const unsigned nu = E::template node<E::P - 1>(tid, (1u << log_sub) + sub);
+        typename E::Tw* o = out + (size_t)sub * E::LAST_WORDS;
+        for (int j = 0; j < LOGR; j++)
+            for (int g = 0; g < (1 << j); g++) o[((1 << j) - 1 + g) * T + tid] = heap[(nu << j) + g];
+    }
+    (void)R;
+}
+template <class E>
+cudaError_t launch_build_last_e(const typename E::Tw* heap, typename E::Tw* out, int log_sub, cudaStream_t st)
+{
+    if constexpr (!E::kLastXp) { (void)heap; (void)out; (void)log_sub; (void)st; return cudaSuccess; }
+    else {
+        k_build_last<E><<<1u << log_sub, E::T < 256 ? E::T : 256, 0, st>>>(heap, out, log_sub);
+        return cudaGetLastError();
+    }
+}
+// does the CTA kernel of a transform of 2^logn words (class A) read a last-pass table?
+template <class A, int LOGN> constexpr bool cta_uses_last() { return CtaCfg<A, LOGN>::E::kLastXp; }
+template <class A>
+bool plan_uses_last(int logn)
+{
+    const int l = logn < kMaxCtaLogN ? logn : kMaxCtaLogN;
+    switch (l) {
+    case 4: return cta_uses_last<A, 4>();
+    case 5: return cta_uses_last<A, 5>();
+    case 6: return cta_uses_last<A, 6>();
+    case 7: return cta_uses_last<A, 7>();
+    case 8: return cta_uses_last<A, 8>();
+    case 9: return cta_uses_last<A, 9>();
+    case 10: return cta_uses_last<A, 10>();
+    case 11: return cta_uses_last<A, 11>();
+    case 12: return cta_uses_last<A, 12>();
+    default: return false;
+    }
+}
+// heap (2^logn entries) -> last-pass table (2^logn entries) for the CTA kernel this plan size launches
+template <class A>
+cudaError_t launch_build_last(int logn, const typename A::Tw* heap, typename A::Tw* out, cudaStream_t st)
+{
+    const int l = logn < kMaxCtaLogN ? logn : kMaxCtaLogN;
+    const int log_sub = logn - l;
+    switch (l) {
+    case 4: return launch_build_last_e<typename CtaCfg<A, 4>::E>(heap, out, log_sub, st);
+    case 5: return launch_build_last_e<typename CtaCfg<A, 5>::E>(heap, out, log_sub, st);
+    case 6: return launch_build_last_e<typename CtaCfg<A, 6>::E>(heap, out, log_sub, st);
+    case 7: return launch_build_last_e<typename CtaCfg<A, 7>::E>(heap, out, log_sub, st);
+    case 8: return launch_build_last_e<typename CtaCfg<A, 8>::E>(heap, out, log_sub, st);
+    case 9: return launch_build_last_e<typename CtaCfg<A, 9>::E>(heap, out, log_sub, st);
+    case 10: return launch_build_last_e<typename CtaCfg<A, 10>::E>(heap, out, log_sub, st);
+    case 11: return launch_build_last_e<typename CtaCfg<A, 11>::E>(heap, out, log_sub, st);
+    case 12: return launch_build_last_e<typename CtaCfg<A, 12>::E>(heap, out, log_sub, st);
+    default: return cudaErrorInvalidValue;
     }
 }
 
@@ -135,14 +219,15 @@ k_ntt_strided(const typename A::Tw* __restrict__ tw, const typename A::Mod m, ty
     W* base = data + (b << logn) + ((size_t)blk << (logn - s0)) + o;
     const unsigned nu = (1u << s0) + blk;
     W x[1][K];
+    const typename E::TwSrc tws = {tw, nullptr};
 #pragma unroll
     for (int k = 0; k < K; k++) x[0][k] = base[(size_t)k * bsub];
     if constexpr (FWD) {
-        E::template fwd_pass<0, 1>(x, tw, nu, m);
+        E::template fwd_pass<0, 1>(x, tws, nu, 0, m);
 #pragma unroll
         for (int k = 0; k < K; k++) base[(size_t)k * bsub] = x[0][k]; // lazy range, consumed by the next level
     } else {
-        E::template inv_pass<0, 1>(x, tw, nu, m);
+        E::template inv_pass<0, 1>(x, tws, nu, 0, m);
 #pragma unroll
         for (int k = 0; k < K; k++) base[(size_t)k * bsub] = A::canon_inv(x[0][k], m);
     }
@@ -178,15 +263,8 @@ k_pointwise(const typename A::Mod m, typename A::W* __restrict__ dst, const type
 template <class A, int LOGN, bool FWD>
 cudaError_t launch_cta_one(const PlanDev<A>& pl, typename A::W* data, unsigned long long nvpoly, int log_sub, cudaStream_t st)
 {
-#ifndef CNTT_LOGR64
-#define CNTT_LOGR64 4
-#endif
-#ifndef CNTT_LOGR32
-#define CNTT_LOGR32 4
-#endif
-    constexpr int LOGR_MAX = sizeof(typename A::W) == 8 ? CNTT_LOGR64 : CNTT_LOGR32;
-    constexpr int LOGR = LOGN < LOGR_MAX ? LOGN : LOGR_MAX;
-    typedef Engine<A, LOGN, LOGR> E;
+    constexpr int LOGR = CtaCfg<A, LOGN>::LOGR;
+    typedef typename CtaCfg<A, LOGN>::E E;
     constexpr int T = E::T;
     constexpr int GP = T >= 128 ? 1 : 128 / T;
     const size_t smem = (size_t)GP * E::NBUF * E::SMEM_WORDS * sizeof(typename A::W);
@@ -198,7 +276,9 @@ cudaError_t launch_cta_one(const PlanDev<A>& pl, typename A::W* data, unsigned l
     const unsigned long long nblk = (nvpoly + GP - 1) / GP;
     if (nblk == 0) return cudaSuccess;
     if (nblk > 0x7fffffffull) return cudaErrorInvalidValue;
-    kern<<<(unsigned)nblk, GP * T, smem, st>>>(FWD ? pl.tw_fwd : pl.tw_inv, pl.mod, data, nvpoly, log_sub);
+    const typename A::Tw* last = FWD ? pl.tw_fwd_last : pl.tw_inv_last;
+    if (E::kLastXp && last == nullptr) return cudaErrorInvalidValue; // plan built without its last-pass table
+    kern<<<(unsigned)nblk, GP * T, smem, st>>>(FWD ? pl.tw_fwd : pl.tw_inv, last, pl.mod, data, nvpoly, log_sub);
     return cudaGetLastError();
 }
 
