@@ -259,10 +259,14 @@ struct A64L2 : A64L4 {
 
 // ---- p = 2^64 - 2^32 + 1 (Solinas / Goldilocks), prime64/generic_solinas.rs:77-129.
 //      2^64 = 2^32 - 1 =: EPS and 2^96 = -1 (mod p), so a 128-bit product (c3,c2,c1,c0) reduces to
-//      (c1:c0) - c3 + c2*EPS with two end-around corrections.  The kernels are integer-issue bound, so
-//      the arithmetic is written on 32-bit limbs with explicit carry chains (PTX add.cc/subc):
-//        mul     10 + 13 + 4 instructions (4 IMAD.WIDE.U32), result canonical
-//        add 6 / sub 5 instructions, valid when the second operand is <= p (any 64-bit first operand)
+//      (c1:c0) - c3 + c2*EPS with end-around corrections.  The class is bound by the integer pipes
+//      (ncu, r01: ALU 83 %, FMA 19 % busy with an all-ALU formulation), so the arithmetic is written on
+//      32-bit limbs in PTX and split across both pipes on purpose:
+//        product   one mad/madc chain: ptxas keeps the carries inside IMAD.WIDE / IMAD.X / IMAD.HI (FMA pipe)
+//        reduce    (c1:c0) - c3 on the ALU (5), then c2*EPS + X as ONE IMAD.WIDE with carry-out (FMA), and the
+//                  end-around correction merged with the canonicalisation: "carry or r >= p" -> r += EPS mod 2^64 (5)
+//        add 6 / sub 5 ALU instructions, valid when the second operand is <= p (any 64-bit first operand)
+//      => 19 ALU + ~13 FMA-pipe instructions per butterfly (was 30 + 8), both pipes ~40 cycles per warp-butterfly.
 //      (carry chains are never mixed: ptxas hands `subc` the raw carry predicate after an add.cc)
 //      Between forward stages values are arbitrary 64-bit representatives ("lazy"); only products are
 //      canonical.  Between inverse stages all values are canonical.
@@ -283,56 +287,46 @@ struct A64S {
         if (x1 == 0xFFFFFFFFu && x0 != 0u) x = (uint64_t)(x0 - 1u);
         return x;
     }
-    // (c3:c2:c1:c0) mod p as some 64-bit representative
-    static __device__ __forceinline__ W reduce128(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3)
+    static __device__ __forceinline__ W mul(W a, W b) // any a, b; result canonical
     {
-        uint32_t r0, r1;
+        uint32_t c0, c1, c2, c3, r0, r1;
         asm("{\n\t"
-            ".reg .u32 m, tl, th;\n\t"
-            "sub.cc.u32   %0, %2, %5;\n\t"   // (c1:c0) - c3
-            "subc.cc.u32  %1, %3, 0;\n\t"
-            "subc.u32     m, 0, 0;\n\t"      // m = -borrow
-            "sub.cc.u32   %0, %0, m;\n\t"    // borrowed 2^64 = EPS too much: subtract EPS
-            "subc.u32     %1, %1, 0;\n\t"
-            "sub.cc.u32   tl, 0, %4;\n\t"    // c2 * EPS = (c2 << 32) - c2
-            "subc.u32     th, %4, 0;\n\t"
-            "add.cc.u32   %0, %0, tl;\n\t"
-            "addc.cc.u32  %1, %1, th;\n\t"
-            "addc.u32     m, 0, 0;\n\t"      // m = carry (never mix add.cc with subc: ptxas feeds subc the raw carry)
-            "sub.cc.u32   %0, %0, m;\n\t"    // dropped 2^64 = EPS = (m << 32) - m: add it back
-            "subc.u32     %1, %1, 0;\n\t"
-            "add.u32      %1, %1, m;\n\t"
+            "mul.lo.u32      %0, %4, %6;\n\t"
+            "mul.hi.u32      %1, %4, %6;\n\t"
+            "mad.lo.cc.u32   %1, %4, %7, %1;\n\t"
+            "madc.hi.cc.u32  %2, %4, %7, 0;\n\t"
+            "addc.u32        %3, 0, 0;\n\t"
+            "mad.lo.cc.u32   %1, %5, %6, %1;\n\t"
+            "madc.hi.cc.u32  %2, %5, %6, %2;\n\t"
+            "addc.u32        %3, %3, 0;\n\t"
+            "mad.lo.cc.u32   %2, %5, %7, %2;\n\t"
+            "madc.hi.u32     %3, %5, %7, %3;\n\t"
+            "}"
+            : "=&r"(c0), "=&r"(c1), "=&r"(c2), "=&r"(c3)
+            : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)));
+        // X = (c1:c0) - c3 (borrow: the wrap added 2^64 = EPS too much);  r = X + c2*EPS mod 2^64, carry m.
+        // m = 1: true value r + 2^64 = r + EPS, and r <= 2^64 - 2^33 so the sum does not wrap and is < p.
+        // m = 0 and r >= p (r1 all ones, r0 != 0): r + EPS wraps to r - p.  Either way: r += EPS mod 2^64.
+        asm("{\n\t"
+            ".reg .u32 m;\n\t"
+            ".reg .pred q;\n\t"
+            "sub.cc.u32      %0, %2, %5;\n\t"
+            "subc.cc.u32     %1, %3, 0;\n\t"
+            "subc.u32        m, 0, 0;\n\t"
+            "sub.cc.u32      %0, %0, m;\n\t"
+            "subc.u32        %1, %1, 0;\n\t"
+            "mad.lo.cc.u32   %0, %4, 0xFFFFFFFF, %0;\n\t"
+            "madc.hi.cc.u32  %1, %4, 0xFFFFFFFF, %1;\n\t"
+            "addc.u32        m, 0, 0;\n\t"
+            "setp.eq.u32     q, %1, 0xFFFFFFFF;\n\t"
+            "setp.ne.and.u32 q, %0, 0, q;\n\t"
+            "setp.ne.or.u32  q, m, 0, q;\n\t"
+            "@q add.cc.u32   %0, %0, 0xFFFFFFFF;\n\t"
+            "@q addc.u32     %1, %1, 0;\n\t"
             "}"
             : "=&r"(r0), "=&r"(r1)
             : "r"(c0), "r"(c1), "r"(c2), "r"(c3));
         return pack(r0, r1);
-    }
-    static __device__ __forceinline__ W mul(W a, W b) // any a, b; result canonical
-    {
-        // 128-bit product from four IMAD.WIDE.U32 without zero-extended addends: the two cross terms
-        // are summed with an explicit carry (their sum can exceed 64 bits).
-        uint32_t c0, c1, c2, c3;
-        asm("{\n\t"
-            ".reg .u64 m00, m01, m10, m11;\n\t"
-            ".reg .u32 h00, l01, h01, l10, h10, l11, h11, x0, x1, xc;\n\t"
-            "mul.wide.u32 m00, %4, %6;\n\t"
-            "mul.wide.u32 m01, %4, %7;\n\t"
-            "mul.wide.u32 m10, %5, %6;\n\t"
-            "mul.wide.u32 m11, %5, %7;\n\t"
-            "mov.b64 {%0, h00}, m00;\n\t"
-            "mov.b64 {l01, h01}, m01;\n\t"
-            "mov.b64 {l10, h10}, m10;\n\t"
-            "mov.b64 {l11, h11}, m11;\n\t"
-            "add.cc.u32  x0, l01, l10;\n\t"
-            "addc.cc.u32 x1, h01, h10;\n\t"
-            "addc.u32    xc, 0, 0;\n\t"
-            "add.cc.u32  %1, h00, x0;\n\t"
-            "addc.cc.u32 %2, l11, x1;\n\t"
-            "addc.u32    %3, h11, xc;\n\t"
-            "}"
-            : "=r"(c0), "=r"(c1), "=r"(c2), "=r"(c3)
-            : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)));
-        return canon(reduce128(c0, c1, c2, c3));
     }
     // z + x, z - x for any 64-bit z and x <= p; result is some 64-bit representative.
     // carry: z + x - 2^64 <= p - 1, so adding EPS cannot overflow again; borrow: z - x + 2^64 >= EPS.
@@ -367,7 +361,26 @@ struct A64S {
             : "r"((uint32_t)z), "r"((uint32_t)(z >> 32)), "r"((uint32_t)x), "r"((uint32_t)(x >> 32)));
         return pack(r0, r1);
     }
-    static __device__ __forceinline__ W add(W a, W b) { return canon(add_lazy(a, b)); } // canonical in/out
+    // canonical a + b for canonical a, b: "carry or sum >= p" -> sum += EPS mod 2^64 (same argument as in mul)
+    static __device__ __forceinline__ W add(W a, W b)
+    {
+        uint32_t r0, r1;
+        asm("{\n\t"
+            ".reg .u32 k;\n\t"
+            ".reg .pred q;\n\t"
+            "add.cc.u32      %0, %2, %4;\n\t"
+            "addc.cc.u32     %1, %3, %5;\n\t"
+            "addc.u32        k, 0, 0;\n\t"
+            "setp.eq.u32     q, %1, 0xFFFFFFFF;\n\t"
+            "setp.ne.and.u32 q, %0, 0, q;\n\t"
+            "setp.ne.or.u32  q, k, 0, q;\n\t"
+            "@q add.cc.u32   %0, %0, 0xFFFFFFFF;\n\t"
+            "@q addc.u32     %1, %1, 0;\n\t"
+            "}"
+            : "=&r"(r0), "=&r"(r1)
+            : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)));
+        return pack(r0, r1);
+    }
     static __device__ __forceinline__ void fwd_bf(W& z0, W& z1, Tw t, const Mod&)
     {
         const W x = mul(z1, t);
@@ -376,7 +389,7 @@ struct A64S {
     }
     static __device__ __forceinline__ void inv_bf(W& z0, W& z1, Tw t, const Mod&) // canonical in/out
     {
-        const W a = canon(add_lazy(z0, z1));
+        const W a = add(z0, z1);
         const W d = sub_lazy(z0, z1);
         z0 = a;
         z1 = mul(d, t);
