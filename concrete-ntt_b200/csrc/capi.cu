@@ -150,6 +150,7 @@ struct cntt_prime32_plan {
     uint2* d_inv;
     uint2* d_fwd_last; // last-pass layouts of the CTA kernel (ntt_engine.cuh, TwSrc); nullptr when unused
     uint2* d_inv_last;
+    TwHead<uint2> head_fwd, head_inv; // host copies of the first heap entries (by-value kernel parameter)
     Staging stg;
 };
 struct cntt_prime64_plan {
@@ -163,6 +164,8 @@ struct cntt_prime64_plan {
     void* d_inv;
     void* d_fwd_last; // as in cntt_prime32_plan
     void* d_inv_last;
+    alignas(16) unsigned char head_fwd[sizeof(TwHead<ulonglong2>)]; // TwHead<Tw> of the plan's class (same bytes for all)
+    alignas(16) unsigned char head_inv[sizeof(TwHead<ulonglong2>)];
     Staging stg;
 };
 
@@ -233,6 +236,9 @@ static int build_prime32(size_t n, uint32_t p, int device, cntt_prime32_plan** o
     m.big_q_m1 = (uint32_t)(big_q - 1);
     m.p_barrett = (uint32_t)((((uint64_t)1) << (big_q + 31)) / p); // prime32.rs:670-671
     pl->d_fwd = pl->d_inv = pl->d_fwd_last = pl->d_inv_last = nullptr;
+    std::memset(&pl->head_fwd, 0, sizeof(pl->head_fwd));
+    std::memset(&pl->head_inv, 0, sizeof(pl->head_inv));
+    for (size_t i = 0; i < n && i < sizeof(pl->head_fwd.e) / sizeof(uint2); i++) { pl->head_fwd.e[i] = hf[i]; pl->head_inv.e[i] = hi[i]; }
     cudaError_t e;
     if ((e = cudaMalloc(&pl->d_fwd, n * sizeof(uint2))) != cudaSuccess || (e = cudaMalloc(&pl->d_inv, n * sizeof(uint2))) != cudaSuccess ||
         (e = cudaMemcpy(pl->d_fwd, hf.data(), n * sizeof(uint2), cudaMemcpyHostToDevice)) != cudaSuccess ||
@@ -268,6 +274,7 @@ template <class A> static PlanDev<A> dev32(const cntt_prime32_plan* pl)
     PlanDev<A> d;
     d.logn = pl->logn; d.mod = pl->mod; d.tw_fwd = pl->d_fwd; d.tw_inv = pl->d_inv;
     d.tw_fwd_last = pl->d_fwd_last; d.tw_inv_last = pl->d_inv_last;
+    d.head_fwd = &pl->head_fwd; d.head_inv = &pl->head_inv;
     return d;
 }
 static cudaError_t run_ntt32(const cntt_prime32_plan* pl, uint32_t* d, size_t batch, bool fwd, cudaStream_t st)
@@ -402,6 +409,13 @@ static int build_prime64(size_t n, uint64_t p, int device, cntt_prime64_plan** o
         bytes = n * sizeof(ulonglong2);
         hf = sf.data(); hi = si.data();
     }
+    {
+        const size_t hb = bytes < sizeof(pl->head_fwd) ? bytes : sizeof(pl->head_fwd);
+        std::memset(pl->head_fwd, 0, sizeof(pl->head_fwd));
+        std::memset(pl->head_inv, 0, sizeof(pl->head_inv));
+        std::memcpy(pl->head_fwd, hf, hb);
+        std::memcpy(pl->head_inv, hi, hb);
+    }
     if ((e = cudaMalloc(&pl->d_fwd, bytes)) != cudaSuccess || (e = cudaMalloc(&pl->d_inv, bytes)) != cudaSuccess ||
         (e = cudaMemcpy(pl->d_fwd, hf, bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMemcpy(pl->d_inv, hi, bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
@@ -438,6 +452,8 @@ template <class A> static PlanDev<A> dev64(const cntt_prime64_plan* pl)
     d.tw_inv = reinterpret_cast<const typename A::Tw*>(pl->d_inv);
     d.tw_fwd_last = reinterpret_cast<const typename A::Tw*>(pl->d_fwd_last);
     d.tw_inv_last = reinterpret_cast<const typename A::Tw*>(pl->d_inv_last);
+    d.head_fwd = reinterpret_cast<const TwHead<typename A::Tw>*>(pl->head_fwd);
+    d.head_inv = reinterpret_cast<const TwHead<typename A::Tw>*>(pl->head_inv);
     return d;
 }
 static cudaError_t run_ntt64(const cntt_prime64_plan* pl, uint64_t* d, size_t batch, bool fwd, cudaStream_t st)

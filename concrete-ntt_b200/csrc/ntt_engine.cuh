@@ -42,6 +42,25 @@ template <class W> struct PadCfg { static constexpr int LOGROW = (sizeof(W) == 4
 template <class W> __host__ __device__ constexpr int padded_words(int n) { return n + (n >> PadCfg<W>::LOGROW); }
 template <class W> __device__ __forceinline__ int pad_idx(int i) { return i + (i >> PadCfg<W>::LOGROW); }
 
+// The first kHeadEntries entries of a heap table, passed BY VALUE as a __grid_constant__ kernel parameter: the
+// leading passes of a transform use the same few twiddles in every thread (pass 0) or in every thread of a
+// warp (middle passes whose blocks span >= 32 threads), so they are read from the constant bank -- as
+// immediate c[0x0][..] operands when the index is a compile-time value -- instead of through L1TEX, which was
+// the limiter of the u32 kernels (ncu r01: l1tex 82-86 % busy, a third of its requests were twiddle loads).
+// exchange buffers per polynomial for 64-bit words: 1 = one buffer and a second barrier per exchange.  The 64-bit
+// kernels are occupancy-limited by shared memory (2 x 17 KB per polynomial at N = 2048), and the extra warps
+// are worth more than the saved barrier (B200, Solinas N = 2048: fwd 1.172 -> 1.132 ms, inv 1.348 -> 1.161 ms).
+#ifndef CNTT_NBUF64
+#define CNTT_NBUF64 1
+#endif
+#ifndef CNTT_HEAD_MINS
+#define CNTT_HEAD_MINS 16
+#endif
+constexpr int kHeadLog = 8;
+constexpr int kHeadEntries = 1 << kHeadLog;
+template <class Tw> struct TwHead { Tw e[kHeadEntries * 8 / (sizeof(Tw) < 8 ? 8 : sizeof(Tw))]; }; // 2 KB of parameter space
+template <class Tw> constexpr int head_log() { return sizeof(Tw) <= 8 ? kHeadLog : kHeadLog - 1; }
+
 template <class A, int LOGN, int LOGR>
 struct Engine {
     typedef Geo<LOGN, LOGR> G;
@@ -75,7 +94,7 @@ struct Engine {
     }
     static constexpr bool kXor = any_wants_perm<0>() && !kPermFeasible;
     static constexpr int SMEM_WORDS = kXor ? N : padded_words<W>(N); // per polynomial, per buffer
-    static constexpr int NBUF = (P >= 3) ? 2 : 1;                    // ping-pong when >1 exchange
+    static constexpr int NBUF = (P >= 3 && !(sizeof(W) == 8 && CNTT_NBUF64 == 1)) ? 2 : 1; // ping-pong when >1 exchange
 
     template <int Q> static __device__ __forceinline__ void decomp(int tid, int& blk, int& o)
     {
@@ -160,12 +179,24 @@ struct Engine {
     struct TwSrc {
         const Tw* __restrict__ heap;
         const Tw* __restrict__ last; // this polynomial's (sub-block's) slice; unused when !kLastXp
+        const TwHead<Tw>* head;      // kernel-parameter copy of heap[0 .. kHeadEntries); nullptr: not available
     };
+    // may pass Q take its twiddles from the constant bank?  (only for whole transforms, nu0 == 1: the caller
+    // says so by passing a non-null `head`; the decision per pass is static)
+    template <int Q> static __host__ __device__ constexpr bool head_ok()
+    {
+        if constexpr (Q == P - 1 && P >= 2) return false;                                 // per-thread sub-trees
+        else if constexpr (Q == 0) return G::R1 <= head_log<Tw>();                        // indices < 2^R1
+        else return stride<Q>() >= CNTT_HEAD_MINS && (G::s0(Q) + LOGR) <= head_log<Tw>(); // (nearly) warp-uniform node
+    }
     static constexpr int LAST_WORDS = (R - 1) * T;             // entries of one sub-block's last-pass table
     template <int Q> static __device__ __forceinline__ Tw tw_at(const TwSrc& s, unsigned nu, int tid, int j, int g)
     {
         if constexpr (kLastXp && Q == P - 1) return __ldg(s.last + ((1 << j) - 1 + g) * T + tid);
-        else return __ldg(s.heap + (nu << j) + g);
+        else if constexpr (head_ok<Q>()) {
+            if (s.head != nullptr) return s.head->e[(nu << j) + g];
+            return __ldg(s.heap + (nu << j) + g);
+        } else return __ldg(s.heap + (nu << j) + g);
     }
     static __device__ __forceinline__ Tw ldtw(const Tw* __restrict__ tw, unsigned idx) { return __ldg(tw + idx); }
 

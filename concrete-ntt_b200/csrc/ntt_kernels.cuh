@@ -25,6 +25,9 @@ struct PlanDev {
     // nullptr when the class / size does not use them
     const typename A::Tw* tw_fwd_last;
     const typename A::Tw* tw_inv_last;
+    // host copies of heap[0 .. kHeadEntries) (entries beyond N are zero), passed by value to the CTA kernel
+    const TwHead<typename A::Tw>* head_fwd;
+    const TwHead<typename A::Tw>* head_inv;
 };
 
 // LOGR of the CTA kernel per word size, and whether the last-pass table exists for a transform size
@@ -91,10 +94,16 @@ __device__ __forceinline__ void load_contig(const W* __restrict__ src, W (&x)[R]
 // nvpoly "virtual polynomials" of N = 2^LOGN words each, contiguous.  With log_sub > 0 they are the
 // 2^log_sub contiguous sub-blocks of larger polynomials and virtual polynomial v uses the twiddle
 // sub-tree rooted at heap node (1 << log_sub) + (v mod 2^log_sub).
-template <class A, int LOGN, int LOGR, int GP, bool FWD>
+// HEAD: whole transforms (log_sub == 0); the leading passes read their twiddles from the by-value `head`.
+// NP: polynomials per thread group.  Every polynomial of a batch uses the same twiddles, so a thread that
+// carries NP polynomials loads each twiddle once for NP butterflies: the last pass reads R-1 table entries
+// per thread (2x the bytes of the data itself for u32 Shoup pairs), and L1TEX wavefronts -- 73 % of them
+// global loads, mostly twiddles -- were the limiter of the u32 kernels at NP = 1 (ncu r01).
+template <class A, int LOGN, int LOGR, int GP, bool FWD, bool HEAD, int NP>
 __global__ void __launch_bounds__(GP * Geo<LOGN, LOGR>::T)
 k_ntt_cta(const typename A::Tw* __restrict__ tw, const typename A::Tw* __restrict__ tw_last, const typename A::Mod m,
-          typename A::W* __restrict__ data, unsigned long long nvpoly, int log_sub)
+          typename A::W* __restrict__ data, unsigned long long nvpoly, int log_sub,
+          const __grid_constant__ TwHead<typename A::Tw> head)
 {
     typedef Engine<A, LOGN, LOGR> E;
     typedef typename A::W W;
@@ -104,29 +113,45 @@ k_ntt_cta(const typename A::Tw* __restrict__ tw, const typename A::Tw* __restric
 
     const int grp = (GP == 1) ? 0 : (int)(threadIdx.x / T);
     const int tid = (GP == 1) ? (int)threadIdx.x : (int)(threadIdx.x % T);
-    unsigned long long vp = (unsigned long long)blockIdx.x * GP + grp;
-    const bool active = vp < nvpoly;
-    if (!active) vp = nvpoly - 1; // keep the group in lock-step (barriers), discard its result
-    W* base = data + vp * (unsigned long long)N;
-    const unsigned sub = (unsigned)(vp & ((1ull << log_sub) - 1ull));
-    const unsigned nu0 = (1u << log_sub) + sub;
-    W* sm = sm_all + (size_t)grp * E::SMEM_WORDS * E::NBUF;
-    const typename E::TwSrc tws = {tw, tw_last + (size_t)sub * E::LAST_WORDS};
+    // group g owns polynomials [g NP, g NP + NP); with log_sub > 0 they are sub-blocks and NP == 1
+    const unsigned long long vp0 = ((unsigned long long)blockIdx.x * GP + grp) * NP;
+    W* base[NP];
+    bool active[NP];
+#pragma unroll
+    for (int np = 0; np < NP; np++) {
+        unsigned long long vp = vp0 + np;
+        active[np] = vp < nvpoly;
+        if (!active[np]) vp = nvpoly - 1; // keep the group in lock-step (barriers), discard its result
+        base[np] = data + vp * (unsigned long long)N;
+    }
+    const unsigned sub = HEAD ? 0u : (unsigned)((vp0 < nvpoly ? vp0 : nvpoly - 1) & ((1ull << log_sub) - 1ull));
+    const unsigned nu0 = HEAD ? 1u : (1u << log_sub) + sub;
+    W* sm = sm_all + (size_t)grp * NP * E::SMEM_WORDS * E::NBUF;
+    const typename E::TwSrc tws = {tw, tw_last + (size_t)sub * E::LAST_WORDS, HEAD ? &head : nullptr};
 
-    W x[1][R];
+    W x[NP][R];
     if constexpr (FWD) {
 #pragma unroll
-        for (int k = 0; k < R; k++) x[0][k] = base[tid + k * T];
-        E::template fwd<1>(x, sm, tws, nu0, tid, m);
+        for (int np = 0; np < NP; np++)
 #pragma unroll
-        for (int k = 0; k < R; k++) x[0][k] = A::canon_fwd(x[0][k], m);
-        if (active) store_contig<W, R>(base + E::elem_last(tid, 0), x[0]);
+            for (int k = 0; k < R; k++) x[np][k] = base[np][tid + k * T];
+        E::template fwd<NP>(x, sm, tws, nu0, tid, m);
+#pragma unroll
+        for (int np = 0; np < NP; np++) {
+#pragma unroll
+            for (int k = 0; k < R; k++) x[np][k] = A::canon_fwd(x[np][k], m);
+            if (active[np]) store_contig<W, R>(base[np] + E::elem_last(tid, 0), x[np]);
+        }
     } else {
-        load_contig<W, R>(base + E::elem_last(tid, 0), x[0]);
-        E::template inv<1>(x, sm, tws, nu0, tid, m);
-        if (active) {
 #pragma unroll
-            for (int k = 0; k < R; k++) base[tid + k * T] = A::canon_inv(x[0][k], m);
+        for (int np = 0; np < NP; np++) load_contig<W, R>(base[np] + E::elem_last(tid, 0), x[np]);
+        E::template inv<NP>(x, sm, tws, nu0, tid, m);
+#pragma unroll
+        for (int np = 0; np < NP; np++) {
+            if (active[np]) {
+#pragma unroll
+                for (int k = 0; k < R; k++) base[np][tid + k * T] = A::canon_inv(x[np][k], m);
+            }
         }
     }
 }
@@ -219,7 +244,7 @@ k_ntt_strided(const typename A::Tw* __restrict__ tw, const typename A::Mod m, ty
     W* base = data + (b << logn) + ((size_t)blk << (logn - s0)) + o;
     const unsigned nu = (1u << s0) + blk;
     W x[1][K];
-    const typename E::TwSrc tws = {tw, nullptr};
+    const typename E::TwSrc tws = {tw, nullptr, nullptr};
 #pragma unroll
     for (int k = 0; k < K; k++) x[0][k] = base[(size_t)k * bsub];
     if constexpr (FWD) {
@@ -260,26 +285,48 @@ k_pointwise(const typename A::Mod m, typename A::W* __restrict__ dst, const type
 }
 
 // ---- launchers --------------------------------------------------------------------------------
-template <class A, int LOGN, bool FWD>
-cudaError_t launch_cta_one(const PlanDev<A>& pl, typename A::W* data, unsigned long long nvpoly, int log_sub, cudaStream_t st)
+#ifndef CNTT_NP32
+#define CNTT_NP32 1
+#endif
+template <class A, int LOGN, bool FWD, int NP>
+cudaError_t launch_cta_np(const PlanDev<A>& pl, typename A::W* data, unsigned long long nvpoly, int log_sub, cudaStream_t st)
 {
     constexpr int LOGR = CtaCfg<A, LOGN>::LOGR;
     typedef typename CtaCfg<A, LOGN>::E E;
     constexpr int T = E::T;
     constexpr int GP = T >= 128 ? 1 : 128 / T;
-    const size_t smem = (size_t)GP * E::NBUF * E::SMEM_WORDS * sizeof(typename A::W);
-    auto kern = k_ntt_cta<A, LOGN, LOGR, GP, FWD>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    const unsigned long long nblk = (nvpoly + GP - 1) / GP;
+    const size_t smem = (size_t)GP * NP * E::NBUF * E::SMEM_WORDS * sizeof(typename A::W);
+    const unsigned long long ngrp = (nvpoly + NP - 1) / NP;
+    const unsigned long long nblk = (ngrp + GP - 1) / GP;
     if (nblk == 0) return cudaSuccess;
     if (nblk > 0x7fffffffull) return cudaErrorInvalidValue;
     const typename A::Tw* last = FWD ? pl.tw_fwd_last : pl.tw_inv_last;
     if (E::kLastXp && last == nullptr) return cudaErrorInvalidValue; // plan built without its last-pass table
-    kern<<<(unsigned)nblk, GP * T, smem, st>>>(FWD ? pl.tw_fwd : pl.tw_inv, last, pl.mod, data, nvpoly, log_sub);
-    return cudaGetLastError();
+    const TwHead<typename A::Tw>* head = FWD ? pl.head_fwd : pl.head_inv;
+    auto launch = [&](auto kern, const TwHead<typename A::Tw>& h) -> cudaError_t {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<(unsigned)nblk, GP * T, smem, st>>>(FWD ? pl.tw_fwd : pl.tw_inv, last, pl.mod, data, nvpoly, log_sub, h);
+        return cudaGetLastError();
+    };
+    if (log_sub == 0 && head != nullptr) return launch(k_ntt_cta<A, LOGN, LOGR, GP, FWD, true, NP>, *head);
+    static const TwHead<typename A::Tw> none = {};
+    if constexpr (NP == 1) return launch(k_ntt_cta<A, LOGN, LOGR, GP, FWD, false, 1>, none);
+    else return cudaErrorInvalidValue; // sub-block launches carry one block per group
+}
+// u32 whole transforms carry CNTT_NP32 polynomials per thread group (twiddle reuse); sub-blocks of a large
+// transform, 64-bit words and tiny batches carry one.
+template <class A, int LOGN, bool FWD>
+cudaError_t launch_cta_one(const PlanDev<A>& pl, typename A::W* data, unsigned long long nvpoly, int log_sub, cudaStream_t st)
+{
+    constexpr int NPW = (sizeof(typename A::W) == 4 && CtaCfg<A, LOGN>::E::P >= 2) ? CNTT_NP32 : 1;
+    if constexpr (NPW > 1) {
+        const TwHead<typename A::Tw>* head = FWD ? pl.head_fwd : pl.head_inv;
+        if (log_sub == 0 && head != nullptr && nvpoly >= 2ull * NPW * 148ull) return launch_cta_np<A, LOGN, FWD, NPW>(pl, data, nvpoly, log_sub, st);
+    }
+    return launch_cta_np<A, LOGN, FWD, 1>(pl, data, nvpoly, log_sub, st);
 }
 
 template <class A, bool FWD>
