@@ -21,6 +21,25 @@ if which == "ntt64":
     for _ in range(reps):
         plan.fwd(d)
         plan.inv(d)
+elif which == "ntt64shoup":
+    p = cntt.prime.largest_prime_in_arithmetic_progression64(1 << 17, 1, 1 << 61, 1 << 62)
+    plan = cntt.prime64.Plan.try_new(n, p)
+    d = torch.randint(0, 2**61, (batch, n), dtype=torch.int64, device="cuda", generator=g)
+    for _ in range(reps):
+        plan.fwd(d)
+        plan.inv(d)
+elif which in ("pointwise32", "pointwise64"):
+    if which == "pointwise32":
+        plan = cntt.prime32.Plan.try_new(n, 1062862849)
+        mk = lambda: torch.randint(0, 1062862849, (batch, n), dtype=torch.int32, device="cuda", generator=g)
+    else:
+        plan = cntt.prime64.Plan.try_new(n, cntt.prime64.Solinas.P)
+        mk = lambda: torch.randint(0, 2**62, (batch, n), dtype=torch.int64, device="cuda", generator=g)
+    a, b, c = mk(), mk(), mk()
+    for _ in range(reps):
+        plan.mul_assign_normalize(a, b)
+        plan.normalize(a)
+        plan.mul_accumulate(c, a, b)
 elif which == "ntt32":
     plan = cntt.prime32.Plan.try_new(n, 1062862849)
     d = torch.randint(0, 1062862849, (batch, n), dtype=torch.int32, device="cuda", generator=g)
