@@ -747,8 +747,9 @@ CNTT_API int cntt_native_inv(const cntt_native_plan* pl, void* d_value, uint32_t
     return CNTT_OK;
 }
 
-// Unfused pipeline (any N the plan supports): residue planes live in a stream-ordered scratch
-// allocation, processed in batch chunks so the scratch stays bounded.
+// Pipelines through residue planes (N > 4096): the planes live in a stream-ordered scratch allocation, processed in
+// batch chunks so the scratch stays bounded.  4096 < N <= 32768 (every size the native plans accept beyond the fused
+// kernel) runs the three-kernel path of native_large.cuh; the plan-API composition below it is the generic fallback.
 static cudaError_t native_polymul_unfused(const cntt_native_plan* pl, void* prod, const void* lhs, const void* rhs, size_t batch, cudaStream_t st)
 {
     const size_t n = pl->n;
@@ -769,6 +770,10 @@ static cudaError_t native_polymul_unfused(const cntt_native_plan* pl, void* prod
         const char* l = static_cast<const char*>(lhs) + b0 * n * wb;
         const char* r = static_cast<const char*>(rhs) + b0 * n * wb;
         char* o = static_cast<char*>(prod) + b0 * n * wb;
+        if (native_large_supported(pl->dev.logn)) { // three fused kernels around the planes (native_large.cuh)
+            if ((e = native_polymul_large(pl->dev, o, l, r, nb, L, R, st)) != cudaSuccess) break;
+            continue;
+        }
         if ((e = native_fwd_impl(pl, l, L, nb, false, st)) != cudaSuccess) break;
         if ((e = native_fwd_impl(pl, r, R, nb, binary, st)) != cudaSuccess) break;
         for (int k = 0; k < np && e == cudaSuccess; k++)

@@ -65,4 +65,10 @@ cudaError_t native_fused_build_last(int logn, const uint2* heap, uint2* out, cud
 cudaError_t native_polymul_fused(const NativePlanDev& pl, void* prod, const void* lhs, const void* rhs, size_t batch,
                                  cudaStream_t st);
 
+// three-kernel polymul for 4096 < N <= 32768 (native_large.cuh).  planes_l / planes_r: nprimes planes of batch * n
+// u32 each (scratch).  Returns cudaErrorNotSupported for other sizes.
+bool native_large_supported(int logn);
+cudaError_t native_polymul_large(const NativePlanDev& pl, void* prod, const void* lhs, const void* rhs, size_t batch,
+                                 uint32_t* planes_l, uint32_t* planes_r, cudaStream_t st);
+
 } // namespace cntt

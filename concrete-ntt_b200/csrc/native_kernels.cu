@@ -196,3 +196,24 @@ cudaError_t native_polymul_fused(const NativePlanDev& pl, void* prod, const void
     }
 }
 } // namespace cntt
+
+#include "native_large.cuh"
+
+namespace cntt {
+bool native_large_supported(int logn) { return logn >= kLargeMinLogN && logn <= kLargeMaxLogN; }
+cudaError_t native_polymul_large(const NativePlanDev& pl, void* prod, const void* lhs, const void* rhs, size_t batch,
+                                 uint32_t* planes_l, uint32_t* planes_r, cudaStream_t st)
+{
+    if (batch == 0) return cudaSuccess;
+    if (!native_large_supported(pl.logn)) return cudaErrorNotSupported;
+    switch (pl.kind) {
+    case NK_NATIVE32: return launch_large_kind<NK_NATIVE32>(pl, prod, lhs, rhs, batch, planes_l, planes_r, st);
+    case NK_NATIVE64: return launch_large_kind<NK_NATIVE64>(pl, prod, lhs, rhs, batch, planes_l, planes_r, st);
+    case NK_NATIVE128: return launch_large_kind<NK_NATIVE128>(pl, prod, lhs, rhs, batch, planes_l, planes_r, st);
+    case NK_BINARY32: return launch_large_kind<NK_BINARY32>(pl, prod, lhs, rhs, batch, planes_l, planes_r, st);
+    case NK_BINARY64: return launch_large_kind<NK_BINARY64>(pl, prod, lhs, rhs, batch, planes_l, planes_r, st);
+    case NK_BINARY128: return launch_large_kind<NK_BINARY128>(pl, prod, lhs, rhs, batch, planes_l, planes_r, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+} // namespace cntt

@@ -106,14 +106,16 @@ def test_crt_on_arbitrary_residues(cntt, oracle, torch_cuda, bits):
         assert (host(out, wdt) == ref).all(), (bits, binary)
 
 
-@pytest.mark.parametrize("n", [8192, 32768])
+@pytest.mark.parametrize("n", [8192, 16384, 32768])
 def test_native_large_n(cntt, oracle, torch_cuda, n):
-    """Reference maximum is 32768 (P1 - 1 = 2^16 * odd); 65536 -> None like the reference."""
+    """4096 < N <= 32768: the three-kernel path (native_large.cuh), every kind, ragged batch of 3.
+    Reference maximum is 32768 (P1 - 1 = 2^16 * odd); 65536 -> None like the reference."""
     g = rng(n)
-    for bits, binary in [(64, False), (64, True), (32, False)]:
+    kinds = [(64, False), (64, True), (32, False), (32, True)] + ([(128, False), (128, True)] if n <= 16384 else [(128, True)])
+    for bits, binary in kinds:
         gp, op = plan_pair(cntt, oracle, n, bits, binary)
-        lhs = rand_words(g, bits, (2, n))
-        rhs = make_rhs(g, bits, (2, n), binary)
+        lhs = rand_words(g, bits, (3, n))
+        rhs = make_rhs(g, bits, (3, n), binary)
         dl, dr = dev(torch_cuda, lhs), dev(torch_cuda, rhs)
         dp = torch_cuda.empty_like(dl)
         gp.negacyclic_polymul(dp, dl, dr)
