@@ -5,6 +5,7 @@ Module layout mirrors the reference crate (src/lib.rs:83-111):
     prime32.Plan, prime64.Plan, prime64.Solinas
     native32.Plan32, native64.Plan32, native128.Plan32
     native_binary32.Plan32, native_binary64.Plan32, native_binary128.Plan32
+    product.Plan, product.FwdMode, product.InvMode
     prime.is_prime64, prime.largest_prime_in_arithmetic_progression64
 
 Import with ``importlib.import_module("concrete-ntt_b200")`` (the directory name is not an identifier).
@@ -58,6 +59,8 @@ native128 = _module("native128", Plan32=_native(128, False))
 native_binary32 = _module("native_binary32", Plan32=_native(32, True))
 native_binary64 = _module("native_binary64", Plan32=_native(64, True))
 native_binary128 = _module("native_binary128", Plan32=_native(128, True))
+product = _module("product", Plan=type("Plan", (_plans.ProductPlan,), {"__doc__": "product::Plan"}),
+                  FwdMode=_plans.FwdMode, InvMode=_plans.InvMode)
 prime = _module("prime", is_prime64=_is_prime64, largest_prime_in_arithmetic_progression64=_largest_prime)
 roots = _module("roots", find_primitive_root64=_find_primitive_root64)
 

@@ -55,6 +55,18 @@ SIGNATURES.update({
     "cntt_native_inv": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "cntt_native_polymul": (_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
     "cntt_native_polymul_host": (_int, [_vp, _vp, _vp, _vp, _sz, _sz]),
+    "cntt_product_plan_new": (_int, [_sz, _u64, C.POINTER(_u64), _sz, _int, C.POINTER(_vp)]),
+    "cntt_product_plan_free": (None, [_vp]),
+    "cntt_product_ntt_size": (_sz, [_vp]),
+    "cntt_product_modulus": (_u64, [_vp]),
+    "cntt_product_ntt_domain_len": (_sz, [_vp]),
+    "cntt_product_num_primes": (_int, [_vp, C.POINTER(_int), C.POINTER(_int)]),
+    "cntt_product_prime": (_u64, [_vp, _int]),
+    "cntt_product_fwd": (_int, [_vp, _vp, _vp, _int, _u64, _sz, _vp]),
+    "cntt_product_inv": (_int, [_vp, _vp, _vp, _int, _sz, _vp]),
+    "cntt_product_mul_assign_normalize": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "cntt_product_normalize": (_int, [_vp, _vp, _sz, _vp]),
+    "cntt_product_mul_accumulate": (_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
 })
 
 _lib = None

@@ -835,3 +835,197 @@ CNTT_API int cntt_native_polymul_host(const cntt_native_plan* pl, void* h_prod, 
     CU(cudaStreamSynchronize(stg.stream2));
     return CNTT_OK;
 }
+
+// ---- product::Plan (src/product.rs) --------------------------------------------------------------------------
+#include "product_kernels.cuh"
+
+struct cntt_product_plan {
+    size_t n;
+    uint64_t modulus;
+    int device;
+    ProductConsts c;
+    cntt_prime32_plan* p32[kProductMaxPrimes];
+    cntt_prime64_plan* p64[kProductMaxPrimes];
+};
+
+static void product_free(cntt_product_plan* pl)
+{
+    for (int k = 0; k < kProductMaxPrimes; k++) {
+        if (pl->p32[k]) cntt_prime32_plan_free(pl->p32[k]);
+        if (pl->p64[k]) cntt_prime64_plan_free(pl->p64[k]);
+    }
+    delete pl;
+}
+
+// try_new (product.rs:152-251): None (a status != OK) for odd n, zero or duplicate factors, a product of the
+// factors (1s skipped, checked multiplication) different from `modulus`, or any factor rejected by its prime plan.
+CNTT_API int cntt_product_plan_new(size_t n, uint64_t modulus, const uint64_t* factors, size_t nfactors, int device, cntt_product_plan** out)
+{
+    if (!out || (!factors && nfactors)) return CNTT_NULL_POINTER;
+    *out = nullptr;
+    if (n % 2 != 0) return CNTT_INVALID_SIZE;
+    std::vector<uint64_t> pr(factors, factors + nfactors);
+    std::sort(pr.begin(), pr.end());
+    uint64_t prev = 0;
+    for (uint64_t f : pr) {
+        if (f == prev) return CNTT_INVALID_MODULUS; // zero or duplicate
+        prev = f;
+    }
+    pr.erase(pr.begin(), std::find_if(pr.begin(), pr.end(), [](uint64_t f) { return f != 1; }));
+    unsigned __int128 prod = 1;
+    for (uint64_t f : pr) {
+        prod *= f;
+        if (prod >> 64) return CNTT_INVALID_MODULUS; // checked_mul overflow
+    }
+    if ((uint64_t)prod != modulus) return CNTT_INVALID_MODULUS;
+    if (pr.size() > (size_t)kProductMaxPrimes) return CNTT_UNSUPPORTED; // cannot happen for accepted sizes
+    cntt_product_plan* pl = new cntt_product_plan();
+    pl->n = n; pl->modulus = modulus; pl->device = device;
+    for (int k = 0; k < kProductMaxPrimes; k++) { pl->p32[k] = nullptr; pl->p64[k] = nullptr; }
+    ProductConsts& c = pl->c;
+    std::memset(&c, 0, sizeof(c));
+    c.modulus = modulus; c.n = n;
+    for (uint64_t f : pr) {
+        int st;
+        if (f < (1ull << 32)) st = build_prime32(n, (uint32_t)f, device, &pl->p32[c.count32]);
+        else st = build_prime64(n, f, device, &pl->p64[c.count64]);
+        if (st != CNTT_OK) { product_free(pl); return st; }
+        const int j = c.count32 + c.count64;
+        c.p[j] = f;
+        c.recip[j] = ~0ull / f;
+        host::Fp fp(f);
+        for (int i = 0; i < j; i++) c.inv[j][i] = fp.inv(c.p[i] % f);
+        if (f < (1ull << 32)) c.count32++; else c.count64++;
+    }
+    c.domain_len = (n / 2) * c.count32 + n * c.count64;
+    *out = pl;
+    return CNTT_OK;
+}
+CNTT_API void cntt_product_plan_free(cntt_product_plan* pl) { if (pl) product_free(pl); }
+CNTT_API size_t cntt_product_ntt_size(const cntt_product_plan* pl) { return pl ? pl->n : 0; }
+CNTT_API uint64_t cntt_product_modulus(const cntt_product_plan* pl) { return pl ? pl->modulus : 0; }
+CNTT_API size_t cntt_product_ntt_domain_len(const cntt_product_plan* pl) { return pl ? (size_t)pl->c.domain_len : 0; }
+CNTT_API int cntt_product_num_primes(const cntt_product_plan* pl, int* count32, int* count64)
+{
+    if (!pl) return CNTT_NULL_POINTER;
+    if (count32) *count32 = pl->c.count32;
+    if (count64) *count64 = pl->c.count64;
+    return CNTT_OK;
+}
+CNTT_API uint64_t cntt_product_prime(const cntt_product_plan* pl, int i) { return (pl && i >= 0 && i < pl->c.count32 + pl->c.count64) ? pl->c.p[i] : 0; }
+
+static cudaError_t run_ntt32_strided(const cntt_prime32_plan* pl, uint32_t* d, size_t batch, size_t stride, bool fwd, cudaStream_t st)
+{
+    switch (pl->cls) {
+    case C32_L4: return ntt_strided_A32L4(dev32<A32L4>(pl), d, batch, stride, fwd, st);
+    case C32_L2: return ntt_strided_A32L2(dev32<A32L2>(pl), d, batch, stride, fwd, st);
+    default: return ntt_strided_A32G(dev32<A32G>(pl), d, batch, stride, fwd, st);
+    }
+}
+static cudaError_t run_ntt64_strided(const cntt_prime64_plan* pl, uint64_t* d, size_t batch, size_t stride, bool fwd, cudaStream_t st)
+{
+    switch (pl->cls) {
+    case C64_L4: return ntt_strided_A64L4(dev64<A64L4>(pl), d, batch, stride, fwd, st);
+    case C64_L2: return ntt_strided_A64L2(dev64<A64L2>(pl), d, batch, stride, fwd, st);
+    case C64_S: return ntt_strided_A64S(dev64<A64S>(pl), d, batch, stride, fwd, st);
+    default: return ntt_strided_A64G(dev64<A64G>(pl), d, batch, stride, fwd, st);
+    }
+}
+static cudaError_t run_pw32_strided(const cntt_prime32_plan* pl, int op, uint32_t* dst, const uint32_t* a, const uint32_t* b, size_t batch, size_t stride, cudaStream_t st)
+{
+    switch (pl->cls) {
+    case C32_L4: return pointwise_strided_A32L4(dev32<A32L4>(pl), op, dst, a, b, batch, stride, st);
+    case C32_L2: return pointwise_strided_A32L2(dev32<A32L2>(pl), op, dst, a, b, batch, stride, st);
+    default: return pointwise_strided_A32G(dev32<A32G>(pl), op, dst, a, b, batch, stride, st);
+    }
+}
+static cudaError_t run_pw64_strided(const cntt_prime64_plan* pl, int op, uint64_t* dst, const uint64_t* a, const uint64_t* b, size_t batch, size_t stride, cudaStream_t st)
+{
+    switch (pl->cls) {
+    case C64_L4: return pointwise_strided_A64L4(dev64<A64L4>(pl), op, dst, a, b, batch, stride, st);
+    case C64_L2: return pointwise_strided_A64L2(dev64<A64L2>(pl), op, dst, a, b, batch, stride, st);
+    case C64_S: return pointwise_strided_A64S(dev64<A64S>(pl), op, dst, a, b, batch, stride, st);
+    default: return pointwise_strided_A64G(dev64<A64G>(pl), op, dst, a, b, batch, stride, st);
+    }
+}
+// the per-prime transforms of every plane of the batch (planes of one polynomial are domain_len u64 apart)
+static cudaError_t product_planes_ntt(const cntt_product_plan* pl, uint64_t* ntt, size_t batch, bool fwd, cudaStream_t st)
+{
+    const ProductConsts& c = pl->c;
+    cudaError_t e;
+    uint32_t* d32 = reinterpret_cast<uint32_t*>(ntt);
+    uint64_t* d64 = ntt + (c.n / 2) * c.count32;
+    for (int k = 0; k < c.count32; k++)
+        if ((e = run_ntt32_strided(pl->p32[k], d32 + (size_t)k * c.n, batch, 2 * (size_t)c.domain_len, fwd, st)) != cudaSuccess) return e;
+    for (int k = 0; k < c.count64; k++)
+        if ((e = run_ntt64_strided(pl->p64[k], d64 + (size_t)k * c.n, batch, (size_t)c.domain_len, fwd, st)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+static cudaError_t product_pointwise(const cntt_product_plan* pl, int op, uint64_t* dst, const uint64_t* a, const uint64_t* b, size_t batch, cudaStream_t st)
+{
+    const ProductConsts& c = pl->c;
+    cudaError_t e;
+    const size_t off64 = (c.n / 2) * c.count32;
+    for (int k = 0; k < c.count32; k++) {
+        const size_t o = (size_t)k * c.n;
+        if ((e = run_pw32_strided(pl->p32[k], op, reinterpret_cast<uint32_t*>(dst) + o, a ? reinterpret_cast<const uint32_t*>(a) + o : nullptr,
+                                  b ? reinterpret_cast<const uint32_t*>(b) + o : nullptr, batch, 2 * (size_t)c.domain_len, st)) != cudaSuccess) return e;
+    }
+    for (int k = 0; k < c.count64; k++) {
+        const size_t o = off64 + (size_t)k * c.n;
+        if ((e = run_pw64_strided(pl->p64[k], op, dst + o, a ? a + o : nullptr, b ? b + o : nullptr, batch, (size_t)c.domain_len, st)) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// fwd (product.rs:272-353): d_ntt[batch * domain_len] <- d_standard[batch * n]; mode 0 = FwdMode::Generic,
+// 1 = FwdMode::Bounded(bound)
+CNTT_API int cntt_product_fwd(const cntt_product_plan* pl, uint64_t* d_ntt, const uint64_t* d_standard, int mode, uint64_t bound, size_t batch, void* stream)
+{
+    if (!pl || ((!d_ntt || !d_standard) && batch)) return CNTT_NULL_POINTER;
+    if (mode != PF_GENERIC && mode != PF_BOUNDED) return CNTT_UNSUPPORTED;
+    if (batch == 0 || pl->c.count32 + pl->c.count64 == 0) return CNTT_OK;
+    GUARD(pl->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned long long ncoef = (unsigned long long)batch * pl->n;
+    k_product_reduce<<<(unsigned)((ncoef + 255) / 256), 256, 0, st>>>(pl->c, d_ntt, d_standard, mode, bound, ncoef);
+    CU(cudaGetLastError());
+    CU(product_planes_ntt(pl, d_ntt, batch, true, st));
+    return CNTT_OK;
+}
+// inv (product.rs:355-880): d_standard[batch * n] <- (or += mod modulus) lift of the inverse transforms of d_ntt, which
+// is clobbered like the reference's `ntt: &mut [u64]`; mode 0 = InvMode::Replace, 1 = InvMode::Accumulate
+CNTT_API int cntt_product_inv(const cntt_product_plan* pl, uint64_t* d_standard, uint64_t* d_ntt, int mode, size_t batch, void* stream)
+{
+    if (!pl || ((!d_ntt || !d_standard) && batch)) return CNTT_NULL_POINTER;
+    if (mode != PI_REPLACE && mode != PI_ACCUMULATE) return CNTT_UNSUPPORTED;
+    if (batch == 0) return CNTT_OK;
+    GUARD(pl->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(product_planes_ntt(pl, d_ntt, batch, false, st));
+    const unsigned long long ncoef = (unsigned long long)batch * pl->n;
+    k_product_crt<<<(unsigned)((ncoef + 255) / 256), 256, 0, st>>>(pl->c, d_standard, d_ntt, mode, ncoef);
+    CU(cudaGetLastError());
+    return CNTT_OK;
+}
+CNTT_API int cntt_product_mul_assign_normalize(const cntt_product_plan* pl, uint64_t* d_lhs, const uint64_t* d_rhs, size_t batch, void* stream)
+{
+    if (!pl || ((!d_lhs || !d_rhs) && batch)) return CNTT_NULL_POINTER;
+    GUARD(pl->device);
+    CU(product_pointwise(pl, OP_MUL_ASSIGN_NORMALIZE, d_lhs, d_rhs, nullptr, batch, (cudaStream_t)stream));
+    return CNTT_OK;
+}
+CNTT_API int cntt_product_normalize(const cntt_product_plan* pl, uint64_t* d_values, size_t batch, void* stream)
+{
+    if (!pl || (!d_values && batch)) return CNTT_NULL_POINTER;
+    GUARD(pl->device);
+    CU(product_pointwise(pl, OP_NORMALIZE, d_values, nullptr, nullptr, batch, (cudaStream_t)stream));
+    return CNTT_OK;
+}
+CNTT_API int cntt_product_mul_accumulate(const cntt_product_plan* pl, uint64_t* d_acc, const uint64_t* d_lhs, const uint64_t* d_rhs, size_t batch, void* stream)
+{
+    if (!pl || ((!d_acc || !d_lhs || !d_rhs) && batch)) return CNTT_NULL_POINTER;
+    GUARD(pl->device);
+    CU(product_pointwise(pl, OP_MUL_ACCUMULATE, d_acc, d_lhs, d_rhs, batch, (cudaStream_t)stream));
+    return CNTT_OK;
+}

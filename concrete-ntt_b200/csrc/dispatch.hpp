@@ -7,6 +7,10 @@ namespace cntt {
 
 #define CNTT_DECLARE_CLASS(A)                                                                                      \
     cudaError_t ntt_##A(const PlanDev<A>& pl, typename A::W* data, size_t batch, bool fwd, cudaStream_t st);        \
+    cudaError_t ntt_strided_##A(const PlanDev<A>& pl, typename A::W* data, size_t batch, size_t poly_stride, bool fwd,    \
+                                cudaStream_t st);                                                                   \
+    cudaError_t pointwise_strided_##A(const PlanDev<A>& pl, int op, typename A::W* dst, const typename A::W* a,    \
+                                      const typename A::W* b, size_t batch, size_t poly_stride, cudaStream_t st);  \
     cudaError_t pointwise_##A(const PlanDev<A>& pl, int op, typename A::W* dst, const typename A::W* a,            \
                               const typename A::W* b, size_t nwords, cudaStream_t st);                             \
     bool uses_last_##A(int logn);                                                                                  \
@@ -29,6 +33,21 @@ CNTT_DECLARE_CLASS(A64G)
     cudaError_t ntt_##A(const PlanDev<A>& pl, typename A::W* data, size_t batch, bool fwd, cudaStream_t st)         \
     {                                                                                                              \
         return fwd ? launch_ntt<A, true>(pl, data, batch, st) : launch_ntt<A, false>(pl, data, batch, st);         \
+    }                                                                                                              \
+    cudaError_t ntt_strided_##A(const PlanDev<A>& pl, typename A::W* data, size_t batch, size_t poly_stride, bool fwd,    \
+                                cudaStream_t st)                                                                    \
+    {                                                                                                              \
+        return fwd ? launch_ntt<A, true>(pl, data, batch, st, poly_stride) : launch_ntt<A, false>(pl, data, batch, st, poly_stride); \
+    }                                                                                                              \
+    cudaError_t pointwise_strided_##A(const PlanDev<A>& pl, int op, typename A::W* dst, const typename A::W* a,    \
+                                      const typename A::W* b, size_t batch, size_t poly_stride, cudaStream_t st)   \
+    {                                                                                                              \
+        switch (op) {                                                                                              \
+        case OP_MUL_ASSIGN_NORMALIZE: return launch_pointwise_strided<A, OP_MUL_ASSIGN_NORMALIZE>(pl, dst, a, b, batch, poly_stride, st); \
+        case OP_NORMALIZE: return launch_pointwise_strided<A, OP_NORMALIZE>(pl, dst, a, b, batch, poly_stride, st); \
+        case OP_MUL_ACCUMULATE: return launch_pointwise_strided<A, OP_MUL_ACCUMULATE>(pl, dst, a, b, batch, poly_stride, st); \
+        default: return cudaErrorInvalidValue;                                                                     \
+        }                                                                                                          \
     }                                                                                                              \
     cudaError_t pointwise_##A(const PlanDev<A>& pl, int op, typename A::W* dst, const typename A::W* a,            \
                               const typename A::W* b, size_t nwords, cudaStream_t st)                              \

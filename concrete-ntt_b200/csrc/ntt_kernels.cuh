@@ -102,7 +102,7 @@ __device__ __forceinline__ void load_contig(const W* __restrict__ src, W (&x)[R]
 template <class A, int LOGN, int LOGR, int GP, bool FWD, bool HEAD, int NP>
 __global__ void __launch_bounds__(GP * Geo<LOGN, LOGR>::T)
 k_ntt_cta(const typename A::Tw* __restrict__ tw, const typename A::Tw* __restrict__ tw_last, const typename A::Mod m,
-          typename A::W* __restrict__ data, unsigned long long nvpoly, int log_sub,
+          typename A::W* __restrict__ data, unsigned long long nvpoly, int log_sub, unsigned long long poly_stride,
           const __grid_constant__ TwHead<typename A::Tw> head)
 {
     typedef Engine<A, LOGN, LOGR> E;
@@ -122,7 +122,9 @@ k_ntt_cta(const typename A::Tw* __restrict__ tw, const typename A::Tw* __restric
         unsigned long long vp = vp0 + np;
         active[np] = vp < nvpoly;
         if (!active[np]) vp = nvpoly - 1; // keep the group in lock-step (barriers), discard its result
-        base[np] = data + vp * (unsigned long long)N;
+        // polynomial (vp >> log_sub) starts at poly_stride words per polynomial (product plans interleave planes;
+        // everywhere else poly_stride == N << log_sub and this is vp * N), sub-block (vp mod 2^log_sub) inside it
+        base[np] = data + (vp >> log_sub) * poly_stride + (vp & ((1ull << log_sub) - 1ull)) * (unsigned long long)N;
     }
     const unsigned sub = HEAD ? 0u : (unsigned)((vp0 < nvpoly ? vp0 : nvpoly - 1) & ((1ull << log_sub) - 1ull));
     const unsigned nu0 = HEAD ? 1u : (1u << log_sub) + sub;
@@ -227,7 +229,7 @@ cudaError_t launch_build_last(int logn, const typename A::Tw* heap, typename A::
 template <class A, int LOGK, bool FWD>
 __global__ void __launch_bounds__(256)
 k_ntt_strided(const typename A::Tw* __restrict__ tw, const typename A::Mod m, typename A::W* __restrict__ data,
-              unsigned long long nitems, int logn, int s0)
+              unsigned long long nitems, int logn, int s0, unsigned long long poly_stride)
 {
     typedef Engine<A, LOGK, LOGK> E; // a single register pass of LOGK levels
     typedef typename A::W W;
@@ -241,7 +243,7 @@ k_ntt_strided(const typename A::Tw* __restrict__ tw, const typename A::Mod m, ty
     const unsigned blk = it >> log_bsub;
     const unsigned o = it & ((1u << log_bsub) - 1u);
     const size_t bsub = (size_t)1 << log_bsub;
-    W* base = data + (b << logn) + ((size_t)blk << (logn - s0)) + o;
+    W* base = data + b * poly_stride + ((size_t)blk << (logn - s0)) + o;
     const unsigned nu = (1u << s0) + blk;
     W x[1][K];
     const typename E::TwSrc tws = {tw, nullptr, nullptr};
@@ -284,12 +286,37 @@ k_pointwise(const typename A::Mod m, typename A::W* __restrict__ dst, const type
     }
 }
 
+// Same streams when the polynomials of a batch are poly_stride words apart (product plans: the planes of one
+// polynomial are interleaved with the other primes' planes).  blockIdx.y = polynomial.
+template <class A, int OP>
+__global__ void __launch_bounds__(256)
+k_pointwise_strided(const typename A::Mod m, typename A::W* __restrict__ dst, const typename A::W* __restrict__ a,
+                    const typename A::W* __restrict__ b, unsigned nvec_per_poly, unsigned long long poly_stride)
+{
+    typedef typename A::W W;
+    constexpr int PER = 16 / (int)sizeof(W);
+    const unsigned long long off = (unsigned long long)blockIdx.y * poly_stride;
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec_per_poly; v += gridDim.x * blockDim.x) {
+        W d[PER], xa[PER], xb[PER];
+        load_contig<W, PER>(dst + off + (size_t)v * PER, d);
+        if constexpr (OP != OP_NORMALIZE) load_contig<W, PER>(a + off + (size_t)v * PER, xa);
+        if constexpr (OP == OP_MUL_ACCUMULATE) load_contig<W, PER>(b + off + (size_t)v * PER, xb);
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            if constexpr (OP == OP_MUL_ASSIGN_NORMALIZE) d[i] = A::mul_norm(d[i], xa[i], m);
+            else if constexpr (OP == OP_NORMALIZE) d[i] = A::norm(d[i], m);
+            else d[i] = A::mul_acc(d[i], xa[i], xb[i], m);
+        }
+        store_contig<W, PER>(dst + off + (size_t)v * PER, d);
+    }
+}
+
 // ---- launchers --------------------------------------------------------------------------------
 #ifndef CNTT_NP32
 #define CNTT_NP32 1
 #endif
 template <class A, int LOGN, bool FWD, int NP>
-cudaError_t launch_cta_np(const PlanDev<A>& pl, typename A::W* data, unsigned long long nvpoly, int log_sub, cudaStream_t st)
+cudaError_t launch_cta_np(const PlanDev<A>& pl, typename A::W* data, unsigned long long nvpoly, int log_sub, size_t poly_stride, cudaStream_t st)
 {
     constexpr int LOGR = CtaCfg<A, LOGN>::LOGR;
     typedef typename CtaCfg<A, LOGN>::E E;
@@ -308,7 +335,7 @@ cudaError_t launch_cta_np(const PlanDev<A>& pl, typename A::W* data, unsigned lo
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        kern<<<(unsigned)nblk, GP * T, smem, st>>>(FWD ? pl.tw_fwd : pl.tw_inv, last, pl.mod, data, nvpoly, log_sub, h);
+        kern<<<(unsigned)nblk, GP * T, smem, st>>>(FWD ? pl.tw_fwd : pl.tw_inv, last, pl.mod, data, nvpoly, log_sub, poly_stride, h);
         return cudaGetLastError();
     };
     if (log_sub == 0 && head != nullptr) return launch(k_ntt_cta<A, LOGN, LOGR, GP, FWD, true, NP>, *head);
@@ -319,51 +346,51 @@ cudaError_t launch_cta_np(const PlanDev<A>& pl, typename A::W* data, unsigned lo
 // u32 whole transforms carry CNTT_NP32 polynomials per thread group (twiddle reuse); sub-blocks of a large
 // transform, 64-bit words and tiny batches carry one.
 template <class A, int LOGN, bool FWD>
-cudaError_t launch_cta_one(const PlanDev<A>& pl, typename A::W* data, unsigned long long nvpoly, int log_sub, cudaStream_t st)
+cudaError_t launch_cta_one(const PlanDev<A>& pl, typename A::W* data, unsigned long long nvpoly, int log_sub, size_t poly_stride, cudaStream_t st)
 {
     constexpr int NPW = (sizeof(typename A::W) == 4 && CtaCfg<A, LOGN>::E::P >= 2) ? CNTT_NP32 : 1;
     if constexpr (NPW > 1) {
         const TwHead<typename A::Tw>* head = FWD ? pl.head_fwd : pl.head_inv;
-        if (log_sub == 0 && head != nullptr && nvpoly >= 2ull * NPW * 148ull) return launch_cta_np<A, LOGN, FWD, NPW>(pl, data, nvpoly, log_sub, st);
+        if (log_sub == 0 && head != nullptr && nvpoly >= 2ull * NPW * 148ull) return launch_cta_np<A, LOGN, FWD, NPW>(pl, data, nvpoly, log_sub, poly_stride, st);
     }
-    return launch_cta_np<A, LOGN, FWD, 1>(pl, data, nvpoly, log_sub, st);
+    return launch_cta_np<A, LOGN, FWD, 1>(pl, data, nvpoly, log_sub, poly_stride, st);
 }
 
 template <class A, bool FWD>
-cudaError_t launch_cta(const PlanDev<A>& pl, int logn_sub, typename A::W* data, unsigned long long nvpoly, int log_sub, cudaStream_t st)
+cudaError_t launch_cta(const PlanDev<A>& pl, int logn_sub, typename A::W* data, unsigned long long nvpoly, int log_sub, size_t poly_stride, cudaStream_t st)
 {
     switch (logn_sub) {
-    case 4: return launch_cta_one<A, 4, FWD>(pl, data, nvpoly, log_sub, st);
-    case 5: return launch_cta_one<A, 5, FWD>(pl, data, nvpoly, log_sub, st);
-    case 6: return launch_cta_one<A, 6, FWD>(pl, data, nvpoly, log_sub, st);
-    case 7: return launch_cta_one<A, 7, FWD>(pl, data, nvpoly, log_sub, st);
-    case 8: return launch_cta_one<A, 8, FWD>(pl, data, nvpoly, log_sub, st);
-    case 9: return launch_cta_one<A, 9, FWD>(pl, data, nvpoly, log_sub, st);
-    case 10: return launch_cta_one<A, 10, FWD>(pl, data, nvpoly, log_sub, st);
-    case 11: return launch_cta_one<A, 11, FWD>(pl, data, nvpoly, log_sub, st);
-    case 12: return launch_cta_one<A, 12, FWD>(pl, data, nvpoly, log_sub, st);
+    case 4: return launch_cta_one<A, 4, FWD>(pl, data, nvpoly, log_sub, poly_stride, st);
+    case 5: return launch_cta_one<A, 5, FWD>(pl, data, nvpoly, log_sub, poly_stride, st);
+    case 6: return launch_cta_one<A, 6, FWD>(pl, data, nvpoly, log_sub, poly_stride, st);
+    case 7: return launch_cta_one<A, 7, FWD>(pl, data, nvpoly, log_sub, poly_stride, st);
+    case 8: return launch_cta_one<A, 8, FWD>(pl, data, nvpoly, log_sub, poly_stride, st);
+    case 9: return launch_cta_one<A, 9, FWD>(pl, data, nvpoly, log_sub, poly_stride, st);
+    case 10: return launch_cta_one<A, 10, FWD>(pl, data, nvpoly, log_sub, poly_stride, st);
+    case 11: return launch_cta_one<A, 11, FWD>(pl, data, nvpoly, log_sub, poly_stride, st);
+    case 12: return launch_cta_one<A, 12, FWD>(pl, data, nvpoly, log_sub, poly_stride, st);
     default: return cudaErrorInvalidValue;
     }
 }
 
 template <class A, int LOGK, bool FWD>
-cudaError_t launch_strided_one(const PlanDev<A>& pl, typename A::W* data, size_t batch, int s0, cudaStream_t st)
+cudaError_t launch_strided_one(const PlanDev<A>& pl, typename A::W* data, size_t batch, int s0, size_t poly_stride, cudaStream_t st)
 {
     const unsigned long long nitems = (unsigned long long)batch << (pl.logn - LOGK);
     const unsigned long long nblk = (nitems + 255) / 256;
     if (nblk == 0) return cudaSuccess;
     if (nblk > 0x7fffffffull) return cudaErrorInvalidValue;
-    k_ntt_strided<A, LOGK, FWD><<<(unsigned)nblk, 256, 0, st>>>(FWD ? pl.tw_fwd : pl.tw_inv, pl.mod, data, nitems, pl.logn, s0);
+    k_ntt_strided<A, LOGK, FWD><<<(unsigned)nblk, 256, 0, st>>>(FWD ? pl.tw_fwd : pl.tw_inv, pl.mod, data, nitems, pl.logn, s0, poly_stride);
     return cudaGetLastError();
 }
 template <class A, bool FWD>
-cudaError_t launch_strided(const PlanDev<A>& pl, int logk, typename A::W* data, size_t batch, int s0, cudaStream_t st)
+cudaError_t launch_strided(const PlanDev<A>& pl, int logk, typename A::W* data, size_t batch, int s0, size_t poly_stride, cudaStream_t st)
 {
     switch (logk) {
-    case 1: return launch_strided_one<A, 1, FWD>(pl, data, batch, s0, st);
-    case 2: return launch_strided_one<A, 2, FWD>(pl, data, batch, s0, st);
-    case 3: return launch_strided_one<A, 3, FWD>(pl, data, batch, s0, st);
-    case 4: return launch_strided_one<A, 4, FWD>(pl, data, batch, s0, st);
+    case 1: return launch_strided_one<A, 1, FWD>(pl, data, batch, s0, poly_stride, st);
+    case 2: return launch_strided_one<A, 2, FWD>(pl, data, batch, s0, poly_stride, st);
+    case 3: return launch_strided_one<A, 3, FWD>(pl, data, batch, s0, poly_stride, st);
+    case 4: return launch_strided_one<A, 4, FWD>(pl, data, batch, s0, poly_stride, st);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -371,29 +398,31 @@ cudaError_t launch_strided(const PlanDev<A>& pl, int logk, typename A::W* data, 
 // Full transform of `batch` polynomials.  N <= 4096: one CTA-kernel launch.  Larger: leading stages
 // strided (<= 4 per launch) until the remaining contiguous blocks are 4096 words, then the CTA
 // kernel on all batch * 2^s blocks; the inverse runs the same schedule backwards.
+// poly_stride: distance in words between consecutive polynomials of the batch (0: contiguous, = N)
 template <class A, bool FWD>
-cudaError_t launch_ntt(const PlanDev<A>& pl, typename A::W* data, size_t batch, cudaStream_t st)
+cudaError_t launch_ntt(const PlanDev<A>& pl, typename A::W* data, size_t batch, cudaStream_t st, size_t poly_stride = 0)
 {
     if (batch == 0) return cudaSuccess;
-    if (pl.logn <= kMaxCtaLogN) return launch_cta<A, FWD>(pl, pl.logn, data, batch, 0, st);
+    if (poly_stride == 0) poly_stride = (size_t)1 << pl.logn;
+    if (pl.logn <= kMaxCtaLogN) return launch_cta<A, FWD>(pl, pl.logn, data, batch, 0, poly_stride, st);
     const int lead = pl.logn - kMaxCtaLogN;
     cudaError_t e;
     if constexpr (FWD) {
         int s0 = 0;
         while (s0 < lead) {
             const int k = (lead - s0) < 4 ? (lead - s0) : 4;
-            if ((e = launch_strided<A, true>(pl, k, data, batch, s0, st)) != cudaSuccess) return e;
+            if ((e = launch_strided<A, true>(pl, k, data, batch, s0, poly_stride, st)) != cudaSuccess) return e;
             s0 += k;
         }
-        return launch_cta<A, true>(pl, kMaxCtaLogN, data, (unsigned long long)batch << lead, lead, st);
+        return launch_cta<A, true>(pl, kMaxCtaLogN, data, (unsigned long long)batch << lead, lead, poly_stride, st);
     } else {
-        if ((e = launch_cta<A, false>(pl, kMaxCtaLogN, data, (unsigned long long)batch << lead, lead, st)) != cudaSuccess) return e;
+        if ((e = launch_cta<A, false>(pl, kMaxCtaLogN, data, (unsigned long long)batch << lead, lead, poly_stride, st)) != cudaSuccess) return e;
         // mirror of the forward schedule: last forward chunk first
         int chunks[8], nc = 0, s = 0;
         while (s < lead) { const int k = (lead - s) < 4 ? (lead - s) : 4; chunks[nc++] = k; s += k; }
         for (int c = nc - 1; c >= 0; c--) {
             s -= chunks[c];
-            if ((e = launch_strided<A, false>(pl, chunks[c], data, batch, s, st)) != cudaSuccess) return e;
+            if ((e = launch_strided<A, false>(pl, chunks[c], data, batch, s, poly_stride, st)) != cudaSuccess) return e;
         }
         return cudaSuccess;
     }
@@ -411,6 +440,24 @@ cudaError_t launch_pointwise(const PlanDev<A>& pl, typename A::W* dst, const typ
     if (nblk > cap) nblk = cap;
     k_pointwise<A, OP><<<(unsigned)nblk, 256, 0, st>>>(pl.mod, dst, a, b, nvec);
     return cudaGetLastError();
+}
+
+// pointwise op on `batch` polynomials of 2^logn words, poly_stride words apart (all three streams share the layout)
+template <class A, int OP>
+cudaError_t launch_pointwise_strided(const PlanDev<A>& pl, typename A::W* dst, const typename A::W* a, const typename A::W* b,
+                                     size_t batch, size_t poly_stride, cudaStream_t st)
+{
+    constexpr int PER = 16 / (int)sizeof(typename A::W);
+    const unsigned nvec = (unsigned)(((size_t)1 << pl.logn) / PER);
+    const unsigned gx = (nvec + 255) / 256;
+    for (size_t b0 = 0; b0 < batch; b0 += 65535) { // grid.y limit
+        const size_t nb = batch - b0 < 65535 ? batch - b0 : 65535;
+        k_pointwise_strided<A, OP><<<dim3(gx, (unsigned)nb), 256, 0, st>>>(pl.mod, dst + b0 * poly_stride, a ? a + b0 * poly_stride : a,
+                                                                         b ? b + b0 * poly_stride : b, nvec, poly_stride);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 } // namespace cntt

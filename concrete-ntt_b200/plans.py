@@ -251,3 +251,125 @@ class _NativePlan:
         else:
             check(_lib.lib().cntt_native_polymul_host(self._h, p.ptr, l.ptr, r.ptr, p.batch * self._n, p.batch))
         return prod
+
+
+class FwdMode:
+    """product::FwdMode (src/product.rs:10-14): FwdMode.Generic or FwdMode.Bounded(bound)."""
+
+    def __init__(self, kind, bound=0):
+        self.kind, self.bound = kind, bound
+
+    @staticmethod
+    def Bounded(bound):
+        return FwdMode(1, int(bound))
+
+    def __repr__(self):
+        return "FwdMode.Generic" if self.kind == 0 else "FwdMode.Bounded(%d)" % self.bound
+
+
+FwdMode.Generic = FwdMode(0)
+
+
+class InvMode:
+    """product::InvMode (src/product.rs:16-20)"""
+    Replace = 0
+    Accumulate = 1
+
+
+class ProductPlan:
+    """product::Plan (src/product.rs:139-967): negacyclic NTT plan for a modulus that is a product of distinct
+    primes.  Device-resident buffers (torch CUDA int64 tensors): `standard` (batch..., n) and NTT-domain buffers
+    (batch..., ntt_domain_len) in the reference's packed layout (u32 planes first, then u64 planes)."""
+
+    def __init__(self, handle, n, modulus, device):
+        self._h, self._n, self._modulus, self._device = handle, n, modulus, device
+        self._dl = _lib.lib().cntt_product_ntt_domain_len(handle)
+
+    @classmethod
+    def try_new(cls, polynomial_size, modulus, factors, device=0):
+        l = _lib.lib()
+        h = C.c_void_p()
+        fs = [int(f) for f in factors]
+        arr = (C.c_uint64 * max(1, len(fs)))(*fs)
+        st = l.cntt_product_plan_new(polynomial_size, modulus, arr, len(fs), device, C.byref(h))
+        if st in (_lib.INVALID_SIZE, _lib.INVALID_MODULUS, _lib.NO_ROOT):
+            return None
+        check(st, "try_new")
+        return cls(h, polynomial_size, modulus, device)
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib().cntt_product_plan_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def ntt_size(self):
+        return _lib.lib().cntt_product_ntt_size(self._h)
+
+    def modulus(self):
+        return _lib.lib().cntt_product_modulus(self._h)
+
+    def ntt_domain_len(self):
+        return self._dl
+
+    def primes(self):
+        c32, c64 = C.c_int(), C.c_int()
+        check(_lib.lib().cntt_product_num_primes(self._h, C.byref(c32), C.byref(c64)))
+        return [_lib.lib().cntt_product_prime(self._h, i) for i in range(c32.value + c64.value)]
+
+    def _std(self, x, name):
+        b = _Buf(x, 8, name)
+        if not b.is_dev:
+            raise TypeError("product::Plan operates on device-resident tensors")
+        if len(b.shape) == 0 or b.shape[-1] != self._n:
+            raise ReferencePanic("assert_eq!(standard.len(), self.ntt_size())")
+        b.batch = b.words // self._n
+        return b
+
+    def _dom(self, x, name, batch=None):
+        b = _Buf(x, 8, name)
+        if not b.is_dev:
+            raise TypeError("product::Plan operates on device-resident tensors")
+        if self._dl == 0:
+            b.batch = batch if batch is not None else 0
+            if b.words != 0:
+                raise ReferencePanic("assert_eq!(%s.len(), self.ntt_domain_len())" % name)
+            return b
+        if len(b.shape) == 0 or b.shape[-1] != self._dl:
+            raise ReferencePanic("assert_eq!(%s.len(), self.ntt_domain_len())" % name)
+        b.batch = b.words // self._dl
+        if batch is not None and b.batch != batch:
+            raise ReferencePanic("batch sizes differ")
+        return b
+
+    def fwd(self, ntt, standard, mode=FwdMode.Generic):
+        s = self._std(standard, "standard")
+        d = self._dom(ntt, "ntt", s.batch)
+        check(_lib.lib().cntt_product_fwd(self._h, d.ptr, s.ptr, mode.kind, mode.bound, s.batch, _stream_of(s.t)), "fwd")
+        return ntt
+
+    def inv(self, standard, ntt, mode=InvMode.Replace):
+        s = self._std(standard, "standard")
+        d = self._dom(ntt, "ntt", s.batch)
+        check(_lib.lib().cntt_product_inv(self._h, s.ptr, d.ptr, mode, s.batch, _stream_of(s.t)), "inv")
+        return standard
+
+    def mul_assign_normalize(self, lhs, rhs):
+        a = self._dom(lhs, "lhs")
+        b = self._dom(rhs, "rhs", a.batch)
+        check(_lib.lib().cntt_product_mul_assign_normalize(self._h, a.ptr, b.ptr, a.batch, _stream_of(a.t)))
+        return lhs
+
+    def normalize(self, values):
+        a = self._dom(values, "values")
+        check(_lib.lib().cntt_product_normalize(self._h, a.ptr, a.batch, _stream_of(a.t)))
+        return values
+
+    def mul_accumulate(self, acc, lhs, rhs):
+        a = self._dom(acc, "acc")
+        l = self._dom(lhs, "lhs", a.batch)
+        r = self._dom(rhs, "rhs", a.batch)
+        check(_lib.lib().cntt_product_mul_accumulate(self._h, a.ptr, l.ptr, r.ptr, a.batch, _stream_of(a.t)))
+        return acc

@@ -137,6 +137,31 @@ int cntt_native_polymul(const cntt_native_plan* plan, void* d_prod, const void* 
 /* host-slice flavour: len = words in each of prod/lhs/rhs; must equal n*batch */
 int cntt_native_polymul_host(const cntt_native_plan* plan, void* h_prod, const void* h_lhs, const void* h_rhs, size_t len, size_t batch);
 
+/* ---- product::Plan (modulus = product of distinct primes, < 2^64)      src/product.rs:139-967 -------------
+ * NTT-domain layout of one polynomial = the reference's (product.rs:261-278): the u32 planes (primes < 2^32,
+ * ascending) bit-cast into the front of the u64 buffer, then the u64 planes; ntt_domain_len u64 words.  A batch is
+ * the reference's slices concatenated: polynomial b at d_ntt + b * ntt_domain_len, d_standard + b * n.
+ */
+typedef struct cntt_product_plan cntt_product_plan;
+/* Plan::try_new(polynomial_size, modulus, factors)    src/product.rs:152-251 ; != CNTT_OK <=> None */
+int cntt_product_plan_new(size_t n, uint64_t modulus, const uint64_t* factors, size_t nfactors, int device, cntt_product_plan** out);
+void cntt_product_plan_free(cntt_product_plan* plan);
+size_t cntt_product_ntt_size(const cntt_product_plan* plan);        /* src/product.rs:254-257 */
+uint64_t cntt_product_modulus(const cntt_product_plan* plan);       /* src/product.rs:260-263 */
+size_t cntt_product_ntt_domain_len(const cntt_product_plan* plan);  /* src/product.rs:265-274 */
+int cntt_product_num_primes(const cntt_product_plan* plan, int* count32, int* count64);
+uint64_t cntt_product_prime(const cntt_product_plan* plan, int i);  /* i-th prime, ascending */
+/* Plan::fwd(ntt, standard, mode)                      src/product.rs:276-353 ; mode 0 = FwdMode::Generic,
+ * 1 = FwdMode::Bounded(bound) */
+int cntt_product_fwd(const cntt_product_plan* plan, uint64_t* d_ntt, const uint64_t* d_standard, int mode, uint64_t bound, size_t batch, void* stream);
+/* Plan::inv(standard, ntt, mode)                      src/product.rs:355-880 ; mode 0 = InvMode::Replace,
+ * 1 = InvMode::Accumulate; d_ntt is clobbered like the reference's `ntt: &mut [u64]` */
+int cntt_product_inv(const cntt_product_plan* plan, uint64_t* d_standard, uint64_t* d_ntt, int mode, size_t batch, void* stream);
+/* Plan::mul_assign_normalize / normalize / mul_accumulate on NTT-domain buffers   src/product.rs:884-967 */
+int cntt_product_mul_assign_normalize(const cntt_product_plan* plan, uint64_t* d_lhs, const uint64_t* d_rhs, size_t batch, void* stream);
+int cntt_product_normalize(const cntt_product_plan* plan, uint64_t* d_values, size_t batch, void* stream);
+int cntt_product_mul_accumulate(const cntt_product_plan* plan, uint64_t* d_acc, const uint64_t* d_lhs, const uint64_t* d_rhs, size_t batch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -300,6 +300,157 @@ class Native:
         self._L.o_native_polymul_batch(self._h, _ptr(prod), _ptr(lhs), _ptr(rhs), batch, nthreads)
 
 
+class Product:
+    """product::Plan (src/product.rs:139-967), restated on top of the oracle's prime plans.  One polynomial per
+    call like the reference: `standard` is a (n,) uint64 array, NTT-domain buffers are (ntt_domain_len,) uint64
+    arrays in the reference's packed layout (u32 planes bit-cast into the front, then the u64 planes,
+    product.rs:261-278).  Scalar paths only; the SIMD bodies of the 2 x u32 case compute the same values."""
+    GENERIC = ("generic", 0)
+
+    @staticmethod
+    def bounded(bound):
+        return ("bounded", int(bound))
+
+    REPLACE, ACCUMULATE = 0, 1
+
+    def __init__(self, n, modulus, primes, p32, p64):
+        self.n, self.modulus, self.primes, self.p32, self.p64 = n, modulus, primes, p32, p64
+        # modular_inverses (product.rs:205-226): inverse of every earlier prime modulo p_j
+        self.minv = {(j, i): pow(primes[i] % primes[j], -1, primes[j]) for j in range(len(primes)) for i in range(j)}
+
+    @classmethod
+    def try_new(cls, n, modulus, factors):               # product.rs:152-251
+        if n % 2 != 0:
+            return None
+        primes = sorted(int(f) for f in factors)
+        prev = 0
+        for f in primes:                                 # zeros / duplicates
+            if f == prev:
+                return None
+            prev = f
+        primes = [f for f in primes if f != 1]
+        prod = 1
+        for f in primes:
+            prod *= f
+            if prod >= 1 << 64:                          # checked_mul
+                return None
+        if prod != modulus:
+            return None
+        p32, p64 = [], []
+        for f in primes:
+            pl = Plan32.try_new(n, f) if f < 1 << 32 else Plan64.try_new(n, f)
+            if pl is None:
+                return None
+            (p32 if f < 1 << 32 else p64).append(pl)
+        return cls(n, modulus, primes, p32, p64)
+
+    def ntt_size(self):
+        return self.n
+
+    def ntt_domain_len(self):                            # product.rs:265-274
+        return (self.n // 2) * len(self.p32) + self.n * len(self.p64)
+
+    def _split(self, ntt):
+        n32 = (self.n // 2) * len(self.p32)
+        return ntt[:n32].view(np.uint32), ntt[n32:]
+
+    def fwd(self, ntt, standard, mode=GENERIC):          # product.rs:276-353
+        assert standard.shape == (self.n,) and ntt.shape == (self.ntt_domain_len(),)
+        n, c32, c64 = self.n, len(self.p32), len(self.p64)
+        ntt32, ntt64 = self._split(ntt)
+        if c32 == 0 and c64 == 1:
+            ntt64[:] = standard
+            self.p64[0].fwd(ntt64)
+            return ntt
+        if c32 == 1 and c64 == 0:
+            ntt32[:] = standard.astype(np.uint32)        # `standard as u32`
+            self.p32[0].fwd(ntt32)
+            return ntt
+        if c32 == 2 and c64 == 0:
+            p0, p1, p = self.primes[0], self.primes[1], self.modulus
+            if mode[0] == "bounded" and mode[1] < p0 and mode[1] < p1:
+                positive = standard < np.uint64(p // 2)
+                s32 = standard.astype(np.uint32)
+                comp = (np.uint32(p & 0xFFFFFFFF) - s32).astype(np.uint32)
+                with np.errstate(over="ignore"):
+                    ntt32[:n] = np.where(positive, s32, np.uint32(p0) - comp)
+                    ntt32[n:] = np.where(positive, s32, np.uint32(p1) - comp)
+            else:
+                ntt32[:n] = (standard % np.uint64(p0)).astype(np.uint32)
+                ntt32[n:] = (standard % np.uint64(p1)).astype(np.uint32)
+            self.p32[0].fwd(ntt32[:n])
+            self.p32[1].fwd(ntt32[n:])
+            return ntt
+        for k, pl in enumerate(self.p32):
+            ntt32[k * n:(k + 1) * n] = (standard % np.uint64(pl.p)).astype(np.uint32)
+            pl.fwd(ntt32[k * n:(k + 1) * n])
+        for k, pl in enumerate(self.p64):
+            ntt64[k * n:(k + 1) * n] = standard % np.uint64(pl.p)
+            pl.fwd(ntt64[k * n:(k + 1) * n])
+        return ntt
+
+    def inv(self, standard, ntt, mode=REPLACE):          # product.rs:355-880
+        assert standard.shape == (self.n,) and ntt.shape == (self.ntt_domain_len(),)
+        n, c32, c64 = self.n, len(self.p32), len(self.p64)
+        ntt32, ntt64 = self._split(ntt)
+        for k, pl in enumerate(self.p32):
+            pl.inv(ntt32[k * n:(k + 1) * n])
+        for k, pl in enumerate(self.p64):
+            pl.inv(ntt64[k * n:(k + 1) * n])
+        M64 = (1 << 64) - 1
+
+        def add_mod_u64(p, a, b):                        # product.rs:83-91
+            s = (a + b) & M64
+            return (s - p) & M64 if (s >= p or a + b > M64) else s
+
+        if c32 == 0 and c64 == 0:
+            if mode == self.REPLACE:
+                standard[:] = 0
+            return standard
+        if c32 == 1 and c64 == 0:
+            p = self.primes[0]
+            for i in range(n):
+                if mode == self.REPLACE:
+                    standard[i] = int(ntt32[i])
+                else:                                    # add_mod_u32(p, *standard as u32, ntt) as u64
+                    a, b = int(standard[i]) & 0xFFFFFFFF, int(ntt32[i])
+                    s = (a + b) & 0xFFFFFFFF
+                    standard[i] = (s - p) & 0xFFFFFFFF if (s >= p or a + b > 0xFFFFFFFF) else s
+            return standard
+        planes = [ntt32[k * n:(k + 1) * n] for k in range(c32)] + [ntt64[k * n:(k + 1) * n] for k in range(c64)]
+        for i in range(n):                               # Knuth 4.3.2 mixed radix, product.rs:806-880
+            v = []
+            for j, pj in enumerate(self.primes):
+                x = int(planes[j][i])
+                for t in range(j):
+                    diff = x - v[t] if x >= v[t] else x - v[t] + pj     # sub_mod
+                    x = diff * self.minv[(j, t)] % pj
+                v.append(x)
+            acc = 0
+            for j in reversed(range(len(v))):
+                acc = (acc * self.primes[j] + v[j]) & M64
+            standard[i] = acc if mode == self.REPLACE else add_mod_u64(self.modulus, int(standard[i]), acc)
+        return standard
+
+    def _pw(self, name, *bufs):                          # product.rs:884-967
+        n = self.n
+        sp = [self._split(b) for b in bufs]
+        for k, pl in enumerate(self.p32):
+            getattr(pl, name)(*[s[0][k * n:(k + 1) * n] for s in sp])
+        for k, pl in enumerate(self.p64):
+            getattr(pl, name)(*[s[1][k * n:(k + 1) * n] for s in sp])
+        return bufs[0]
+
+    def mul_assign_normalize(self, lhs, rhs):
+        return self._pw("mul_assign_normalize", lhs, rhs)
+
+    def normalize(self, values):
+        return self._pw("normalize", values)
+
+    def mul_accumulate(self, acc, lhs, rhs):
+        return self._pw("mul_accumulate", acc, lhs, rhs)
+
+
 def schoolbook32(p, lhs, rhs):
     out = np.empty_like(lhs)
     lib().o_schoolbook32(lhs.size, p, _ptr(lhs), _ptr(rhs), _ptr(out))

@@ -258,3 +258,116 @@ def test_crt_sign_rule(oracle):
         assert O.lib().o_reconstruct_32bit_012_u32(*r[:3]) == x % 2**32
         if abs(x) < P[0] * P[1] // 2:
             assert O.lib().o_reconstruct_32bit_01(*r[:2]) == x % 2**32
+
+
+# ---- product::Plan (src/product.rs:969-1170) -------------------------------------------------------------
+def _product_cases(O, n):
+    """the prime sets of the reference's product tests (src/product.rs:976-1155), n = 256 there"""
+    f = O.largest_prime_in_arithmetic_progression64
+    d = 2 * n
+    u64x1 = [f(d, 1, 0, 2**64 - 1)]
+    u32x1 = [f(d, 1, 0, 2**32 - 1)]
+    p0 = f(d, 1, 0, 2**32 - 1)
+    u32x2 = [p0, f(d, 1, 0, p0 - 1)]
+    q0 = f(d, 1, 0, 1 << 30)
+    u30x2 = [q0, f(d, 1, 0, q0 - 1)]
+    r = [f(d, 1, 0, 2**16 - 1)]
+    for _ in range(3):
+        nxt = f(d, 1, 0, r[-1] - 1)
+        if nxt is None:                                  # n > 256: fewer than four such primes below 2^16
+            break
+        r.append(nxt)
+    if n <= 256:
+        s1 = f(d, 1, 0, 1 << 15)
+        mixed = [f(d, 1, 0, 1 << 33), s1, f(d, 1, 0, s1 - 1)]
+    else:                                                # larger n: same shape, windows that still hold primes
+        s1 = f(d, 1, 0, 1 << 16)
+        s2 = f(d, 1, 0, s1 - 1)
+        mixed = [f(d, 1, 1 << 32, (2**64 - 1) // (s1 * s2)), s1, s2]
+    return {"u64x1": u64x1, "u32x1": u32x1, "u32x2": u32x2, "u30x2": u30x2, "u32x4": r, "u32x2_u64x1": mixed}
+
+
+def _prod(ps):
+    m = 1
+    for p in ps:
+        m *= p
+    return m
+
+
+@pytest.mark.parametrize("case", ["u64x1", "u32x1", "u32x2", "u30x2", "u32x4", "u32x2_u64x1"])
+def test_product_roundtrip(oracle, case):
+    """test_product_* (src/product.rs:976-1155): inv(fwd(x)) * n^-1 == x mod the composite modulus, both
+    InvModes (Accumulate onto zeros)."""
+    n = 256
+    ps = _product_cases(oracle, n)[case]
+    p = _prod(ps)
+    assert p < 2**64
+    plan = oracle.Product.try_new(n, p, ps)
+    assert plan is not None and plan.ntt_size() == n
+    g = rng(sum(case.encode()))
+    standard = rand_mod(g, p, (n,), np.uint64)
+    n_inv = pow(n, -1, p)
+    for mode in (plan.REPLACE, plan.ACCUMULATE):
+        ntt = np.zeros(plan.ntt_domain_len(), dtype=np.uint64)
+        rt = np.zeros(n, dtype=np.uint64)
+        plan.fwd(ntt, standard, plan.GENERIC)
+        plan.inv(rt, ntt, mode)
+        got = [int(x) * n_inv % p for x in rt]
+        assert got == [int(x) for x in standard], (case, mode)
+
+
+def test_product_failures(oracle):
+    """test_plan_failure_zero / _dup (src/product.rs:1155-1170) and the other None outcomes of try_new"""
+    O = oracle
+    n = 256
+    f = O.largest_prime_in_arithmetic_progression64
+    p0, p1 = f(2 * n, 1, 0, 1 << 33), f(2 * n, 1, 0, 1 << 15)
+    assert O.Product.try_new(n, 0, [p0, 0]) is None
+    assert O.Product.try_new(n, p0 * p1 * p1 % 2**64, [p1, p0, p1]) is None
+    assert O.Product.try_new(n, p0 * p1 + 1, [p0, p1]) is None          # product != modulus
+    assert O.Product.try_new(n, p0 * p1, [p0, p1, 1]) is not None       # 1s are skipped
+    assert O.Product.try_new(n, 15 * p1, [15, p1]) is None              # a non-prime factor
+    big = f(2 * n, 1, 0, 2**64 - 1)
+    assert O.Product.try_new(n, (big * p0) % 2**64, [big, p0]) is None  # checked_mul overflow
+
+
+def test_product_bounded_and_polymul(oracle):
+    """FwdMode::Bounded on the two-u32-prime plan gives the residues of the centred value (product.rs:305-322),
+    and mul_assign_normalize + inv is the negacyclic product mod p0*p1."""
+    n = 64
+    f = oracle.largest_prime_in_arithmetic_progression64
+    p0 = f(2 * n, 1, 0, 1 << 31)
+    p1 = f(2 * n, 1, 0, p0 - 1)
+    p = p0 * p1
+    plan = oracle.Product.try_new(n, p, [p0, p1])
+    g = rng(77)
+    bound = 1 << 20
+    small = g.integers(-bound + 1, bound, size=n)
+    standard = np.array([int(x) % p for x in small], dtype=np.uint64)
+    a = np.zeros(plan.ntt_domain_len(), dtype=np.uint64)
+    b = np.zeros_like(a)
+    plan.fwd(a, standard, plan.bounded(bound))
+    plan.fwd(b, standard, plan.GENERIC)
+    assert (a == b).all()
+    rhs = rand_mod(g, p, (n,), np.uint64)
+    c = np.zeros_like(a)
+    plan.fwd(c, rhs, plan.GENERIC)
+    plan.mul_assign_normalize(a, c)
+    out = np.zeros(n, dtype=np.uint64)
+    plan.inv(out, a, plan.REPLACE)
+    ref = [0] * n
+    for i in range(n):
+        for j in range(n):
+            t = int(standard[i]) * int(rhs[j])
+            if i + j < n:
+                ref[i + j] = (ref[i + j] + t) % p
+            else:
+                ref[i + j - n] = (ref[i + j - n] - t) % p
+    assert [int(x) for x in out] == ref
+    # Accumulate adds the same lift modulo p (product.rs:749-753)
+    acc0 = rand_mod(g, p, (n,), np.uint64)
+    acc = acc0.copy()
+    plan.fwd(a, standard, plan.GENERIC)
+    plan.mul_assign_normalize(a, c)
+    plan.inv(acc, a, plan.ACCUMULATE)
+    assert [int(x) for x in acc] == [(int(s) + r) % p for s, r in zip(acc0, ref)]
