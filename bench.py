@@ -33,8 +33,28 @@ WORKLOAD = "prime64 Plan N=2048 p=2^64-2^32+1 (Solinas) batch 65536 per GPU, fwd
 # algorithmic HBM bytes of one NTT launch over the batch: every word read once and written once
 ALG_BYTES_PER_NTT = 2 * N_POLY * 8
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_ntt_cta<A64S,11> launch over the batch, from the
-# ncu --set full capture under profiles/ (None until captured)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = None
+# ncu --set full capture committed under profiles/ (parsed at run time; None if the summary is absent)
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r01_kernels", "ncu_ntt64s_2048.txt")
+
+
+def ncu_traffic(direction):
+    """DRAM bytes per launch of k_ntt_cta<A64S,11,...,FWD> at grid 65536 from the committed ncu summary:
+    template argument 5 is FWD (1 = forward, 0 = inverse)."""
+    try:
+        want = "1" if direction == "fwd" else "0"
+        cur, tot = None, {}
+        for line in open(NCU_SUMMARY):
+            if line.startswith("=="):
+                args = line.split("<", 1)[1].split(">", 1)[0].split(",")
+                cur = args[4].strip()
+                tot[cur] = 0.0
+            elif "dram__bytes_read.sum" in line or "dram__bytes_write.sum" in line:
+                f = line.split()
+                scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[-1]]
+                tot[cur] += float(f[-2]) * scale
+        return tot.get(want) or None
+    except Exception:
+        return None
 
 
 def peaks():
@@ -339,7 +359,7 @@ def run_ours(args):
                     "steps": ke, "api": "cntt_prime64_fwd_inv_host (pinned host slice, chunked double-buffered staging)"},
             "gpu_launches": 2 * K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "kernel": "k_ntt_cta<A64S,11,4> (%s)" % which,
+                         "traffic": ncu_traffic(which), "traffic_source": "profiles/r01_kernels/ncu_ntt64s_2048.txt (ncu --set full, dram read+write bytes per launch)", "kernel": "k_ntt_cta<A64S,11,4> (%s)" % which,
                          "peak_source": peak_src, "ms_per_launch": {"fwd": fwd_ms, "inv": inv_ms},
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_NTT * BATCH,
                          "note": "integer-issue bound kernel; see DESIGN.md for the integer roofline"},

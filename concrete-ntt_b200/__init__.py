@@ -6,7 +6,8 @@ Module layout mirrors the reference crate (src/lib.rs:83-111):
     native32.Plan32, native64.Plan32, native128.Plan32
     native_binary32.Plan32, native_binary64.Plan32, native_binary128.Plan32
     product.Plan, product.FwdMode, product.InvMode
-    prime.is_prime64, prime.largest_prime_in_arithmetic_progression64
+    prime.is_prime64, prime.largest_prime_in_arithmetic_progression64, prime.{mul,exp}_mod{32,64}
+    fastdiv.Div32, fastdiv.Div64, roots.find_primitive_root64
 
 Import with ``importlib.import_module("concrete-ntt_b200")`` (the directory name is not an identifier).
 """
@@ -51,6 +52,71 @@ def _find_primitive_root64(p, degree):
     return out.value if ok else None
 
 
+class _Div:
+    """fastdiv::Div32 / Div64 (src/fastdiv.rs:28-150): plan-time helper, host only.  The reference precomputes a
+    double-word reciprocal; the quotients and remainders it returns are the exact ones, which is all that is
+    observable, so the mirror keeps the divisor and uses exact integer division.  `new` panics for 0 and 1
+    like the reference's `assert!(divisor > 1)` (src/fastdiv.rs:49,99)."""
+    _bits = 32
+
+    def __init__(self, divisor):
+        divisor = int(divisor)
+        if not 1 < divisor < (1 << self._bits):
+            raise ReferencePanic("assert!(divisor > 1)")
+        self._d = divisor
+
+    @classmethod
+    def new(cls, divisor):
+        return cls(divisor)
+
+    def divisor(self):
+        return self._d
+
+    @staticmethod
+    def div(n, d):
+        return int(n) // d._d
+
+    @staticmethod
+    def rem(n, d):
+        return int(n) % d._d
+
+
+class _Div32(_Div):
+    _bits = 32
+    div_u64 = staticmethod(lambda n, d: int(n) // d._d)
+    rem_u64 = staticmethod(lambda n, d: int(n) % d._d)
+
+
+class _Div64(_Div):
+    _bits = 64
+    div_u128 = staticmethod(lambda n, d: int(n) // d._d)
+    rem_u128 = staticmethod(lambda n, d: int(n) % d._d)
+
+
+def _div_of(n, cls):
+    return n if isinstance(n, _Div) else cls(n)
+
+
+def _mul_mod32(n, x, y):
+    """prime::mul_mod32 (src/prime.rs:4-6)"""
+    return int(x) * int(y) % _div_of(n, _Div32)._d
+
+
+def _mul_mod64(n, x, y):
+    """prime::mul_mod64 (src/prime.rs:8-10)"""
+    return int(x) * int(y) % _div_of(n, _Div64)._d
+
+
+def _exp_mod32(n, base, power):
+    """prime::exp_mod32 (src/prime.rs:12-29)"""
+    return pow(int(base), int(power), _div_of(n, _Div32)._d)
+
+
+def _exp_mod64(n, base, power):
+    """prime::exp_mod64 (src/prime.rs:31-48)"""
+    return pow(int(base), int(power), _div_of(n, _Div64)._d)
+
+
 prime32 = _module("prime32", Plan=type("Plan", (_plans.Plan32Prime,), {"__doc__": "prime32::Plan"}))
 prime64 = _module("prime64", Plan=type("Plan", (_plans.Plan64Prime,), {"__doc__": "prime64::Plan"}), Solinas=_Solinas)
 native32 = _module("native32", Plan32=_native(32, False))
@@ -61,7 +127,9 @@ native_binary64 = _module("native_binary64", Plan32=_native(64, True))
 native_binary128 = _module("native_binary128", Plan32=_native(128, True))
 product = _module("product", Plan=type("Plan", (_plans.ProductPlan,), {"__doc__": "product::Plan"}),
                   FwdMode=_plans.FwdMode, InvMode=_plans.InvMode)
-prime = _module("prime", is_prime64=_is_prime64, largest_prime_in_arithmetic_progression64=_largest_prime)
+prime = _module("prime", is_prime64=_is_prime64, largest_prime_in_arithmetic_progression64=_largest_prime,
+                mul_mod32=_mul_mod32, mul_mod64=_mul_mod64, exp_mod32=_exp_mod32, exp_mod64=_exp_mod64)
+fastdiv = _module("fastdiv", Div32=_Div32, Div64=_Div64)
 roots = _module("roots", find_primitive_root64=_find_primitive_root64)
 
 

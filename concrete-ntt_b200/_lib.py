@@ -67,6 +67,11 @@ SIGNATURES.update({
     "cntt_product_mul_assign_normalize": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "cntt_product_normalize": (_int, [_vp, _vp, _sz, _vp]),
     "cntt_product_mul_accumulate": (_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "cntt_product_fwd_host": (_int, [_vp, _vp, _vp, _sz, _sz, _int, _u64, _sz]),
+    "cntt_product_inv_host": (_int, [_vp, _vp, _vp, _sz, _sz, _int, _sz]),
+    "cntt_product_mul_assign_normalize_host": (_int, [_vp, _vp, _vp, _sz, _sz]),
+    "cntt_product_normalize_host": (_int, [_vp, _vp, _sz, _sz]),
+    "cntt_product_mul_accumulate_host": (_int, [_vp, _vp, _vp, _vp, _sz, _sz]),
 })
 
 _lib = None

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -846,6 +847,7 @@ struct cntt_product_plan {
     ProductConsts c;
     cntt_prime32_plan* p32[kProductMaxPrimes];
     cntt_prime64_plan* p64[kProductMaxPrimes];
+    Staging stg;
 };
 
 static void product_free(cntt_product_plan* pl)
@@ -854,6 +856,7 @@ static void product_free(cntt_product_plan* pl)
         if (pl->p32[k]) cntt_prime32_plan_free(pl->p32[k]);
         if (pl->p64[k]) cntt_prime64_plan_free(pl->p64[k]);
     }
+    pl->stg.release();
     delete pl;
 }
 
@@ -1028,4 +1031,79 @@ CNTT_API int cntt_product_mul_accumulate(const cntt_product_plan* pl, uint64_t* 
     GUARD(pl->device);
     CU(product_pointwise(pl, OP_MUL_ACCUMULATE, d_acc, d_lhs, d_rhs, batch, (cudaStream_t)stream));
     return CNTT_OK;
+}
+
+// host-slice flavours (the reference's call shape, one or `batch` concatenated polynomials): staged through the plan's
+// arena, synchronous.  h_bufs[i] holds words[i] u64 words; copy_back[i] says whether the reference mutates it.
+static int product_host(const cntt_product_plan* pl, int nbuf, uint64_t* const* h_bufs, const size_t* words, const bool* copy_back,
+                        const std::function<int(uint64_t* const*, cudaStream_t)>& body)
+{
+    auto* mpl = const_cast<cntt_product_plan*>(pl);
+    DeviceGuard guard(pl->device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    std::lock_guard<std::mutex> lk(mpl->stg.mu);
+    size_t total = 0;
+    for (int i = 0; i < nbuf; i++) total += (words[i] + 1) & ~(size_t)1; // keep every buffer 16-byte aligned
+    CU(mpl->stg.ensure(std::max<size_t>(total, 2) * sizeof(uint64_t)));
+    uint64_t* d[4];
+    size_t off = 0;
+    for (int i = 0; i < nbuf; i++) {
+        d[i] = static_cast<uint64_t*>(mpl->stg.buf) + off;
+        off += (words[i] + 1) & ~(size_t)1;
+        if (words[i]) CU(cudaMemcpyAsync(d[i], h_bufs[i], words[i] * sizeof(uint64_t), cudaMemcpyHostToDevice, mpl->stg.stream));
+    }
+    const int st = body(d, mpl->stg.stream);
+    if (st != CNTT_OK) return st;
+    for (int i = 0; i < nbuf; i++)
+        if (copy_back[i] && words[i]) CU(cudaMemcpyAsync(h_bufs[i], d[i], words[i] * sizeof(uint64_t), cudaMemcpyDeviceToHost, mpl->stg.stream));
+    CU(cudaStreamSynchronize(mpl->stg.stream));
+    return CNTT_OK;
+}
+CNTT_API int cntt_product_fwd_host(const cntt_product_plan* pl, uint64_t* h_ntt, const uint64_t* h_standard, size_t ntt_len, size_t standard_len,
+                                   int mode, uint64_t bound, size_t batch)
+{
+    if (!pl || ((!h_ntt && ntt_len) || (!h_standard && standard_len))) return CNTT_NULL_POINTER;
+    if (standard_len != pl->n * batch || ntt_len != (size_t)pl->c.domain_len * batch) return CNTT_LENGTH_MISMATCH; // assert_eq!, product.rs:278-279
+    uint64_t* bufs[2] = {h_ntt, const_cast<uint64_t*>(h_standard)};
+    const size_t words[2] = {ntt_len, standard_len};
+    const bool back[2] = {true, false};
+    return product_host(pl, 2, bufs, words, back, [&](uint64_t* const* d, cudaStream_t st) { return cntt_product_fwd(pl, d[0], d[1], mode, bound, batch, st); });
+}
+CNTT_API int cntt_product_inv_host(const cntt_product_plan* pl, uint64_t* h_standard, uint64_t* h_ntt, size_t standard_len, size_t ntt_len, int mode,
+                                   size_t batch)
+{
+    if (!pl || ((!h_ntt && ntt_len) || (!h_standard && standard_len))) return CNTT_NULL_POINTER;
+    if (standard_len != pl->n * batch || ntt_len != (size_t)pl->c.domain_len * batch) return CNTT_LENGTH_MISMATCH; // product.rs:357-358
+    uint64_t* bufs[2] = {h_standard, h_ntt};
+    const size_t words[2] = {standard_len, ntt_len};
+    const bool back[2] = {true, true}; // the reference's inv leaves the inverse transforms in `ntt`
+    return product_host(pl, 2, bufs, words, back, [&](uint64_t* const* d, cudaStream_t st) { return cntt_product_inv(pl, d[0], d[1], mode, batch, st); });
+}
+CNTT_API int cntt_product_mul_assign_normalize_host(const cntt_product_plan* pl, uint64_t* h_lhs, const uint64_t* h_rhs, size_t len, size_t batch)
+{
+    if (!pl || ((!h_lhs || !h_rhs) && len)) return CNTT_NULL_POINTER;
+    if (len != (size_t)pl->c.domain_len * batch) return CNTT_LENGTH_MISMATCH; // product.rs:887-888
+    uint64_t* bufs[2] = {h_lhs, const_cast<uint64_t*>(h_rhs)};
+    const size_t words[2] = {len, len};
+    const bool back[2] = {true, false};
+    return product_host(pl, 2, bufs, words, back, [&](uint64_t* const* d, cudaStream_t st) { return cntt_product_mul_assign_normalize(pl, d[0], d[1], batch, st); });
+}
+CNTT_API int cntt_product_normalize_host(const cntt_product_plan* pl, uint64_t* h_values, size_t len, size_t batch)
+{
+    if (!pl || (!h_values && len)) return CNTT_NULL_POINTER;
+    if (len != (size_t)pl->c.domain_len * batch) return CNTT_LENGTH_MISMATCH; // product.rs:920
+    uint64_t* bufs[1] = {h_values};
+    const size_t words[1] = {len};
+    const bool back[1] = {true};
+    return product_host(pl, 1, bufs, words, back, [&](uint64_t* const* d, cudaStream_t st) { return cntt_product_normalize(pl, d[0], batch, st); });
+}
+CNTT_API int cntt_product_mul_accumulate_host(const cntt_product_plan* pl, uint64_t* h_acc, const uint64_t* h_lhs, const uint64_t* h_rhs, size_t len,
+                                              size_t batch)
+{
+    if (!pl || ((!h_acc || !h_lhs || !h_rhs) && len)) return CNTT_NULL_POINTER;
+    if (len != (size_t)pl->c.domain_len * batch) return CNTT_LENGTH_MISMATCH; // product.rs:938-939
+    uint64_t* bufs[3] = {h_acc, const_cast<uint64_t*>(h_lhs), const_cast<uint64_t*>(h_rhs)};
+    const size_t words[3] = {len, len, len};
+    const bool back[3] = {true, false, false};
+    return product_host(pl, 3, bufs, words, back, [&](uint64_t* const* d, cudaStream_t st) { return cntt_product_mul_accumulate(pl, d[0], d[1], d[2], batch, st); });
 }

@@ -278,8 +278,9 @@ class InvMode:
 
 class ProductPlan:
     """product::Plan (src/product.rs:139-967): negacyclic NTT plan for a modulus that is a product of distinct
-    primes.  Device-resident buffers (torch CUDA int64 tensors): `standard` (batch..., n) and NTT-domain buffers
-    (batch..., ntt_domain_len) in the reference's packed layout (u32 planes first, then u64 planes)."""
+    primes.  `standard` buffers are (batch..., n) and NTT-domain buffers (batch..., ntt_domain_len) u64 words in
+    the reference's packed layout (u32 planes first, then u64 planes); torch CUDA int64 tensors run device-resident
+    and asynchronously, numpy uint64 arrays take the host-slice path (the reference's call shape)."""
 
     def __init__(self, handle, n, modulus, device):
         self._h, self._n, self._modulus, self._device = handle, n, modulus, device
@@ -321,55 +322,74 @@ class ProductPlan:
 
     def _std(self, x, name):
         b = _Buf(x, 8, name)
-        if not b.is_dev:
-            raise TypeError("product::Plan operates on device-resident tensors")
         if len(b.shape) == 0 or b.shape[-1] != self._n:
             raise ReferencePanic("assert_eq!(standard.len(), self.ntt_size())")
         b.batch = b.words // self._n
         return b
 
-    def _dom(self, x, name, batch=None):
+    def _dom(self, x, name, like=None):
         b = _Buf(x, 8, name)
-        if not b.is_dev:
-            raise TypeError("product::Plan operates on device-resident tensors")
         if self._dl == 0:
-            b.batch = batch if batch is not None else 0
+            b.batch = like.batch if like is not None else 0
             if b.words != 0:
                 raise ReferencePanic("assert_eq!(%s.len(), self.ntt_domain_len())" % name)
-            return b
-        if len(b.shape) == 0 or b.shape[-1] != self._dl:
-            raise ReferencePanic("assert_eq!(%s.len(), self.ntt_domain_len())" % name)
-        b.batch = b.words // self._dl
-        if batch is not None and b.batch != batch:
-            raise ReferencePanic("batch sizes differ")
+        else:
+            if len(b.shape) == 0 or b.shape[-1] != self._dl:
+                raise ReferencePanic("assert_eq!(%s.len(), self.ntt_domain_len())" % name)
+            b.batch = b.words // self._dl
+        if like is not None:
+            if b.batch != like.batch:
+                raise ReferencePanic("batch sizes differ")
+            if b.is_dev != like.is_dev:
+                raise TypeError("all buffers of one call must be device tensors or all host arrays")
         return b
 
     def fwd(self, ntt, standard, mode=FwdMode.Generic):
         s = self._std(standard, "standard")
-        d = self._dom(ntt, "ntt", s.batch)
-        check(_lib.lib().cntt_product_fwd(self._h, d.ptr, s.ptr, mode.kind, mode.bound, s.batch, _stream_of(s.t)), "fwd")
+        d = self._dom(ntt, "ntt", s)
+        l = _lib.lib()
+        if s.is_dev:
+            check(l.cntt_product_fwd(self._h, d.ptr, s.ptr, mode.kind, mode.bound, s.batch, _stream_of(s.t)), "fwd")
+        else:
+            check(l.cntt_product_fwd_host(self._h, d.ptr, s.ptr, d.words, s.words, mode.kind, mode.bound, s.batch), "fwd")
         return ntt
 
     def inv(self, standard, ntt, mode=InvMode.Replace):
         s = self._std(standard, "standard")
-        d = self._dom(ntt, "ntt", s.batch)
-        check(_lib.lib().cntt_product_inv(self._h, s.ptr, d.ptr, mode, s.batch, _stream_of(s.t)), "inv")
+        d = self._dom(ntt, "ntt", s)
+        l = _lib.lib()
+        if s.is_dev:
+            check(l.cntt_product_inv(self._h, s.ptr, d.ptr, mode, s.batch, _stream_of(s.t)), "inv")
+        else:
+            check(l.cntt_product_inv_host(self._h, s.ptr, d.ptr, s.words, d.words, mode, s.batch), "inv")
         return standard
 
     def mul_assign_normalize(self, lhs, rhs):
         a = self._dom(lhs, "lhs")
-        b = self._dom(rhs, "rhs", a.batch)
-        check(_lib.lib().cntt_product_mul_assign_normalize(self._h, a.ptr, b.ptr, a.batch, _stream_of(a.t)))
+        b = self._dom(rhs, "rhs", a)
+        l = _lib.lib()
+        if a.is_dev:
+            check(l.cntt_product_mul_assign_normalize(self._h, a.ptr, b.ptr, a.batch, _stream_of(a.t)))
+        else:
+            check(l.cntt_product_mul_assign_normalize_host(self._h, a.ptr, b.ptr, a.words, a.batch))
         return lhs
 
     def normalize(self, values):
         a = self._dom(values, "values")
-        check(_lib.lib().cntt_product_normalize(self._h, a.ptr, a.batch, _stream_of(a.t)))
+        l = _lib.lib()
+        if a.is_dev:
+            check(l.cntt_product_normalize(self._h, a.ptr, a.batch, _stream_of(a.t)))
+        else:
+            check(l.cntt_product_normalize_host(self._h, a.ptr, a.words, a.batch))
         return values
 
     def mul_accumulate(self, acc, lhs, rhs):
         a = self._dom(acc, "acc")
-        l = self._dom(lhs, "lhs", a.batch)
-        r = self._dom(rhs, "rhs", a.batch)
-        check(_lib.lib().cntt_product_mul_accumulate(self._h, a.ptr, l.ptr, r.ptr, a.batch, _stream_of(a.t)))
+        x = self._dom(lhs, "lhs", a)
+        y = self._dom(rhs, "rhs", a)
+        l = _lib.lib()
+        if a.is_dev:
+            check(l.cntt_product_mul_accumulate(self._h, a.ptr, x.ptr, y.ptr, a.batch, _stream_of(a.t)))
+        else:
+            check(l.cntt_product_mul_accumulate_host(self._h, a.ptr, x.ptr, y.ptr, a.words, a.batch))
         return acc

@@ -161,6 +161,13 @@ int cntt_product_inv(const cntt_product_plan* plan, uint64_t* d_standard, uint64
 int cntt_product_mul_assign_normalize(const cntt_product_plan* plan, uint64_t* d_lhs, const uint64_t* d_rhs, size_t batch, void* stream);
 int cntt_product_normalize(const cntt_product_plan* plan, uint64_t* d_values, size_t batch, void* stream);
 int cntt_product_mul_accumulate(const cntt_product_plan* plan, uint64_t* d_acc, const uint64_t* d_lhs, const uint64_t* d_rhs, size_t batch, void* stream);
+/* host-slice flavours: the reference's `&mut [u64]` call shape (lengths checked like its assert_eq!), `batch`
+ * concatenated polynomials, synchronous, staged through the plan's device arena */
+int cntt_product_fwd_host(const cntt_product_plan* plan, uint64_t* h_ntt, const uint64_t* h_standard, size_t ntt_len, size_t standard_len, int mode, uint64_t bound, size_t batch);
+int cntt_product_inv_host(const cntt_product_plan* plan, uint64_t* h_standard, uint64_t* h_ntt, size_t standard_len, size_t ntt_len, int mode, size_t batch);
+int cntt_product_mul_assign_normalize_host(const cntt_product_plan* plan, uint64_t* h_lhs, const uint64_t* h_rhs, size_t len, size_t batch);
+int cntt_product_normalize_host(const cntt_product_plan* plan, uint64_t* h_values, size_t len, size_t batch);
+int cntt_product_mul_accumulate_host(const cntt_product_plan* plan, uint64_t* h_acc, const uint64_t* h_lhs, const uint64_t* h_rhs, size_t len, size_t batch);
 
 #ifdef __cplusplus
 }

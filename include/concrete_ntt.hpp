@@ -142,4 +142,50 @@ namespace native_binary32 { using Plan32 = NativePlan32<32, true, uint32_t>; }
 namespace native_binary64 { using Plan32 = NativePlan32<64, true, uint64_t>; }
 namespace native_binary128 { using Plan32 = NativePlan32<128, true, unsigned __int128>; }
 
+// product::Plan (src/product.rs:139-967): modulus = product of distinct primes.  NTT-domain buffers hold
+// ntt_domain_len() u64 words per polynomial in the reference's packed layout.
+namespace product {
+struct FwdMode {
+    int kind;       // 0 = Generic, 1 = Bounded(bound)
+    uint64_t bound;
+    static FwdMode Generic() { return {0, 0}; }
+    static FwdMode Bounded(uint64_t b) { return {1, b}; }
+};
+enum class InvMode : int { Replace = 0, Accumulate = 1 };
+
+class Plan {
+    cntt_product_plan* h_ = nullptr;
+    explicit Plan(cntt_product_plan* h) : h_(h) {}
+
+  public:
+    Plan(Plan&& o) noexcept : h_(std::exchange(o.h_, nullptr)) {}
+    Plan(const Plan&) = delete;
+    ~Plan() { cntt_product_plan_free(h_); }
+    /* Plan::try_new(polynomial_size, modulus, factors) -> Option<Plan> */
+    static std::optional<Plan> try_new(size_t polynomial_size, uint64_t modulus, const uint64_t* factors, size_t nfactors, int device = 0)
+    {
+        cntt_product_plan* h = nullptr;
+        int st = cntt_product_plan_new(polynomial_size, modulus, factors, nfactors, device, &h);
+        if (is_none(st)) return std::nullopt;
+        check(st);
+        return Plan(h);
+    }
+    size_t ntt_size() const { return cntt_product_ntt_size(h_); }
+    uint64_t modulus() const { return cntt_product_modulus(h_); }
+    size_t ntt_domain_len() const { return cntt_product_ntt_domain_len(h_); }
+    // reference shape: host slices, one polynomial
+    void fwd(uint64_t* ntt, size_t ntt_len, const uint64_t* standard, size_t standard_len, FwdMode mode) const { check(cntt_product_fwd_host(h_, ntt, standard, ntt_len, standard_len, mode.kind, mode.bound, 1)); }
+    void inv(uint64_t* standard, size_t standard_len, uint64_t* ntt, size_t ntt_len, InvMode mode) const { check(cntt_product_inv_host(h_, standard, ntt, standard_len, ntt_len, (int)mode, 1)); }
+    void mul_assign_normalize(uint64_t* lhs, const uint64_t* rhs, size_t len) const { check(cntt_product_mul_assign_normalize_host(h_, lhs, rhs, len, 1)); }
+    void normalize(uint64_t* values, size_t len) const { check(cntt_product_normalize_host(h_, values, len, 1)); }
+    void mul_accumulate(uint64_t* acc, const uint64_t* lhs, const uint64_t* rhs, size_t len) const { check(cntt_product_mul_accumulate_host(h_, acc, lhs, rhs, len, 1)); }
+    // batch / device extensions
+    void fwd_device(uint64_t* ntt, const uint64_t* standard, FwdMode mode, size_t batch, void* stream = nullptr) const { check(cntt_product_fwd(h_, ntt, standard, mode.kind, mode.bound, batch, stream)); }
+    void inv_device(uint64_t* standard, uint64_t* ntt, InvMode mode, size_t batch, void* stream = nullptr) const { check(cntt_product_inv(h_, standard, ntt, (int)mode, batch, stream)); }
+    void mul_assign_normalize_device(uint64_t* lhs, const uint64_t* rhs, size_t batch, void* stream = nullptr) const { check(cntt_product_mul_assign_normalize(h_, lhs, rhs, batch, stream)); }
+    void normalize_device(uint64_t* values, size_t batch, void* stream = nullptr) const { check(cntt_product_normalize(h_, values, batch, stream)); }
+    void mul_accumulate_device(uint64_t* acc, const uint64_t* lhs, const uint64_t* rhs, size_t batch, void* stream = nullptr) const { check(cntt_product_mul_accumulate(h_, acc, lhs, rhs, batch, stream)); }
+};
+} // namespace product
+
 } // namespace concrete_ntt

@@ -113,6 +113,37 @@ int main()
         plan.normalize(buf.data(), buf.size());
         REQUIRE(buf == a);
     }
+    // product::Plan, the tfhe-rs NTT-PBS shape (src/product.rs:444-445): two primes < 2^31; polymul mod p0*p1 through
+    // fwd (Generic and Bounded) / mul_assign_normalize / inv (Replace, then Accumulate), host slices
+    {
+        const size_t n = 256;
+        const uint64_t p0 = prime::largest_prime_in_arithmetic_progression64(2 * n, 1, 0, 1ull << 31).value();
+        const uint64_t p1 = prime::largest_prime_in_arithmetic_progression64(2 * n, 1, 0, p0 - 1).value();
+        const uint64_t p = p0 * p1, factors[2] = {p0, p1};
+        auto plan = product::Plan::try_new(n, p, factors, 2).value();
+        REQUIRE(plan.ntt_size() == n && plan.modulus() == p && plan.ntt_domain_len() == n);
+        const uint64_t dup[3] = {p1, p0, p1};
+        REQUIRE(!product::Plan::try_new(n, p0 * p1 * p1, dup, 3).has_value());   // src/product.rs:1162-1169
+        std::vector<uint64_t> a(n), b(n);
+        for (auto& v : a) v = rng() % 1000;          // small: also a valid input of FwdMode::Bounded(1000)
+        for (auto& v : b) v = rng() % p;
+        auto expect = schoolbook(a, b, p);
+        const size_t dl = plan.ntt_domain_len();
+        std::vector<uint64_t> fa(dl), fa2(dl), fb(dl), out(n), acc(n);
+        plan.fwd(fa.data(), dl, a.data(), n, product::FwdMode::Generic());
+        plan.fwd(fa2.data(), dl, a.data(), n, product::FwdMode::Bounded(1000));
+        REQUIRE(fa == fa2);
+        plan.fwd(fb.data(), dl, b.data(), n, product::FwdMode::Generic());
+        plan.mul_assign_normalize(fa.data(), fb.data(), dl);
+        fa2 = fa;
+        plan.inv(out.data(), n, fa.data(), dl, product::InvMode::Replace);
+        REQUIRE(out == expect);
+        for (auto& v : acc) v = rng() % p;
+        auto acc0 = acc;
+        plan.inv(acc.data(), n, fa2.data(), dl, product::InvMode::Accumulate);
+        for (size_t i = 0; i < n; i++) REQUIRE(acc[i] == (uint64_t)(((unsigned __int128)acc0[i] + expect[i]) % p));
+        try { plan.normalize(fa.data(), dl - 1); REQUIRE(false); } catch (const Panic&) {}
+    }
     std::printf("facade ok\n");
     return 0;
 }

@@ -81,3 +81,31 @@ def test_product_does_not_touch_oracle():
                 assert "oracle" not in txt.lower(), os.path.join(d, f)
     out = subprocess.check_output(["ldd", os.path.join(pkg, "libcntt_b200.so")], text=True)
     assert "oracle" not in out
+
+
+def test_fastdiv_and_prime_helpers(cntt, oracle):
+    """fastdiv::{Div32,Div64} and prime::{mul,exp}_mod (src/fastdiv.rs:152-208 tests: div/rem agree with `/`, `%`)."""
+    g = np.random.Generator(np.random.PCG64(11))
+    D32, D64 = cntt.fastdiv.Div32, cntt.fastdiv.Div64
+    for _ in range(200):
+        d = int(g.integers(2, 2**32))
+        n = int(g.integers(0, 2**64, dtype=np.uint64))
+        dv = D32.new(d)
+        assert dv.divisor() == d
+        assert D32.div(n & 0xFFFFFFFF, dv) == (n & 0xFFFFFFFF) // d and D32.rem(n & 0xFFFFFFFF, dv) == (n & 0xFFFFFFFF) % d
+        assert D32.div_u64(n, dv) == n // d and D32.rem_u64(n, dv) == n % d
+        d = int(g.integers(2, 2**64, dtype=np.uint64))
+        big = n * int(g.integers(0, 2**64, dtype=np.uint64))
+        dv = D64.new(d)
+        assert D64.div(n, dv) == n // d and D64.rem(n, dv) == n % d
+        assert D64.div_u128(big, dv) == big // d and D64.rem_u128(big, dv) == big % d
+    for bad in (0, 1):
+        with pytest.raises(cntt.ReferencePanic):
+            D32.new(bad)
+        with pytest.raises(cntt.ReferencePanic):
+            D64.new(bad)
+    p = 0xFFFFFFFF00000001
+    assert cntt.prime.exp_mod64(D64.new(p), 7, p - 1) == 1 == oracle.exp_mod64(p, 7, p - 1)
+    assert cntt.prime.mul_mod64(D64.new(p), p - 1, p - 1) == 1
+    assert cntt.prime.exp_mod32(D32.new(1062862849), 5, 1062862848) == 1
+    assert cntt.prime.mul_mod32(1062862849, 1062862848, 2) == 1062862847

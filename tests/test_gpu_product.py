@@ -140,3 +140,42 @@ def test_product_pbs_shape_roundtrip_large(cntt, oracle, torch_cuda):
     # n * x mod p for every polynomial, vectorised through the two residues
     for q in (p0, p1):
         assert ((got % np.uint64(q)) == (std % np.uint64(q)) * np.uint64(n % q) % np.uint64(q)).all()
+
+
+def test_product_host_slices(cntt, oracle):
+    """The reference's call shape: numpy host slices through the *_host entry points (staged inside the library)."""
+    n = 512
+    ps = _product_cases(oracle, n)["u32x2_u64x1"]
+    p = _prod(ps)
+    op, gp = oracle.Product.try_new(n, p, ps), cntt.product.Plan.try_new(n, p, ps)
+    g = rng(31337)
+    dl = op.ntt_domain_len()
+    a, b = rand_mod(g, p, (n,), np.uint64), rand_mod(g, p, (n,), np.uint64)
+    ra, rb = np.zeros(dl, np.uint64), np.zeros(dl, np.uint64)
+    ga, gb = np.zeros(dl, np.uint64), np.zeros(dl, np.uint64)
+    op.fwd(ra, a, op.GENERIC); op.fwd(rb, b, op.GENERIC)
+    gp.fwd(ga, a); gp.fwd(gb, b)
+    assert (ga == ra).all() and (gb == rb).all()
+    racc, gacc = ra.copy(), ga.copy()
+    op.mul_accumulate(racc, ra, rb); gp.mul_accumulate(gacc, ga, gb)
+    assert (gacc == racc).all()
+    op.normalize(racc); gp.normalize(gacc)
+    assert (gacc == racc).all()
+    op.mul_assign_normalize(ra, rb); gp.mul_assign_normalize(ga, gb)
+    assert (ga == ra).all()
+    ro, go = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+    keep_r, keep_g = ra.copy(), ga.copy()
+    op.inv(ro, ra, op.REPLACE); gp.inv(go, ga, cntt.product.InvMode.Replace)
+    assert (go == ro).all() and (ga == ra).all()
+    op.inv(ro, keep_r, op.ACCUMULATE); gp.inv(go, keep_g, cntt.product.InvMode.Accumulate)
+    assert (go == ro).all()
+    with pytest.raises(cntt.ReferencePanic):
+        gp.fwd(np.zeros(dl + 1, np.uint64), a)
+    # batch of 3 concatenated polynomials through the same host entry points
+    A = rand_mod(g, p, (3, n), np.uint64)
+    G = np.zeros((3, dl), np.uint64)
+    gp.fwd(G, A)
+    for i in range(3):
+        r = np.zeros(dl, np.uint64)
+        op.fwd(r, A[i], op.GENERIC)
+        assert (G[i] == r).all()
