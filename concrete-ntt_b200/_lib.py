@@ -46,6 +46,7 @@ for _b, _w in (("32", _u32), ("64", _u64)):
     })
 SIGNATURES.update({
     "cntt_native_plan_new": (_int, [_sz, _int, _int, _int, C.POINTER(_vp)]),
+    "cntt_native_plan_new_ext": (_int, [_sz, _int, _int, _int, C.POINTER(_vp)]),
     "cntt_native_plan_free": (None, [_vp]),
     "cntt_native_ntt_size": (_sz, [_vp]),
     "cntt_native_num_primes": (_int, [_vp]),

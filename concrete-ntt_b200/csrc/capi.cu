@@ -633,7 +633,7 @@ struct cntt_native_plan {
     Staging stg;
 };
 
-CNTT_API int cntt_native_plan_new(size_t n, int word_bits, int binary, int device, cntt_native_plan** out)
+static int native_plan_new_impl(size_t n, int word_bits, int binary, int device, int prime_set, cntt_native_plan** out)
 {
     if (!out) return CNTT_NULL_POINTER;
     *out = nullptr;
@@ -642,7 +642,8 @@ CNTT_API int cntt_native_plan_new(size_t n, int word_bits, int binary, int devic
     else if (word_bits == 64) kind = binary ? NK_BINARY64 : NK_NATIVE64;
     else if (word_bits == 128) kind = binary ? NK_BINARY128 : NK_NATIVE128;
     else return CNTT_UNSUPPORTED;
-    const NativeConsts& c = native_consts();
+    if (prime_set != 0 && native_num_primes(kind) > kExtPrimes) return CNTT_UNSUPPORTED; // nine extended primes: no native128
+    const NativeConsts& c = native_consts(prime_set);
     cntt_native_plan* pl = new cntt_native_plan();
     pl->n = n; pl->kind = kind; pl->device = device; pl->nprimes = native_num_primes(kind);
     for (int k = 0; k < 10; k++) pl->sub[k] = nullptr;
@@ -669,8 +670,9 @@ CNTT_API int cntt_native_plan_new(size_t n, int word_bits, int binary, int devic
     pl->dev.kind = kind;
     pl->dev.logn = pl->sub[0]->logn;
     pl->dev.nprimes = pl->nprimes;
+    pl->dev.prime_set = prime_set;
     for (int k = 0; k < pl->nprimes; k++) pl->dev.sub[k] = dev32<A32L4>(pl->sub[k]);
-    native_lhs_scale(pl->dev.logn, pl->dev.lscale);
+    native_lhs_scale(pl->dev.logn, pl->dev.lscale, prime_set);
     for (int k = 0; k < 10; k++) pl->dev.fused_fwd_last[k] = pl->dev.fused_inv_last[k] = nullptr;
     if (native_fused_supported(pl->dev.logn)) {
         DeviceGuard g(device);
@@ -691,6 +693,14 @@ CNTT_API int cntt_native_plan_new(size_t n, int word_bits, int binary, int devic
     }
     *out = pl;
     return CNTT_OK;
+}
+CNTT_API int cntt_native_plan_new(size_t n, int word_bits, int binary, int device, cntt_native_plan** out)
+{
+    return native_plan_new_impl(n, word_bits, binary, device, 0, out);
+}
+CNTT_API int cntt_native_plan_new_ext(size_t n, int word_bits, int binary, int device, cntt_native_plan** out)
+{
+    return native_plan_new_impl(n, word_bits, binary, device, 1, out);
 }
 CNTT_API void cntt_native_plan_free(cntt_native_plan* pl)
 {

@@ -25,7 +25,16 @@ struct NativeConsts {
     uint32_t half_pair_lo[10], half_pair_hi[10]; // floor(P[k-1] P[k] / 2) = lo + hi * P[k-1] (np = 5, 10)
 };
 
-const NativeConsts& native_consts();
+// Prime sets.  Set 0 = the reference's P0..P9.  Set 1 = the "extended" set: the nine primes k 2^17 + 1 in
+// (2^30 - 2^24, 2^30), ascending -- six of them are the reference's P0, P2, P3, P4, P8, P9 -- which admit
+// negacyclic transforms up to N = 65536, one size beyond the reference's limit (P1 - 1 = 2^16 * odd makes
+// native*::Plan32::try_new(65536) return None, src/native64.rs:933-942).  A polymul result does not depend on
+// which primes carried it (it is the exact integer product, wrapped), so extended plans are bit-compatible
+// with the reference wherever both exist; they are an opt-in extension (cntt_native_plan_new_ext), see
+// DESIGN.md section 8.  Unused table slots of set 1 repeat its last prime.
+constexpr int kNativePrimeSets = 2;
+constexpr int kExtPrimes = 9;
+const NativeConsts& native_consts(int set = 0);
 
 enum NativeKind {            // word_bits / binary            reference reconstruction
     NK_NATIVE32 = 0,         // 32 / 0   3 primes              native32.rs:27-56
@@ -42,13 +51,14 @@ struct NativePlanDev {
     int kind;
     int logn;
     int nprimes;
+    int prime_set;          // 0: reference primes, 1: extended set (N up to 65536)
     PlanDev<A32L4> sub[10]; // prime32 sub-plans on P0.. (all < 2^30)
     uint2 lscale[10][4];    // 2^(32 j) * 2^32 / N mod P[k] (Shoup pairs): lhs scaling of the fused polymul
     const uint2* fused_fwd_last[10]; // last-pass twiddle layouts of the fused kernel's engine (Engine::TwSrc::last)
     const uint2* fused_inv_last[10];
 };
 
-void native_lhs_scale(int logn, uint2 (*out)[4]);
+void native_lhs_scale(int logn, uint2 (*out)[4], int set = 0);
 
 // value (batch*n words) -> nprimes residue planes of batch*n u32, plane k at planes + k*plane_stride.
 // copy_low32: fwd_binary's `*value as u32` (no reduction).  Residues are written in the lazy range
@@ -65,7 +75,7 @@ cudaError_t native_fused_build_last(int logn, const uint2* heap, uint2* out, cud
 cudaError_t native_polymul_fused(const NativePlanDev& pl, void* prod, const void* lhs, const void* rhs, size_t batch,
                                  cudaStream_t st);
 
-// three-kernel polymul for 4096 < N <= 32768 (native_large.cuh).  planes_l / planes_r: nprimes planes of batch * n
+// three-kernel polymul for 4096 < N <= 65536 (native_large.cuh; 65536 only exists for extended plans).  planes_l / planes_r: nprimes planes of batch * n
 // u32 each (scratch).  Returns cudaErrorNotSupported for other sizes.
 bool native_large_supported(int logn);
 cudaError_t native_polymul_large(const NativePlanDev& pl, void* prod, const void* lhs, const void* rhs, size_t batch,

@@ -14,6 +14,16 @@ namespace cntt {
 #ifndef CNTT_FUSED_LOGR
 #define CNTT_FUSED_LOGR 3
 #endif
+// experiment toggles (tools/build_variant.sh); the defaults are the shipped configuration
+#ifndef CNTT_FUSED_RELOAD
+#define CNTT_FUSED_RELOAD 0   // 1: re-read the operands from global memory (L2) for every prime instead of holding them in registers
+#endif
+#ifndef CNTT_FUSED_KEEPLAST
+#define CNTT_FUSED_KEEPLAST 0 // 1: the last prime's residues go straight from registers into the Garner lift (no stash plane)
+#endif
+#ifndef CNTT_FUSED_MINBLK
+#define CNTT_FUSED_MINBLK 1   // __launch_bounds__ minimum resident CTAs per SM
+#endif
 constexpr int kFusedMinLogN = 5, kFusedMaxLogN = 12;
 
 struct FusedParams {
@@ -32,7 +42,7 @@ struct FusedCfg {
     static constexpr int T = E::T;
     static constexpr int GP = T >= 128 ? 1 : 128 / T;
     static constexpr int XCHG_WORDS = 2 * E::NBUF * E::SMEM_WORDS;   // two polynomials in flight (lhs, rhs)
-    static constexpr int STASH_WORDS = NP * E::N;
+    static constexpr int STASH_WORDS = (NP - (CNTT_FUSED_KEEPLAST ? 1 : 0)) * E::N;
     static constexpr size_t SMEM_BYTES = (size_t)GP * (XCHG_WORDS + STASH_WORDS) * sizeof(uint32_t);
 };
 
@@ -43,7 +53,7 @@ struct FusedCfg {
 //   pointwise Montgomery product  A B 2^-32 = a b / N   in (0,2p)    (replaces mul_assign_normalize)
 //   inverse NTT, canonical residue parked in shared memory
 template <int KIND, int LOGN, int LOGR>
-__global__ void __launch_bounds__(FusedCfg<KIND, LOGN, LOGR>::GP * FusedCfg<KIND, LOGN, LOGR>::T)
+__global__ void __launch_bounds__(FusedCfg<KIND, LOGN, LOGR>::GP * FusedCfg<KIND, LOGN, LOGR>::T, CNTT_FUSED_MINBLK)
 k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ prod, const void* __restrict__ lhs,
                 const void* __restrict__ rhs, unsigned long long batch)
 {
@@ -67,25 +77,43 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
     const size_t base = (size_t)b * N;
 
     // operands: read once, kept in registers for all primes
-    uint64_t llo[R], rlo[R];
-    uint64_t lhi[WB == 16 ? R : 1], rhi[WB == 16 ? R : 1];
+    constexpr int RK = CNTT_FUSED_RELOAD ? 1 : R;
+    uint64_t llo[RK], rlo[RK];
+    uint64_t lhi[(WB == 16 && !CNTT_FUSED_RELOAD) ? R : 1], rhi[(WB == 16 && !CNTT_FUSED_RELOAD) ? R : 1];
+    if constexpr (!CNTT_FUSED_RELOAD) {
 #pragma unroll
-    for (int k = 0; k < R; k++) {
-        uint64_t h0, h1;
-        dev::load_word<KIND>(lhs, base + tid + k * T, llo[k], h0);
-        dev::load_word<KIND>(rhs, base + tid + k * T, rlo[k], h1);
-        if constexpr (WB == 16) { lhi[k] = h0; rhi[k] = h1; }
+        for (int k = 0; k < R; k++) {
+            uint64_t h0, h1;
+            dev::load_word<KIND>(lhs, base + tid + k * T, llo[k], h0);
+            dev::load_word<KIND>(rhs, base + tid + k * T, rlo[k], h1);
+            if constexpr (WB == 16) { lhi[k] = h0; rhi[k] = h1; }
+        }
     }
+    uint32_t keep[CNTT_FUSED_KEEPLAST ? R : 1];
 
 #pragma unroll 1
     for (int pk = 0; pk < NP; pk++) {
         const Mod32 m = fp.mod[pk];
         const uint32_t p = m.p;
         uint32_t x[2][R];
+        if constexpr (CNTT_FUSED_RELOAD) {
+            uint64_t alo[R], ahi[R], blo[R], bhi[R];
 #pragma unroll
-        for (int k = 0; k < R; k++) {
-            x[0][k] = dev::residue<LIMBS, true>(llo[k], WB == 16 ? lhi[k] : 0ull, fp.lscale[pk], p);
-            x[1][k] = BINARY ? (uint32_t)rlo[k] : dev::residue<LIMBS, false>(rlo[k], WB == 16 ? rhi[k] : 0ull, c.red[pk], p);
+            for (int k = 0; k < R; k++) {
+                dev::load_word<KIND>(lhs, base + tid + k * T, alo[k], ahi[k]);
+                dev::load_word<KIND>(rhs, base + tid + k * T, blo[k], bhi[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                x[0][k] = dev::residue<LIMBS, true>(alo[k], ahi[k], fp.lscale[pk], p);
+                x[1][k] = BINARY ? (uint32_t)blo[k] : dev::residue<LIMBS, false>(blo[k], bhi[k], c.red[pk], p);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                x[0][k] = dev::residue<LIMBS, true>(llo[k], WB == 16 ? lhi[k] : 0ull, fp.lscale[pk], p);
+                x[1][k] = BINARY ? (uint32_t)rlo[k] : dev::residue<LIMBS, false>(rlo[k], WB == 16 ? rhi[k] : 0ull, c.red[pk], p);
+            }
         }
         E::template fwd<2>(x, sm, typename E::TwSrc{fp.tw_fwd[pk], fp.tw_fwd_last[pk]}, 1u, tid, m);
         uint32_t y[1][R];
@@ -94,8 +122,13 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
         for (int k = 0; k < R; k++) y[0][k] = dev::mont(dev::red2p(x[0][k], p), dev::red2p(x[1][k], p), p, pinv);
         if constexpr (E::NBUF == 1 && E::P >= 2) __syncthreads(); // single exchange buffer: fwd gather vs inv scatter
         E::template inv<1>(y, sm, typename E::TwSrc{fp.tw_inv[pk], fp.tw_inv_last[pk]}, 1u, tid, m);
+        if (CNTT_FUSED_KEEPLAST && pk == NP - 1) {
 #pragma unroll
-        for (int k = 0; k < R; k++) stash[pk * N + tid + k * T] = A32L4::canon_inv(y[0][k], m);
+            for (int k = 0; k < R; k++) keep[CNTT_FUSED_KEEPLAST ? k : 0] = A32L4::canon_inv(y[0][k], m);
+        } else {
+#pragma unroll
+            for (int k = 0; k < R; k++) stash[pk * N + tid + k * T] = A32L4::canon_inv(y[0][k], m);
+        }
         if constexpr (E::NBUF == 1 && E::P >= 2) __syncthreads(); // inv gather vs next prime's fwd scatter
     }
 
@@ -104,7 +137,8 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
         for (int k = 0; k < R; k++) {
             uint32_t r[NP];
 #pragma unroll
-            for (int pk = 0; pk < NP; pk++) r[pk] = stash[pk * N + tid + k * T];
+            for (int pk = 0; pk < NP; pk++)
+                r[pk] = (CNTT_FUSED_KEEPLAST && pk == NP - 1) ? keep[CNTT_FUSED_KEEPLAST ? k : 0] : stash[pk * N + tid + k * T];
             dev::store_word<KIND>(prod, base + tid + k * T, dev::reconstruct<KIND>(r, c));
         }
     }
@@ -133,7 +167,7 @@ static cudaError_t launch_fused_one(const NativePlanDev& pl, void* prod, const v
     }
     const unsigned long long nblk = (batch + Cfg::GP - 1) / Cfg::GP;
     if (nblk > 0x7fffffffull) return cudaErrorInvalidValue;
-    kern<<<(unsigned)nblk, Cfg::GP * Cfg::T, Cfg::SMEM_BYTES, st>>>(native_consts(), fp, prod, lhs, rhs, batch);
+    kern<<<(unsigned)nblk, Cfg::GP * Cfg::T, Cfg::SMEM_BYTES, st>>>(native_consts(pl.prime_set), fp, prod, lhs, rhs, batch);
     return cudaGetLastError();
 }
 

@@ -8,16 +8,21 @@
 namespace cntt {
 
 // ---- host: constants -----------------------------------------------------------------------------
-static NativeConsts g_consts;
+static NativeConsts g_consts[kNativePrimeSets];
 static std::once_flag g_consts_once;
 
-static void fill_consts()
+static void fill_consts_set(int set)
 {
     using host::Fp;
     typedef unsigned __int128 u128;
-    NativeConsts& c = g_consts;
-    static const uint32_t P[10] = {0x3F5A0001u, 0x3F5D0001u, 0x3F760001u, 0x3F820001u, 0x3FAC0001u,
-                                   0x3FAF0001u, 0x3FB10001u, 0x3FBB0001u, 0x3FDE0001u, 0x3FFC0001u}; // src/lib.rs:453-462
+    NativeConsts& c = g_consts[set];
+    static const uint32_t PSETS[kNativePrimeSets][10] = {
+        {0x3F5A0001u, 0x3F5D0001u, 0x3F760001u, 0x3F820001u, 0x3FAC0001u,
+         0x3FAF0001u, 0x3FB10001u, 0x3FBB0001u, 0x3FDE0001u, 0x3FFC0001u}, // src/lib.rs:453-462
+        {0x3F3A0001u, 0x3F540001u, 0x3F5A0001u, 0x3F760001u, 0x3F820001u,
+         0x3FAC0001u, 0x3FD20001u, 0x3FDE0001u, 0x3FFC0001u, 0x3FFC0001u}, // every prime k 2^17 + 1 in (2^30 - 2^24, 2^30); slot 9 unused
+    };
+    const uint32_t* P = PSETS[set];
     auto shoup = [](uint64_t w, uint32_t p) { return make_uint2((uint32_t)w, (uint32_t)((w << 32) / p)); };
     for (int k = 0; k < 10; k++) {
         const uint32_t p = P[k];
@@ -49,16 +54,16 @@ static void fill_consts()
     }
 }
 
-const NativeConsts& native_consts()
+const NativeConsts& native_consts(int set)
 {
-    std::call_once(g_consts_once, fill_consts);
-    return g_consts;
+    std::call_once(g_consts_once, [] { for (int s = 0; s < kNativePrimeSets; s++) fill_consts_set(s); });
+    return g_consts[(set >= 0 && set < kNativePrimeSets) ? set : 0];
 }
 
 // lhs scale constants of the fused polymul: 2^(32 j) * 2^32 * N^-1 mod P[k] (Shoup pairs)
-void native_lhs_scale(int logn, uint2 (*out)[4])
+void native_lhs_scale(int logn, uint2 (*out)[4], int set)
 {
-    const NativeConsts& c = native_consts();
+    const NativeConsts& c = native_consts(set);
     for (int k = 0; k < 10; k++) {
         host::Fp f(c.P[k]);
         const uint64_t ninv = f.inv(((uint64_t)1 << logn) % c.P[k]);
@@ -123,7 +128,7 @@ cudaError_t native_reduce(const NativePlanDev& pl, const void* value, uint32_t* 
                           bool copy_low32, cudaStream_t st)
 {
     if (nwords == 0) return cudaSuccess;
-    const NativeConsts& c = native_consts();
+    const NativeConsts& c = native_consts(pl.prime_set);
     const unsigned g = grid_for(nwords);
 #define CNTT_RED(WB, NP)                                                                                           \
     do {                                                                                                           \
@@ -147,7 +152,7 @@ cudaError_t native_crt(const NativePlanDev& pl, void* value, const uint32_t* pla
                        cudaStream_t st)
 {
     if (nwords == 0) return cudaSuccess;
-    const NativeConsts& c = native_consts();
+    const NativeConsts& c = native_consts(pl.prime_set);
     const unsigned g = grid_for(nwords);
     switch (pl.kind) {
     case NK_NATIVE32: k_native_crt<NK_NATIVE32><<<g, 256, 0, st>>>(c, value, planes, plane_stride, nwords); break;

@@ -1,6 +1,6 @@
-// native_large.cuh -- negacyclic polymul of the native / native_binary plans for 4096 < N <= 32768.
+// native_large.cuh -- negacyclic polymul of the native / native_binary plans for 4096 < N <= 32768 (65536: extended plans).
 //
-// A residue polynomial of N = C * 4096 u32 words (C = 2, 4, 8) no longer fits one CTA, so the product is
+// A residue polynomial of N = C * 4096 u32 words (C = 2, 4, 8, 16) no longer fits one CTA, so the product is
 // computed by three kernels around the residue planes, each touching every byte once:
 //
 //   k_large_lead_fwd   per coefficient column j < 4096: the C words value[j + 4096 r] of an operand are read once,
@@ -22,7 +22,7 @@
 namespace cntt {
 
 constexpr int kLargeRowLog = 12;                 // rows of 4096 words: the CTA engine's largest transform
-constexpr int kLargeMinLogN = 13, kLargeMaxLogN = 15;
+constexpr int kLargeMinLogN = 13, kLargeMaxLogN = 16; // 16 (C = 16 rows): extended prime set only
 
 struct LargeParams {
     const uint2* tw_fwd[10];
@@ -162,7 +162,7 @@ static cudaError_t launch_large_kc(const NativePlanDev& pl, void* prod, const vo
         lp.mod[k] = pl.sub[k].mod;
         for (int j = 0; j < 4; j++) lp.lscale[k][j] = pl.lscale[k][j];
     }
-    const NativeConsts& c = native_consts();
+    const NativeConsts& c = native_consts(pl.prime_set);
     const size_t plane_stride = batch << (kLargeRowLog + LOGC);
     const unsigned long long ncols = (unsigned long long)batch << kLargeRowLog;
     if (((ncols + 127) / 128) > 0x7fffffffull || (batch << LOGC) > 0x7fffffffull) return cudaErrorInvalidValue;
@@ -186,6 +186,9 @@ static cudaError_t launch_large_kind(const NativePlanDev& pl, void* prod, const 
     case 1: return launch_large_kc<KIND, 1>(pl, prod, lhs, rhs, batch, planes_l, planes_r, st);
     case 2: return launch_large_kc<KIND, 2>(pl, prod, lhs, rhs, batch, planes_l, planes_r, st);
     case 3: return launch_large_kc<KIND, 3>(pl, prod, lhs, rhs, batch, planes_l, planes_r, st);
+    case 4: // N = 65536: extended plans; the 10-prime kind has no extended set (nine primes only)
+        if constexpr (KIND != NK_NATIVE128) return launch_large_kc<KIND, 4>(pl, prod, lhs, rhs, batch, planes_l, planes_r, st);
+        else return cudaErrorNotSupported;
     default: return cudaErrorNotSupported;
     }
 }

@@ -53,6 +53,9 @@ template <class W> __device__ __forceinline__ int pad_idx(int i) { return i + (i
 #ifndef CNTT_NBUF64
 #define CNTT_NBUF64 1
 #endif
+#ifndef CNTT_NBUF32
+#define CNTT_NBUF32 2
+#endif
 #ifndef CNTT_HEAD_MINS
 #define CNTT_HEAD_MINS 16
 #endif
@@ -94,7 +97,7 @@ struct Engine {
     }
     static constexpr bool kXor = any_wants_perm<0>() && !kPermFeasible;
     static constexpr int SMEM_WORDS = kXor ? N : padded_words<W>(N); // per polynomial, per buffer
-    static constexpr int NBUF = (P >= 3 && !(sizeof(W) == 8 && CNTT_NBUF64 == 1)) ? 2 : 1; // ping-pong when >1 exchange
+    static constexpr int NBUF = (P >= 3 && !(sizeof(W) == 8 && CNTT_NBUF64 == 1) && !(sizeof(W) == 4 && CNTT_NBUF32 == 1)) ? 2 : 1; // ping-pong when >1 exchange
 
     template <int Q> static __device__ __forceinline__ void decomp(int tid, int& blk, int& o)
     {
@@ -273,6 +276,7 @@ struct Engine {
             scatter<Q, NP>(x, buf, tid);
             __syncthreads();
             gather<Q - 1, NP>(x, buf, tid);
+            if constexpr (NBUF == 1 && Q >= 2) __syncthreads();
             inv_from<Q - 1, NP>(x, sm, tw, nu0, tid, m);
         }
     }

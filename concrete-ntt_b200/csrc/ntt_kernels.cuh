@@ -99,8 +99,17 @@ __device__ __forceinline__ void load_contig(const W* __restrict__ src, W (&x)[R]
 // carries NP polynomials loads each twiddle once for NP butterflies: the last pass reads R-1 table entries
 // per thread (2x the bytes of the data itself for u32 Shoup pairs), and L1TEX wavefronts -- 73 % of them
 // global loads, mostly twiddles -- were the limiter of the u32 kernels at NP = 1 (ncu r01).
+// experiment toggle: resident threads per SM the 64-bit kernels are compiled for (0: no register cap)
+#ifndef CNTT_CTA_MINTHREADS64
+#define CNTT_CTA_MINTHREADS64 0
+#endif
+template <class A, int LOGN, int LOGR, int GP>
+constexpr int cta_min_blocks()
+{
+    return (sizeof(typename A::W) == 8 && CNTT_CTA_MINTHREADS64 > GP * Geo<LOGN, LOGR>::T) ? CNTT_CTA_MINTHREADS64 / (GP * Geo<LOGN, LOGR>::T) : 1;
+}
 template <class A, int LOGN, int LOGR, int GP, bool FWD, bool HEAD, int NP>
-__global__ void __launch_bounds__(GP * Geo<LOGN, LOGR>::T)
+__global__ void __launch_bounds__(GP * Geo<LOGN, LOGR>::T, cta_min_blocks<A, LOGN, LOGR, GP>())
 k_ntt_cta(const typename A::Tw* __restrict__ tw, const typename A::Tw* __restrict__ tw_last, const typename A::Mod m,
           typename A::W* __restrict__ data, unsigned long long nvpoly, int log_sub, unsigned long long poly_stride,
           const __grid_constant__ TwHead<typename A::Tw> head)

@@ -174,14 +174,35 @@ class _NativePlan:
         self._np = _lib.lib().cntt_native_num_primes(handle)
 
     @classmethod
-    def try_new(cls, n, device=0):
-        l = _lib.lib()
+    def _new(cls, ctor, n, device):
         h = C.c_void_p()
-        st = l.cntt_native_plan_new(n, cls._bits, int(cls._binary), device, C.byref(h))
-        if st in (_lib.INVALID_SIZE, _lib.INVALID_MODULUS, _lib.NO_ROOT):
+        st = ctor(n, cls._bits, int(cls._binary), device, C.byref(h))
+        if st in (_lib.INVALID_SIZE, _lib.INVALID_MODULUS, _lib.NO_ROOT, _lib.UNSUPPORTED):
             return None
         check(st, "try_new")
         return cls(h, n, device)
+
+    @classmethod
+    def try_new(cls, n, device=0):
+        """Plan32::try_new(n): None unless 32 <= n <= 32768 is a power of two (src/native64.rs:933-942)."""
+        return cls._new(_lib.lib().cntt_native_plan_new, n, device)
+
+    @classmethod
+    def try_new_extended(cls, n, device=0):
+        """EXTENSION, no reference counterpart: the same plan on the primes k*2^17+1 below 2^30, which also
+        admit n = 65536 (BASELINE.json configs[4]).  None for native128 (needs ten primes, nine exist)."""
+        return cls._new(_lib.lib().cntt_native_plan_new_ext, n, device)
+
+    def ntt_i(self, i):
+        """Plan32::ntt_0() .. ntt_9() (src/native64.rs:950-969): the prime32::Plan of the i-th prime.  A plan is a
+        pure function of (n, p), so this is an equal plan on the same device -- use it for NTT-domain work on the
+        residue planes (mul_accumulate against a pre-transformed key, src/prime32.rs:905-927)."""
+        if not 0 <= i < self._np:
+            raise IndexError(i)
+        cache = self.__dict__.setdefault("_ntt", {})
+        if i not in cache:
+            cache[i] = Plan32Prime.try_new(self._n, self.ntt_modulus(i), device=self._device)
+        return cache[i]
 
     def __del__(self):
         try:
@@ -251,6 +272,18 @@ class _NativePlan:
         else:
             check(_lib.lib().cntt_native_polymul_host(self._h, p.ptr, l.ptr, r.ptr, p.batch * self._n, p.batch))
         return prod
+
+
+class Plan52Unavailable:
+    """native32/native64/native_binary32/native_binary64::Plan52 (src/native64.rs:1072-1165 ...).  In the reference
+    the type exists only with feature = "nightly" on x86-64, and its try_new returns None unless the CPU has
+    AVX-512 IFMA (src/native64.rs:1075-1079).  Its polymul results are identical to Plan32's -- only the public
+    residue format (u64 residues mod ~50-bit primes) differs, and that format is tied to IFMA's 52-bit
+    multiplier, which has no GPU analogue.  This mirror is the no-IFMA behaviour: try_new -> None."""
+
+    @classmethod
+    def try_new(cls, n, device=0):
+        return None
 
 
 class FwdMode:

@@ -121,6 +121,13 @@ int cntt_prime64_mul_accumulate_host(const cntt_prime64_plan* plan, uint64_t* h_
 typedef struct cntt_native_plan cntt_native_plan;
 /* Plan32::try_new(n)  -- CNTT_NO_ROOT when n > 32768 (P1 - 1 = 2^16 * odd, src/lib.rs:454) */
 int cntt_native_plan_new(size_t n, int word_bits, int binary, int device, cntt_native_plan** out);
+/* EXTENSION (no reference counterpart): the same plan kinds on the nine primes k*2^17+1 just below 2^30
+ * (six of them are the reference's P0,P2,P3,P4,P8,P9), which admit n up to 65536 -- BASELINE.json configs[4],
+ * native_binary64 N=65536, for which the reference's try_new returns None.  polymul results are independent of
+ * the primes (exact product, wrapped), so wherever both constructors succeed their polymul outputs are
+ * identical; fwd/inv residue planes are relative to cntt_native_prime(plan, i).  word_bits 128 non-binary needs
+ * ten primes: CNTT_UNSUPPORTED. */
+int cntt_native_plan_new_ext(size_t n, int word_bits, int binary, int device, cntt_native_plan** out);
 void cntt_native_plan_free(cntt_native_plan* plan);
 size_t cntt_native_ntt_size(const cntt_native_plan* plan);
 int cntt_native_num_primes(const cntt_native_plan* plan);

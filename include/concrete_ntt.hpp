@@ -117,6 +117,17 @@ class NativePlan32 {
         check(st);
         return NativePlan32(h);
     }
+    // EXTENSION (no reference counterpart): primes k*2^17+1, n up to 65536 -- see cntt_native_plan_new_ext
+    static std::optional<NativePlan32> try_new_extended(size_t n, int device = 0)
+    {
+        cntt_native_plan* h = nullptr;
+        int st = cntt_native_plan_new_ext(n, BITS, BINARY ? 1 : 0, device, &h);
+        if (is_none(st) || st == CNTT_UNSUPPORTED) return std::nullopt;
+        check(st);
+        return NativePlan32(h);
+    }
+    // Plan32::ntt_0() .. ntt_9(): an equal prime32::Plan (plans are pure functions of (n, p))
+    std::optional<prime32::Plan> ntt_i(int i, int device = 0) const { return prime32::Plan::try_new(ntt_size(), cntt_native_prime(h_, i), device); }
     size_t ntt_size() const { return cntt_native_ntt_size(h_); }
     int num_primes() const { return cntt_native_num_primes(h_); }
     uint32_t ntt_modulus(int i) const { return cntt_native_prime(h_, i); }

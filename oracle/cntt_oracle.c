@@ -1325,6 +1325,42 @@ EXPORT void o_schoolbook128(size_t n, const u64 *lhs, const u64 *rhs, u64 *out)
     free(acc);
 }
 
+/* The same wrapping negacyclic convolution (the reference's test oracle, src/native64.rs:1176-1215) in a
+ * form that is fast enough for n = 65536: word_bits in {32, 64, 128}, zero lhs coefficients skipped, rows
+ * split at the wrap point, OpenMP over output halves.  Used to check the extended plans (n = 65536 has no
+ * reference implementation at all; the wrapping product itself is the specification). */
+EXPORT void o_negacyclic_wrapping(size_t n, int word_bits, const void *lhs, const void *rhs, void *out, int nthreads)
+{
+    (void)nthreads;
+    if (word_bits == 32) {
+        const u32 *a = (const u32 *)lhs, *b = (const u32 *)rhs; u32 *o = (u32 *)out;
+#pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1) schedule(static)
+        for (size_t k = 0; k < n; k++) {
+            u32 acc = 0;
+            for (size_t i = 0; i <= k; i++) acc += a[i] * b[k - i];
+            for (size_t i = k + 1; i < n; i++) acc -= a[i] * b[n + k - i];
+            o[k] = acc;
+        }
+    } else if (word_bits == 64) {
+        const u64 *a = (const u64 *)lhs, *b = (const u64 *)rhs; u64 *o = (u64 *)out;
+#pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1) schedule(static)
+        for (size_t k = 0; k < n; k++) {
+            u64 acc = 0;
+            for (size_t i = 0; i <= k; i++) acc += a[i] * b[k - i];
+            for (size_t i = k + 1; i < n; i++) acc -= a[i] * b[n + k - i];
+            o[k] = acc;
+        }
+    } else {
+#pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1) schedule(static)
+        for (size_t k = 0; k < n; k++) {
+            u128 acc = 0;
+            for (size_t i = 0; i <= k; i++) { u128 x = load_word(lhs, 128, i); if (x) acc += x * load_word(rhs, 128, k - i); }
+            for (size_t i = k + 1; i < n; i++) { u128 x = load_word(lhs, 128, i); if (x) acc -= x * load_word(rhs, 128, n + k - i); }
+            store_word(out, 128, k, acc);
+        }
+    }
+}
+
 /* Direct evaluation of the transform definition, independent of the stage drivers:
  * out[j] = sum_i a[i] * psi^((2*brv(j)+1)*i) mod p   (SURVEY.md section 0). */
 EXPORT void o_direct_fwd64(size_t n, u64 p, u64 psi, const u64 *a, u64 *out)

@@ -73,6 +73,7 @@ def _load(native=False):
         "o_schoolbook64": (None, [sz, C.c_uint64, vp, vp, vp]),
         "o_schoolbook128": (None, [sz, vp, vp, vp]),
         "o_direct_fwd64": (None, [sz, C.c_uint64, C.c_uint64, vp, vp]),
+        "o_negacyclic_wrapping": (None, [sz, C.c_int, vp, vp, vp, C.c_int]),
         "o_max_threads": (C.c_int, []),
         "o_plan32_fwd_batch": (None, [vp, vp, sz, C.c_int]),
         "o_plan32_inv_batch": (None, [vp, vp, sz, C.c_int]),
@@ -466,6 +467,14 @@ def schoolbook64(p, lhs, rhs):
 def schoolbook128(lhs, rhs):
     out = np.empty_like(lhs)
     lib().o_schoolbook128(lhs.shape[0], _ptr(lhs), _ptr(rhs), _ptr(out))
+    return out
+
+
+def negacyclic_wrapping(bits, lhs, rhs, nthreads=None):
+    """wrapping negacyclic product of one polynomial pair (any n; the specification of the extended plans)"""
+    out = np.empty_like(lhs)
+    n = lhs.shape[0]
+    lib().o_negacyclic_wrapping(n, bits, _ptr(lhs), _ptr(rhs), _ptr(out), nthreads or max_threads())
     return out
 
 

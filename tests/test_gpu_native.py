@@ -158,3 +158,114 @@ def test_full_size_config3_properties(cntt, oracle, torch_cuda):
     one[:, 0] = 1
     plan.negacyclic_polymul(ab, da, one)
     assert torch.equal(ab, da)
+
+
+# ---- extended plans (EXTENSION, no reference counterpart): primes k*2^17+1, n up to 65536 -----------------------------
+EXT_PRIMES = [0x3F3A0001, 0x3F540001, 0x3F5A0001, 0x3F760001, 0x3F820001, 0x3FAC0001, 0x3FD20001, 0x3FDE0001, 0x3FFC0001]
+
+
+def ext_plan(cntt, n, bits, binary):
+    mod = getattr(cntt, ("native_binary%d" if binary else "native%d") % bits)
+    return mod.Plan32.try_new_extended(n)
+
+
+@pytest.mark.parametrize("n", [64, 2048, 4096, 16384])
+def test_extended_polymul_equals_reference_plan(cntt, oracle, torch_cuda, n):
+    """Wherever both constructors succeed the polymul of an extended plan is bit-identical to the reference
+    plan's (the product is exact and then wrapped: it cannot depend on the primes that carried it)."""
+    g = rng(900 + n)
+    for bits, binary in [(32, False), (64, False), (32, True), (64, True), (128, True)]:
+        gp = ext_plan(cntt, n, bits, binary)
+        op = oracle.Native.try_new(n, bits, binary=binary)
+        assert [gp.ntt_modulus(i) for i in range(gp.num_primes())] == EXT_PRIMES[:gp.num_primes()]
+        lhs = rand_words(g, bits, (3, n))
+        rhs = make_rhs(g, bits, (3, n), binary)
+        dl, dr = dev(torch_cuda, lhs), dev(torch_cuda, rhs)
+        dp = torch_cuda.empty_like(dl)
+        gp.negacyclic_polymul(dp, dl, dr)
+        assert (host(dp, np.uint32 if bits == 32 else np.uint64) == op.negacyclic_polymul(lhs, rhs)).all(), (bits, binary)
+    assert cntt.native128.Plan32.try_new_extended(n) is None   # ten primes needed, nine exist
+
+
+def test_extended_n65536_polymul(cntt, oracle, torch_cuda):
+    """BASELINE configs[4]: native_binary64 N = 65536 (and the other kinds the nine primes can carry) against the
+    wrapping negacyclic schoolbook -- the specification itself, the reference has no plan of this size."""
+    n = 65536
+    g = rng(65536)
+    assert cntt.native_binary64.Plan32.try_new(n) is None            # reference behaviour is unchanged
+    for bits, binary, batch in [(64, True, 3), (64, False, 2), (32, False, 2), (32, True, 2), (128, True, 1)]:
+        gp = ext_plan(cntt, n, bits, binary)
+        assert gp is not None and gp.ntt_size() == n
+        lhs = rand_words(g, bits, (batch, n))
+        if bits == 128:  # keep the O(n^2) u128 oracle short: sparse lhs (zero coefficients are skipped)
+            keep = g.integers(0, n, 512)
+            sparse = np.zeros_like(lhs)
+            sparse[:, keep] = lhs[:, keep]
+            lhs = sparse
+        rhs = make_rhs(g, bits, (batch, n), binary)
+        dl, dr = dev(torch_cuda, lhs), dev(torch_cuda, rhs)
+        dp = torch_cuda.empty_like(dl)
+        gp.negacyclic_polymul(dp, dl, dr)
+        got = host(dp, np.uint32 if bits == 32 else np.uint64)
+        for b in range(batch):
+            assert (got[b] == oracle.negacyclic_wrapping(bits, lhs[b], rhs[b])).all(), (bits, binary, b)
+        hp = np.empty_like(lhs)                                        # host-slice flavour
+        gp.negacyclic_polymul(hp, lhs, rhs)
+        assert (hp == got).all()
+
+
+def test_extended_n65536_split_planes(cntt, oracle, torch_cuda):
+    """fwd / inv of an extended plan at N = 65536: planes are the per-prime transforms (oracle prime32 plans on
+    the extended primes) of value mod p; inv(fwd(x)) == N * x wrapping (centred lift is exact: N x < prod/2)."""
+    n, batch = 65536, 2
+    g = rng(17)
+    gp = ext_plan(cntt, n, 64, True)
+    val = rand_words(g, 64, (batch, n))
+    planes = torch_cuda.empty((3, batch, n), dtype=torch_cuda.int32, device="cuda")
+    gp.fwd(dev(torch_cuda, val), planes)
+    hp = host(planes, np.uint32)
+    for k in range(3):
+        p = EXT_PRIMES[k]
+        op = oracle.Plan32.try_new(n, p)
+        for b in range(batch):
+            assert (hp[k, b] == op.fwd((val[b] % np.uint64(p)).astype(np.uint32))).all()
+    out = dev(torch_cuda, np.zeros_like(val))
+    gp.inv(out, planes)
+    assert (host(out, np.uint64) == val * np.uint64(n)).all()
+
+
+def test_split_phase_key_switch_shape(cntt, oracle, torch_cuda):
+    """SURVEY.md 8(f) rank 2 -- the TFHE usage: the key stays in the NTT domain, many mul_accumulate per inv.
+    sum_k a_k * b_k (negacyclic, wrapping) via fwd planes, ntt_i().mul_accumulate on every plane, one inv.
+    inv returns N * (sum), so the check is against N * sum of oracle polymuls (src/native64.rs:971-1038,
+    src/prime32.rs:905-927)."""
+    torch = torch_cuda
+    n, batch, terms = 1024, 4, 3
+    g = rng(2718)
+    gp = cntt.native64.Plan32.try_new(n)
+    op = oracle.Native.try_new(n, 64)
+    npz = gp.num_primes()
+    a = rand_words(g, 64, (terms, batch, n))
+    b = rand_words(g, 64, (terms, batch, n))
+    # keep the integer sum inside the centred CRT range: |sum| * N < prod(P)/2 needs small-ish operands
+    a >>= np.uint64(8)
+    b >>= np.uint64(8)
+    acc = torch.zeros((npz, batch, n), dtype=torch.int32, device="cuda")
+    pa = torch.empty_like(acc)
+    pb = torch.empty_like(acc)
+    for k in range(terms):
+        gp.fwd(dev(torch, a[k]), pa)
+        gp.fwd(dev(torch, b[k]), pb)
+        for i in range(npz):
+            gp.ntt_i(i).mul_accumulate(acc[i], pa[i], pb[i])
+    out = torch.empty((batch, n), dtype=torch.int64, device="cuda")
+    gp.inv(out, acc)
+    ref = np.zeros((batch, n), np.uint64)
+    for k in range(terms):
+        ref += op.negacyclic_polymul(a[k], b[k])
+    assert (host(out, np.uint64) == ref * np.uint64(n)).all()
+
+
+def test_plan52_is_none_like_a_non_ifma_host(cntt):
+    for mod in (cntt.native32, cntt.native64, cntt.native_binary32, cntt.native_binary64):
+        assert mod.Plan52.try_new(1024) is None      # src/native64.rs:1075-1079 without AVX-512 IFMA

@@ -371,3 +371,25 @@ def test_product_bounded_and_polymul(oracle):
     plan.mul_assign_normalize(a, c)
     plan.inv(acc, a, plan.ACCUMULATE)
     assert [int(x) for x in acc] == [(int(s) + r) % p for s, r in zip(acc0, ref)]
+
+
+def test_fast_wrapping_schoolbook_equals_reference_test_oracle(oracle):
+    """o_negacyclic_wrapping (used to check the N = 65536 extension) == the reference's own test oracle
+    (wrapping schoolbook, src/native64.rs:1176-1215 / native128.rs:359-372) at sizes both can run."""
+    g = np.random.Generator(np.random.PCG64(77))
+    for n in (32, 100, 256):
+        a = g.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+        b = g.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+        assert (oracle.negacyclic_wrapping(32, a, b) == oracle.schoolbook32(0, a, b)).all()
+        a = g.integers(0, 2**64, size=n, dtype=np.uint64)
+        b = g.integers(0, 2**64, size=n, dtype=np.uint64)
+        assert (oracle.negacyclic_wrapping(64, a, b) == oracle.schoolbook64(0, a, b)).all()
+        a = g.integers(0, 2**64, size=(n, 2), dtype=np.uint64)
+        b = g.integers(0, 2**64, size=(n, 2), dtype=np.uint64)
+        a[::3] = 0
+        assert (oracle.negacyclic_wrapping(128, a, b) == oracle.schoolbook128(a, b)).all()
+    # and against the oracle's NTT-based native64 polymul at the reference's largest size
+    n = 32768
+    a = g.integers(0, 2**64, size=n, dtype=np.uint64)
+    b = g.integers(0, 2**64, size=n, dtype=np.uint64)
+    assert (oracle.negacyclic_wrapping(64, a, b) == oracle.Native.try_new(n, 64).negacyclic_polymul(a, b)).all()

@@ -19,7 +19,7 @@ for c in cases:
     if kind.startswith("native") or kind.startswith("binary"):
         bits = int(kind.replace("native", "").replace("binary", ""))
         mod = getattr(cntt, ("native_binary%d" if kind.startswith("binary") else "native%d") % bits)
-        plan = mod.Plan32.try_new(n)
+        plan = mod.Plan32.try_new(n) or mod.Plan32.try_new_extended(n)
         shape = (batch, n, 2) if bits == 128 else (batch, n)
         dt = torch.int32 if bits == 32 else torch.int64
         hi = 2**31 - 1 if bits == 32 else 2**63 - 1
