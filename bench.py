@@ -68,27 +68,79 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).  NVML is polled
+    in-process every 2 ms (the timed region of the default run is ~50 ms, shorter than nvidia-smi's start-up);
+    `nvidia-smi --query-gpu=... -lms` is the fallback when pynvml is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.samples, self.lines, self.proc = index, [], [], None
+        self.nvml, self.handle, self.stop_flag, self.thread, self.smax = None, None, False, None, None
+
+    def _phys_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.index])
+            except Exception:
+                pass
+        return self.index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._phys_index())
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self._phys_index()), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            t_end = time.time() + 5.0
+            while not self.lines and time.time() < t_end:   # wait for nvidia-smi's first sample
+                time.sleep(0.02)
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        n = self.nvml
+        names = (("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap))
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                try:
+                    pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                except Exception:
+                    pw = None
+                self.samples.append((time.time(), sm, [k for k, bit in names if mask & bit], pw))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append((time.time(), line.strip()))
 
     def stop(self, t0, t1):
+        if self.nvml is not None:
+            self.stop_flag = True
+            if self.thread:
+                self.thread.join(timeout=1.0)
+            inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples
+            reasons = sorted({r for s in inside for r in s[2]})
+            power = [s[3] for s in inside if s[3] is not None]
+            return {"sm_mhz": float(np.median([s[1] for s in inside])) if inside else None, "sm_max_mhz": self.smax,
+                    "reasons": reasons, "power_w_max": max(power) if power else None, "samples": len(inside), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -116,7 +168,7 @@ class ClockSampler:
                 except Exception:
                     pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "power_w_max": max(power) if power else None, "samples": len(sm)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "source": "nvidia-smi"}
 
 
 def make_inputs(rank, batch, n, p):

@@ -43,6 +43,30 @@ template <class A, int LOGN> struct CtaCfg {
     typedef Engine<A, LOGN, LOGR> E;
 };
 
+// ---- batch data accesses ----------------------------------------------------------------------
+// Batch words are touched exactly once per launch; with CNTT_STREAM_LDST they bypass L1 allocation (ld.global.cs /
+// st.global.cs) so that the few KB of L1 left beside the shared-memory carve-out keep the twiddle tables, which
+// every polynomial re-reads.
+#ifndef CNTT_STREAM_LDST
+#define CNTT_STREAM_LDST 1
+#endif
+template <class T> __device__ __forceinline__ T ld_data(const T* p)
+{
+#if CNTT_STREAM_LDST
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+template <class T> __device__ __forceinline__ void st_data(T* p, T v)
+{
+#if CNTT_STREAM_LDST
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
 // ---- vector helpers -------------------------------------------------------------------------
 template <class W, int R>
 __device__ __forceinline__ void store_contig(W* __restrict__ dst, const W (&x)[R])
@@ -60,11 +84,11 @@ __device__ __forceinline__ void store_contig(W* __restrict__ dst, const W (&x)[R
                 uint64_t a = (uint64_t)x[2 * v], b = (uint64_t)x[2 * v + 1];
                 q = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
             }
-            d4[v] = q;
+            st_data(d4 + v, q);
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < R; k++) dst[k] = x[k];
+        for (int k = 0; k < R; k++) st_data(dst + k, x[k]);
     }
 }
 template <class W, int R>
@@ -76,7 +100,7 @@ __device__ __forceinline__ void load_contig(const W* __restrict__ src, W (&x)[R]
         const uint4* s4 = reinterpret_cast<const uint4*>(src);
 #pragma unroll
         for (int v = 0; v < R / PER; v++) {
-            uint4 q = s4[v];
+            uint4 q = ld_data(s4 + v);
             if constexpr (sizeof(W) == 4) {
                 x[4 * v] = q.x; x[4 * v + 1] = q.y; x[4 * v + 2] = q.z; x[4 * v + 3] = q.w;
             } else {
@@ -86,7 +110,7 @@ __device__ __forceinline__ void load_contig(const W* __restrict__ src, W (&x)[R]
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < R; k++) x[k] = src[k];
+        for (int k = 0; k < R; k++) x[k] = ld_data(src + k);
     }
 }
 
@@ -145,7 +169,7 @@ k_ntt_cta(const typename A::Tw* __restrict__ tw, const typename A::Tw* __restric
 #pragma unroll
         for (int np = 0; np < NP; np++)
 #pragma unroll
-            for (int k = 0; k < R; k++) x[np][k] = base[np][tid + k * T];
+            for (int k = 0; k < R; k++) x[np][k] = ld_data(base[np] + tid + k * T);
         E::template fwd<NP>(x, sm, tws, nu0, tid, m);
 #pragma unroll
         for (int np = 0; np < NP; np++) {
@@ -161,9 +185,98 @@ k_ntt_cta(const typename A::Tw* __restrict__ tw, const typename A::Tw* __restric
         for (int np = 0; np < NP; np++) {
             if (active[np]) {
 #pragma unroll
-                for (int k = 0; k < R; k++) base[np][tid + k * T] = A::canon_inv(x[np][k], m);
+                for (int k = 0; k < R; k++) st_data(base[np] + tid + k * T, A::canon_inv(x[np][k], m));
             }
         }
+    }
+}
+
+// ---- persistent, software-pipelined CTA kernel (whole transforms only) ------------------------------------
+// The one-shot kernel above gives every thread group a single polynomial: load, wait ~1 us for HBM, transform,
+// store, exit.  With CTAs this short-lived the 32-bit kernels spend their time in load latency and CTA
+// turnover, not in the integer pipes (ncu r01, prime32 N=1024 fwd: fmaheavy 53 %, long_scoreboard + drain among
+// the top stalls; the inverse, whose loads are 128-bit, ran 1.35x faster than the forward).  Here the grid is
+// sized to the resident CTAs of the device and every group walks the batch with stride gridDim.x * GP; the
+// loads of the group's NEXT polynomial are issued into a second register set before the current one is
+// transformed, so HBM latency is hidden behind a whole transform.
+#ifndef CNTT_PIPE32
+#define CNTT_PIPE32 1
+#endif
+#ifndef CNTT_PIPE64
+#define CNTT_PIPE64 0
+#endif
+template <class A, int LOGN, int LOGR, int GP, bool FWD, int NP>
+__global__ void __launch_bounds__(GP * Geo<LOGN, LOGR>::T)
+k_ntt_cta_pipe(const typename A::Tw* __restrict__ tw, const typename A::Tw* __restrict__ tw_last, const typename A::Mod m,
+               typename A::W* __restrict__ data, unsigned long long nvpoly, unsigned long long poly_stride,
+               const __grid_constant__ TwHead<typename A::Tw> head)
+{
+    typedef Engine<A, LOGN, LOGR> E;
+    typedef typename A::W W;
+    constexpr int T = E::T, R = E::R;
+    // does iteration i+1's first scatter need a barrier against iteration i's last gather?  (not when the two
+    // use different ping-pong buffers, i.e. exactly two exchanges on two buffers, or when every exchange of the
+    // run-time pass loop already ends with a barrier)
+    constexpr bool kTailSync = E::P >= 2 && !(E::NBUF == 2 && E::P == 3) && !(E::kLoopPasses && E::NBUF == 1 && E::P >= 3);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    W* sm_all = reinterpret_cast<W*>(smem_raw);
+    const int grp = (GP == 1) ? 0 : (int)(threadIdx.x / T);
+    const int tid = (GP == 1) ? (int)threadIdx.x : (int)(threadIdx.x % T);
+    W* sm = sm_all + (size_t)grp * NP * E::SMEM_WORDS * E::NBUF;
+    const typename E::TwSrc tws = {tw, tw_last, &head};
+    const unsigned long long ngroups = (unsigned long long)gridDim.x * GP;
+    const unsigned long long ngrp_total = (nvpoly + NP - 1) / NP;
+    const unsigned long long iters = (ngrp_total + ngroups - 1) / ngroups; // uniform across the CTA (barriers)
+    unsigned long long g = (unsigned long long)blockIdx.x * GP + grp;
+    const int off_in = FWD ? tid : E::elem_last(tid, 0);
+
+    auto fetch = [&](W (&dst)[NP][R], unsigned long long gi) {
+#pragma unroll
+        for (int np = 0; np < NP; np++) {
+            unsigned long long vp = gi * NP + np;
+            if (vp >= nvpoly) vp = nvpoly - 1; // keep the group in lock-step, result discarded
+            const W* src = data + vp * poly_stride + off_in;
+            if constexpr (FWD) {
+#pragma unroll
+                for (int k = 0; k < R; k++) dst[np][k] = ld_data(src + k * T);
+            } else {
+                load_contig<W, R>(src, dst[np]);
+            }
+        }
+    };
+
+    W nx[NP][R];
+    fetch(nx, g);
+#pragma unroll 1
+    for (unsigned long long it = 0; it < iters; ++it, g += ngroups) {
+        W x[NP][R];
+#pragma unroll
+        for (int np = 0; np < NP; np++)
+#pragma unroll
+            for (int k = 0; k < R; k++) x[np][k] = nx[np][k];
+        if (it + 1 < iters) fetch(nx, g + ngroups);
+        if constexpr (FWD) {
+            E::template fwd<NP>(x, sm, tws, 1u, tid, m);
+#pragma unroll
+            for (int np = 0; np < NP; np++) {
+#pragma unroll
+                for (int k = 0; k < R; k++) x[np][k] = A::canon_fwd(x[np][k], m);
+                const unsigned long long vp = g * NP + np;
+                if (vp < nvpoly) store_contig<W, R>(data + vp * poly_stride + E::elem_last(tid, 0), x[np]);
+            }
+        } else {
+            E::template inv<NP>(x, sm, tws, 1u, tid, m);
+#pragma unroll
+            for (int np = 0; np < NP; np++) {
+                const unsigned long long vp = g * NP + np;
+                if (vp < nvpoly) {
+                    W* dst = data + vp * poly_stride;
+#pragma unroll
+                    for (int k = 0; k < R; k++) st_data(dst + tid + k * T, A::canon_inv(x[np][k], m));
+                }
+            }
+        }
+        if constexpr (kTailSync) __syncthreads();
     }
 }
 
@@ -347,6 +460,31 @@ cudaError_t launch_cta_np(const PlanDev<A>& pl, typename A::W* data, unsigned lo
         kern<<<(unsigned)nblk, GP * T, smem, st>>>(FWD ? pl.tw_fwd : pl.tw_inv, last, pl.mod, data, nvpoly, log_sub, poly_stride, h);
         return cudaGetLastError();
     };
+    // measured on B200 (prime32, batch 65536): forward +6 % at N = 1024..4096; the inverse loses 14 % (its 128-bit
+    // loads were never latency-bound and the second register set costs occupancy), so only the forward pipelines
+    constexpr bool kPipe = FWD && (sizeof(typename A::W) == 4 ? CNTT_PIPE32 : CNTT_PIPE64) != 0;
+    if constexpr (kPipe) {
+        // persistent variant: needs whole transforms and at least two polynomials per resident group to pipeline
+        if (log_sub == 0 && head != nullptr) {
+            auto kern = k_ntt_cta_pipe<A, LOGN, LOGR, GP, FWD, NP>;
+            static int resident[64] = {0}; // CTAs the device holds at once, per device ordinal (0: not queried yet)
+            int dev = 0;
+            cudaError_t e = cudaGetDevice(&dev);
+            if (e != cudaSuccess) return e;
+            if (dev < 0 || dev >= 64) dev = 0;
+            if (resident[dev] == 0) {
+                if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+                int per_sm = 0, sms = 0;
+                if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GP * T, smem)) != cudaSuccess) return e;
+                if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+                resident[dev] = per_sm * sms > 0 ? per_sm * sms : 1;
+            }
+            if (nblk >= 2ull * (unsigned long long)resident[dev]) {
+                kern<<<(unsigned)resident[dev], GP * T, smem, st>>>(FWD ? pl.tw_fwd : pl.tw_inv, last, pl.mod, data, nvpoly, poly_stride, *head);
+                return cudaGetLastError();
+            }
+        }
+    }
     if (log_sub == 0 && head != nullptr) return launch(k_ntt_cta<A, LOGN, LOGR, GP, FWD, true, NP>, *head);
     static const TwHead<typename A::Tw> none = {};
     if constexpr (NP == 1) return launch(k_ntt_cta<A, LOGN, LOGR, GP, FWD, false, 1>, none);

@@ -3,7 +3,7 @@
 # usage: tools/gpu_stalls.sh NAME KERNEL_REGEX driver-args...
 mkdir -p gpurun_out
 name=$1; rx=$2; shift 2
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$rx" -s 2 -c 1 -f -o gpurun_out/st_$name python tools/prof_driver.py "$@" > gpurun_out/st_$name.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$rx" -s ${SKIP:-2} -c ${COUNT:-1} -f -o gpurun_out/st_$name python tools/prof_driver.py "$@" > gpurun_out/st_$name.log 2>&1
 echo "$name rc=$?"
 ncu -i gpurun_out/st_$name.ncu-rep --page raw --csv > gpurun_out/st_${name}_raw.csv 2>/dev/null
 python - "$name" <<'P'

@@ -21,9 +21,14 @@ for r in rows[2:]:
     d = dict(zip(hdr, r))
     print("==", d.get("Kernel Name", "")[:150])
     for k in hdr:
-        if k in KEYS or "warp_issue_stalled" in k and k.endswith("_per_warp_active.pct") or "pipe" in k and "pct_of_peak_sustained_active" in k and "inst_executed" in k:
+        if (k in KEYS or "warp_issue_stalled" in k and k.endswith("_per_warp_active.pct")
+                or "pipe" in k and "pct_of_peak_sustained_active" in k and "inst_executed" in k
+                or k.startswith("smsp__average_warps_issue_stalled") and k.endswith("_per_issue_active.ratio")
+                or k in ("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed",
+                         "sm__pipe_fmalite_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__issue_active.avg.pct_of_peak_sustained_elapsed")):
             v = d[k]
             try:
+                if abs(float(v.replace(",", ""))) < 0.02 and "stalled" in k: continue
                 if float(v.replace(",", "")) == 0: continue
             except Exception: pass
             print("  %-90s %s %s" % (k, v, units[hdr.index(k)]))

@@ -5,7 +5,7 @@
 mkdir -p gpurun_out
 run() { # name kernel-regex driver-args...
   local name=$1 rx=$2; shift 2
-  timeout 600 ncu --set full --clock-control none -k regex:"$rx" -s 1 -c 2 -f -o gpurun_out/prof_$name python tools/prof_driver.py "$@" > gpurun_out/ncu_$name.log 2>&1
+  timeout 600 ncu --set full --clock-control none -k regex:"$rx" -s ${SKIP:-1} -c ${COUNT:-2} -f -o gpurun_out/prof_$name python tools/prof_driver.py "$@" > gpurun_out/ncu_$name.log 2>&1
   echo "$name rc=$?"
   python tools/ncu_summary.py gpurun_out/prof_$name.ncu-rep > gpurun_out/ncu_sum_$name.txt 2>&1
   rm -f gpurun_out/prof_$name.ncu-rep gpurun_out/ncu_$name.log   # the 64 MiB return limit: only summaries travel back
@@ -23,5 +23,6 @@ run polymul64_2048  'k_polymul_fused'  polymul64 32768 2048
 run polymul32_2048  'k_polymul_fused'  polymul32 32768 2048
 run polymul128_4096 'k_polymul_fused'  polymul128 2048 4096
 run polymulb64_2048 'k_polymul_fused'  polymulb64 32768 2048
-run polymulb64_32768 'k_native|k_ntt|k_pointwise' polymulb64 256 32768
+SKIP=3 COUNT=3 run polymulb64_32768 'k_large' polymulb64 256 32768
+SKIP=3 COUNT=3 run polymulb64_65536 'k_large' polymulb64 128 65536
 ls -la gpurun_out/

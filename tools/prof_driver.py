@@ -48,7 +48,7 @@ elif which == "ntt32":
         plan.inv(d)
 elif which in ("polymul64", "polymulb64", "polymul32"):
     mod = {"polymul64": cntt.native64, "polymulb64": cntt.native_binary64, "polymul32": cntt.native32}[which]
-    plan = mod.Plan32.try_new(n)
+    plan = mod.Plan32.try_new(n) or mod.Plan32.try_new_extended(n)
     dt = torch.int32 if which == "polymul32" else torch.int64
     hi = 2**31 - 1 if which == "polymul32" else 2**63 - 1
     lhs = torch.randint(-hi - 1, hi, (batch, n), dtype=dt, device="cuda", generator=g)
