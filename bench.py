@@ -171,6 +171,14 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "source": "nvidia-smi"}
 
 
+def host_threads():
+    """every core this process may run on (torchrun exports OMP_NUM_THREADS=1, which is not the host's core count)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def make_inputs(rank, batch, n, p):
     g = np.random.Generator(np.random.PCG64(0xC0FFEE + 2 + 1000 * rank))
     a = g.integers(0, 2**64, size=(batch, n), dtype=np.uint64)
@@ -191,7 +199,7 @@ def run_reference(args):
         native = True
     except Exception:
         native = False
-    threads = O.lib(native).o_max_threads()
+    threads = host_threads()
     plan = O.Plan64.try_new(N_POLY, SOLINAS_P, native=native)
     sample = 4096
     buf = make_inputs(0, sample, N_POLY, SOLINAS_P)
@@ -227,7 +235,7 @@ def cpu_baseline_leg():
         native = True
     except Exception:
         native = False
-    threads = O.lib(native).o_max_threads()
+    threads = host_threads()
     plan = O.Plan64.try_new(N_POLY, SOLINAS_P, native=native)
     probe = make_inputs(7, 256, N_POLY, SOLINAS_P)
     t0 = time.perf_counter()

@@ -23,7 +23,14 @@ struct NativeConsts {
     uint64_t gm[11][2];     // gm[j] = P_0 ... P_{j-1} mod 2^128 as {lo, hi}; gm[0] = 1
     uint32_t half_single[10]; // floor(P[k] / 2): sign threshold when the top digit decides (np = 2, 3)
     uint32_t half_pair_lo[10], half_pair_hi[10]; // floor(P[k-1] P[k] / 2) = lo + hi * P[k-1] (np = 5, 10)
+    // Quotient-estimate CRT of the fused polymul kernels (native_device.cuh, reconstruct_bounded), per prime
+    // count class cls = 0..3 for np = 2, 3, 5, 10 with M = P_0 ... P_{np-1}:
+    uint64_t am[4][10][2];  // (M / P[k]) mod 2^128 as {lo, hi}
+    uint64_t aM[4][2];      // M mod 2^128
+    uint32_t acinv[4][10];  // ((M / P[k]) mod P[k])^-1 mod P[k]: folded into the lhs scale constants
+    float ainv[10];         // 1 / P[k]
 };
+inline int native_np_class(int np) { return np == 2 ? 0 : np == 3 ? 1 : np == 5 ? 2 : 3; }
 
 // Prime sets.  Set 0 = the reference's P0..P9.  Set 1 = the "extended" set: the nine primes k 2^17 + 1 in
 // (2^30 - 2^24, 2^30), ascending -- six of them are the reference's P0, P2, P3, P4, P8, P9 -- which admit
@@ -53,12 +60,12 @@ struct NativePlanDev {
     int nprimes;
     int prime_set;          // 0: reference primes, 1: extended set (N up to 65536)
     PlanDev<A32L4> sub[10]; // prime32 sub-plans on P0.. (all < 2^30)
-    uint2 lscale[10][4];    // 2^(32 j) * 2^32 / N mod P[k] (Shoup pairs): lhs scaling of the fused polymul
+    uint2 lscale[10][4];    // 2^(32 j) * (2^32 / N) * acinv[cls][k] mod P[k] (Shoup pairs): lhs scaling of the fused polymul
     const uint2* fused_fwd_last[10]; // last-pass twiddle layouts of the fused kernel's engine (Engine::TwSrc::last)
     const uint2* fused_inv_last[10];
 };
 
-void native_lhs_scale(int logn, uint2 (*out)[4], int set = 0);
+void native_lhs_scale(int logn, uint2 (*out)[4], int set, int np);
 
 // value (batch*n words) -> nprimes residue planes of batch*n u32, plane k at planes + k*plane_stride.
 // copy_low32: fwd_binary's `*value as u32` (no reduction).  Residues are written in the lazy range

@@ -119,5 +119,43 @@ __device__ __forceinline__ typename KindInfo<KIND>::Word reconstruct(const uint3
     }
 }
 
+// Reconstruction for the fused polymul kernels.  There the integer behind the residues is a negacyclic product
+// coefficient, |x| < n 2^(2w) (n 2^w for binary plans), at most 2^-5.9 of M = prod P_k for every plan the library
+// builds -- so the quotient of the classical CRT sum is known from a float estimate and no mixed-radix chain is
+// needed.  With y_k = x (M/P_k)^-1 mod P_k (the factor is folded into the lhs scale constants, so y_k is what
+// the inverse NTT already delivers):   x = sum_k y_k (M/P_k) - q M,   q = round(sum_k y_k / P_k),
+// because sum_k y_k / P_k = x / M + q exactly and |x / M| <= 2^-5.9 while the float sum is off by < 2^-19.
+// Only the low word of x is wanted, so the sum runs modulo 2^w.  The result is the centred lift wrapped to the
+// word -- the value the reference's reconstruct_* returns (src/native64.rs:90-141 etc.) whenever the bound holds,
+// i.e. for every negacyclic_polymul input.  (Plan32::inv on caller-supplied residues keeps the exact Garner
+// chain above: there the bound is the caller's business and the reference's sign rule must be reproduced.)
+template <int KIND>
+__device__ __forceinline__ typename KindInfo<KIND>::Word reconstruct_bounded(const uint32_t* y, const NativeConsts& c)
+{
+    typedef typename KindInfo<KIND>::Word Word;
+    constexpr int NP = KindInfo<KIND>::NP;
+    constexpr int CLS = NP == 2 ? 0 : NP == 3 ? 1 : NP == 5 ? 2 : 3;
+    float f = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NP; k++) f = fmaf(__uint2float_rn(y[k]), c.ainv[k], f);
+    const uint32_t q = (uint32_t)__float2int_rn(f);
+    if constexpr (sizeof(Word) == 4) {
+        uint32_t x = 0u - q * (uint32_t)c.aM[CLS][0];
+#pragma unroll
+        for (int k = 0; k < NP; k++) x += y[k] * (uint32_t)c.am[CLS][k][0];
+        return x;
+    } else if constexpr (sizeof(Word) == 8) {
+        uint64_t x = 0ull - (uint64_t)q * c.aM[CLS][0];
+#pragma unroll
+        for (int k = 0; k < NP; k++) x += (uint64_t)y[k] * c.am[CLS][k][0];
+        return x;
+    } else {
+        u128 x = (u128)0 - (u128)q * (((u128)c.aM[CLS][1] << 64) | c.aM[CLS][0]);
+#pragma unroll
+        for (int k = 0; k < NP; k++) x += (u128)y[k] * (((u128)c.am[CLS][k][1] << 64) | c.am[CLS][k][0]);
+        return x;
+    }
+}
+
 } // namespace dev
 } // namespace cntt

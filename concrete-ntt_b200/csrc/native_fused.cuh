@@ -14,15 +14,20 @@ namespace cntt {
 #ifndef CNTT_FUSED_LOGR
 #define CNTT_FUSED_LOGR 3
 #endif
-// experiment toggles (tools/build_variant.sh); the defaults are the shipped configuration
-#ifndef CNTT_FUSED_RELOAD
-#define CNTT_FUSED_RELOAD 0   // 1: re-read the operands from global memory (L2) for every prime instead of holding them in registers
+// Per-kind configuration (bit k = NativeKind k; tools/build_variant.sh overrides these for A/B runs):
+//   RELOAD: the operands are re-read from global memory (L2 hits after the first prime) for every prime instead of
+//           living in registers across the prime loop (128-bit words: 64 registers per thread)
+//   ACC:    the reconstruction sum of reconstruct_bounded is accumulated per prime in registers (word + float per
+//           coefficient) instead of parking np residue polynomials in shared memory -- for the 128-bit kinds that
+//           is 160 KB at N = 4096, which pinned the kernel at one CTA per SM
+#ifndef CNTT_FUSED_RELOAD_MASK
+#define CNTT_FUSED_RELOAD_MASK 0x24
 #endif
-#ifndef CNTT_FUSED_KEEPLAST
-#define CNTT_FUSED_KEEPLAST 0 // 1: the last prime's residues go straight from registers into the Garner lift (no stash plane)
+#ifndef CNTT_FUSED_ACC_MASK
+#define CNTT_FUSED_ACC_MASK 0x24
 #endif
-#ifndef CNTT_FUSED_MINBLK
-#define CNTT_FUSED_MINBLK 1   // __launch_bounds__ minimum resident CTAs per SM
+#ifndef CNTT_FUSED_MINTHREADS
+#define CNTT_FUSED_MINTHREADS 768 // resident threads per SM the kernel is compiled for (register cap 65536 / this)
 #endif
 constexpr int kFusedMinLogN = 5, kFusedMaxLogN = 12;
 
@@ -42,8 +47,16 @@ struct FusedCfg {
     static constexpr int T = E::T;
     static constexpr int GP = T >= 128 ? 1 : 128 / T;
     static constexpr int XCHG_WORDS = 2 * E::NBUF * E::SMEM_WORDS;   // two polynomials in flight (lhs, rhs)
-    static constexpr int STASH_WORDS = (NP - (CNTT_FUSED_KEEPLAST ? 1 : 0)) * E::N;
+    // measured on B200 (native128): N = 2048 4.74 -> 4.99 M polymul/s with RELOAD + ACC, N = 4096 2.46 -> 2.25 (512
+    // threads per CTA leave 128 registers per thread either way, and the accumulators spill), so N <= 2048 only;
+    // the 32/64-bit kinds lose 4 % with ACC (registers) and are left on the shared-memory stash
+    static constexpr bool RELOAD = ((CNTT_FUSED_RELOAD_MASK >> KIND) & 1) != 0 && LOGN <= 11;
+    static constexpr bool ACC = ((CNTT_FUSED_ACC_MASK >> KIND) & 1) != 0 && LOGN <= 11;
+    static constexpr int STASH_WORDS = ACC ? 0 : NP * E::N;
     static constexpr size_t SMEM_BYTES = (size_t)GP * (XCHG_WORDS + STASH_WORDS) * sizeof(uint32_t);
+    static constexpr int BLK_BY_THREADS = CNTT_FUSED_MINTHREADS > GP * T ? CNTT_FUSED_MINTHREADS / (GP * T) : 1;
+    static constexpr int BLK_BY_SMEM = (int)((size_t)227 * 1024 / (SMEM_BYTES + 1024)) > 0 ? (int)((size_t)227 * 1024 / (SMEM_BYTES + 1024)) : 1;
+    static constexpr int MINBLK = BLK_BY_THREADS < BLK_BY_SMEM ? BLK_BY_THREADS : BLK_BY_SMEM; // no point capping registers below what shared memory admits
 };
 
 // Per prime p_k (all arithmetic 32-bit, lazy ranges of policy A32L4):
@@ -53,7 +66,7 @@ struct FusedCfg {
 //   pointwise Montgomery product  A B 2^-32 = a b / N   in (0,2p)    (replaces mul_assign_normalize)
 //   inverse NTT, canonical residue parked in shared memory
 template <int KIND, int LOGN, int LOGR>
-__global__ void __launch_bounds__(FusedCfg<KIND, LOGN, LOGR>::GP * FusedCfg<KIND, LOGN, LOGR>::T, CNTT_FUSED_MINBLK)
+__global__ void __launch_bounds__(FusedCfg<KIND, LOGN, LOGR>::GP * FusedCfg<KIND, LOGN, LOGR>::T, FusedCfg<KIND, LOGN, LOGR>::MINBLK)
 k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ prod, const void* __restrict__ lhs,
                 const void* __restrict__ rhs, unsigned long long batch)
 {
@@ -76,11 +89,13 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
     uint32_t* stash = sm + Cfg::XCHG_WORDS;
     const size_t base = (size_t)b * N;
 
-    // operands: read once, kept in registers for all primes
-    constexpr int RK = CNTT_FUSED_RELOAD ? 1 : R;
+    // operands: read once and kept in registers for all primes, or (RELOAD) re-read per prime
+    constexpr bool RELOAD = Cfg::RELOAD, ACC = Cfg::ACC;
+    constexpr int CLS = NP == 2 ? 0 : NP == 3 ? 1 : NP == 5 ? 2 : 3;
+    constexpr int RK = RELOAD ? 1 : R;
     uint64_t llo[RK], rlo[RK];
-    uint64_t lhi[(WB == 16 && !CNTT_FUSED_RELOAD) ? R : 1], rhi[(WB == 16 && !CNTT_FUSED_RELOAD) ? R : 1];
-    if constexpr (!CNTT_FUSED_RELOAD) {
+    uint64_t lhi[(WB == 16 && !RELOAD) ? R : 1], rhi[(WB == 16 && !RELOAD) ? R : 1];
+    if constexpr (!RELOAD) {
 #pragma unroll
         for (int k = 0; k < R; k++) {
             uint64_t h0, h1;
@@ -89,24 +104,26 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
             if constexpr (WB == 16) { lhi[k] = h0; rhi[k] = h1; }
         }
     }
-    uint32_t keep[CNTT_FUSED_KEEPLAST ? R : 1];
+    Word acc[ACC ? R : 1];
+    float accf[ACC ? R : 1];
+    if constexpr (ACC) {
+#pragma unroll
+        for (int k = 0; k < R; k++) { acc[k] = 0; accf[k] = 0.0f; }
+    }
 
 #pragma unroll 1
     for (int pk = 0; pk < NP; pk++) {
         const Mod32 m = fp.mod[pk];
         const uint32_t p = m.p;
         uint32_t x[2][R];
-        if constexpr (CNTT_FUSED_RELOAD) {
-            uint64_t alo[R], ahi[R], blo[R], bhi[R];
+        if constexpr (RELOAD) {
 #pragma unroll
             for (int k = 0; k < R; k++) {
-                dev::load_word<KIND>(lhs, base + tid + k * T, alo[k], ahi[k]);
-                dev::load_word<KIND>(rhs, base + tid + k * T, blo[k], bhi[k]);
-            }
-#pragma unroll
-            for (int k = 0; k < R; k++) {
-                x[0][k] = dev::residue<LIMBS, true>(alo[k], ahi[k], fp.lscale[pk], p);
-                x[1][k] = BINARY ? (uint32_t)blo[k] : dev::residue<LIMBS, false>(blo[k], bhi[k], c.red[pk], p);
+                uint64_t alo, ahi, blo, bhi;
+                dev::load_word<KIND>(lhs, base + tid + k * T, alo, ahi);
+                dev::load_word<KIND>(rhs, base + tid + k * T, blo, bhi);
+                x[0][k] = dev::residue<LIMBS, true>(alo, ahi, fp.lscale[pk], p);
+                x[1][k] = BINARY ? (uint32_t)blo : dev::residue<LIMBS, false>(blo, bhi, c.red[pk], p);
             }
         } else {
 #pragma unroll
@@ -122,9 +139,18 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
         for (int k = 0; k < R; k++) y[0][k] = dev::mont(dev::red2p(x[0][k], p), dev::red2p(x[1][k], p), p, pinv);
         if constexpr (E::NBUF == 1 && E::P >= 2) __syncthreads(); // single exchange buffer: fwd gather vs inv scatter
         E::template inv<1>(y, sm, typename E::TwSrc{fp.tw_inv[pk], fp.tw_inv_last[pk]}, 1u, tid, m);
-        if (CNTT_FUSED_KEEPLAST && pk == NP - 1) {
+        if constexpr (ACC) {
+            // reconstruct_bounded, one prime at a time: acc += y (M/P_k) mod 2^w,  accf += y / P_k
+            const float ip = c.ainv[pk];
+            Word mk;
+            if constexpr (WB == 16) mk = ((dev::u128)c.am[CLS][pk][1] << 64) | c.am[CLS][pk][0];
+            else mk = (Word)c.am[CLS][pk][0];
 #pragma unroll
-            for (int k = 0; k < R; k++) keep[CNTT_FUSED_KEEPLAST ? k : 0] = A32L4::canon_inv(y[0][k], m);
+            for (int k = 0; k < R; k++) {
+                const uint32_t yk = A32L4::canon_inv(y[0][k], m);
+                acc[k] += (Word)yk * mk;
+                accf[k] = fmaf(__uint2float_rn(yk), ip, accf[k]);
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < R; k++) stash[pk * N + tid + k * T] = A32L4::canon_inv(y[0][k], m);
@@ -133,13 +159,23 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
     }
 
     if (active) {
+        if constexpr (ACC) {
+            Word bigm;
+            if constexpr (WB == 16) bigm = ((dev::u128)c.aM[CLS][1] << 64) | c.aM[CLS][0];
+            else bigm = (Word)c.aM[CLS][0];
 #pragma unroll
-        for (int k = 0; k < R; k++) {
-            uint32_t r[NP];
+            for (int k = 0; k < R; k++) {
+                const uint32_t q = (uint32_t)__float2int_rn(accf[k]);
+                dev::store_word<KIND>(prod, base + tid + k * T, (Word)(acc[k] - (Word)q * bigm));
+            }
+        } else {
 #pragma unroll
-            for (int pk = 0; pk < NP; pk++)
-                r[pk] = (CNTT_FUSED_KEEPLAST && pk == NP - 1) ? keep[CNTT_FUSED_KEEPLAST ? k : 0] : stash[pk * N + tid + k * T];
-            dev::store_word<KIND>(prod, base + tid + k * T, dev::reconstruct<KIND>(r, c));
+            for (int k = 0; k < R; k++) {
+                uint32_t r[NP];
+#pragma unroll
+                for (int pk = 0; pk < NP; pk++) r[pk] = stash[pk * N + tid + k * T];
+                dev::store_word<KIND>(prod, base + tid + k * T, dev::reconstruct_bounded<KIND>(r, c));
+            }
         }
     }
 }

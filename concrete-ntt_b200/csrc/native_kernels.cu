@@ -46,6 +46,28 @@ static void fill_consts_set(int set)
             c.half_pair_lo[k] = c.half_pair_hi[k] = 0;
         }
     }
+    static const int kNp[4] = {2, 3, 5, 10};
+    for (int cls = 0; cls < 4; cls++) {
+        const int np = kNp[cls];
+        u128 M = 1; // wrapping mod 2^128 is all the kernels need
+        for (int j = 0; j < np; j++) M *= (u128)P[j];
+        c.aM[cls][0] = (uint64_t)M; c.aM[cls][1] = (uint64_t)(M >> 64);
+        for (int k = 0; k < 10; k++) {
+            c.am[cls][k][0] = c.am[cls][k][1] = 0; c.acinv[cls][k] = 0;
+            if (k >= np) continue;
+            u128 mk = 1;        // M / P[k] mod 2^128
+            uint64_t mk_modp = 1; // M / P[k] mod P[k]
+            Fp f(P[k]);
+            for (int j = 0; j < np; j++) {
+                if (j == k) continue;
+                mk *= (u128)P[j];
+                mk_modp = f.mul(mk_modp, P[j] % P[k]);
+            }
+            c.am[cls][k][0] = (uint64_t)mk; c.am[cls][k][1] = (uint64_t)(mk >> 64);
+            c.acinv[cls][k] = (uint32_t)f.inv(mk_modp);
+        }
+    }
+    for (int k = 0; k < 10; k++) c.ainv[k] = 1.0f / (float)P[k];
     u128 m = 1;
     for (int j = 0; j <= 10; j++) {
         c.gm[j][0] = (uint64_t)m;
@@ -60,14 +82,16 @@ const NativeConsts& native_consts(int set)
     return g_consts[(set >= 0 && set < kNativePrimeSets) ? set : 0];
 }
 
-// lhs scale constants of the fused polymul: 2^(32 j) * 2^32 * N^-1 mod P[k] (Shoup pairs)
-void native_lhs_scale(int logn, uint2 (*out)[4], int set)
+// lhs scale constants of the fused polymul: 2^(32 j) * 2^32 * N^-1 * acinv[cls][k] mod P[k] (Shoup pairs)
+void native_lhs_scale(int logn, uint2 (*out)[4], int set, int np)
 {
     const NativeConsts& c = native_consts(set);
+    const int cls = native_np_class(np);
     for (int k = 0; k < 10; k++) {
         host::Fp f(c.P[k]);
         const uint64_t ninv = f.inv(((uint64_t)1 << logn) % c.P[k]);
         uint64_t w = f.mul(((uint64_t)1 << 32) % c.P[k], ninv);
+        if (k < np) w = f.mul(w, c.acinv[cls][k]); // residues leave the inverse NTT pre-multiplied for reconstruct_bounded
         for (int j = 0; j < 4; j++) {
             out[k][j] = make_uint2((uint32_t)w, (uint32_t)((w << 32) / c.P[k]));
             w = f.mul(w, ((uint64_t)1 << 32) % c.P[k]);

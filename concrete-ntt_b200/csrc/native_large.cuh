@@ -143,7 +143,7 @@ k_large_lead_inv(const NativeConsts c, const LargeParams lp, void* __restrict__ 
         uint32_t rr[NP];
 #pragma unroll
         for (int pk = 0; pk < NP; pk++) rr[pk] = res[pk][r];
-        dev::store_word<KIND>(prod, base + ((size_t)r << kLargeRowLog), dev::reconstruct<KIND>(rr, c));
+        dev::store_word<KIND>(prod, base + ((size_t)r << kLargeRowLog), dev::reconstruct_bounded<KIND>(rr, c));
     }
 }
 

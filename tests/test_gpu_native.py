@@ -269,3 +269,40 @@ def test_split_phase_key_switch_shape(cntt, oracle, torch_cuda):
 def test_plan52_is_none_like_a_non_ifma_host(cntt):
     for mod in (cntt.native32, cntt.native64, cntt.native_binary32, cntt.native_binary64):
         assert mod.Plan52.try_new(1024) is None      # src/native64.rs:1075-1079 without AVX-512 IFMA
+
+
+@pytest.mark.parametrize("n", [2048, 4096, 32768])
+def test_polymul_extreme_magnitudes(cntt, oracle, torch_cuda, n):
+    """Largest |coefficient| the plans can meet (all words 2^w - 1: coefficient n-1 = +n max^2, coefficient 0 =
+    -(n-2) max^2): the reconstruction's quotient estimate (native_device.cuh, reconstruct_bounded) must still land
+    on the centred lift.  Checked against the oracle's exact Garner path."""
+    for bits, binary in [(32, False), (64, False), (128, False), (32, True), (64, True), (128, True)]:
+        if n > 16384 and bits == 128 and not binary:
+            continue
+        gp, op = plan_pair(cntt, oracle, n, bits, binary)
+        wdt = np.uint32 if bits == 32 else np.uint64
+        shape = (2, n) if bits != 128 else (2, n, 2)
+        lhs = np.full(shape, np.iinfo(wdt).max, wdt)
+        rhs = np.full(shape, np.iinfo(wdt).max, wdt)
+        lhs[1, ::2] = 0                 # second polynomial: mixed signs / half the terms
+        if binary:
+            rhs = np.ones(shape, wdt)
+            if bits == 128:
+                rhs[..., 1] = 0
+        dl, dr = dev(torch_cuda, lhs), dev(torch_cuda, rhs)
+        dp = torch_cuda.empty_like(dl)
+        gp.negacyclic_polymul(dp, dl, dr)
+        assert (host(dp, wdt) == op.negacyclic_polymul(lhs, rhs)).all(), (bits, binary)
+
+
+def test_extended_n65536_extreme_magnitudes(cntt, oracle, torch_cuda):
+    n = 65536
+    for bits, binary in [(64, False), (64, True), (32, False)]:
+        gp = ext_plan(cntt, n, bits, binary)
+        wdt = np.uint32 if bits == 32 else np.uint64
+        lhs = np.full((1, n), np.iinfo(wdt).max, wdt)
+        rhs = np.ones((1, n), wdt) if binary else np.full((1, n), np.iinfo(wdt).max, wdt)
+        dl, dr = dev(torch_cuda, lhs), dev(torch_cuda, rhs)
+        dp = torch_cuda.empty_like(dl)
+        gp.negacyclic_polymul(dp, dl, dr)
+        assert (host(dp, wdt)[0] == oracle.negacyclic_wrapping(bits, lhs[0], rhs[0])).all(), (bits, binary)
