@@ -123,9 +123,11 @@ __device__ __forceinline__ void load_contig(const W* __restrict__ src, W (&x)[R]
 // carries NP polynomials loads each twiddle once for NP butterflies: the last pass reads R-1 table entries
 // per thread (2x the bytes of the data itself for u32 Shoup pairs), and L1TEX wavefronts -- 73 % of them
 // global loads, mostly twiddles -- were the limiter of the u32 kernels at NP = 1 (ncu r01).
-// experiment toggle: resident threads per SM the 64-bit kernels are compiled for (0: no register cap)
+// resident threads per SM the 64-bit kernels are compiled for (register cap 65536 / this; 0: none).  B200, r01:
+// 768 (<= 85 registers) vs uncapped: Solinas N=4096 inverse 1.52 -> 1.27 ms per 32768, N=2048 +1 %, Shoup-64 +3 %;
+// 896 and 1024 lose on the N=2048 inverse.
 #ifndef CNTT_CTA_MINTHREADS64
-#define CNTT_CTA_MINTHREADS64 0
+#define CNTT_CTA_MINTHREADS64 768
 #endif
 template <class A, int LOGN, int LOGR, int GP>
 constexpr int cta_min_blocks()

@@ -198,3 +198,24 @@ def test_full_size_properties(cntt, torch_cuda):
     # awkward in numpy; instead undo the scaling on the GPU and compare bytes.
     plan.normalize(d)
     assert (host(d, np.uint64) == a).all()
+
+
+@pytest.mark.parametrize("n,batch", [(256, 40003), (1024, 20001), (2048, 9999), (4096, 5003)])
+def test_prime32_persistent_forward_kernel(cntt, oracle, torch_cuda, n, batch):
+    """Large ragged batches take the persistent software-pipelined forward kernel (k_ntt_cta_pipe: grid = resident
+    CTAs, every group strides over the batch, tail groups clamp): oracle on sampled polynomials incl. the first and
+    the last, canonical range everywhere, and inv + normalize brings the whole batch back."""
+    torch = torch_cuda
+    p = 1062862849
+    g = rng(n + batch)
+    a = rand_mod(g, p, (batch, n), np.uint32)
+    gp, op = cntt.prime32.Plan.try_new(n, p), oracle.Plan32.try_new(n, p)
+    d = dev(torch, a)
+    gp.fwd(d)
+    f = host(d, np.uint32)
+    assert (f < np.uint32(p)).all()
+    for r in [0, 1, batch - 2, batch - 1] + [int(x) for x in g.integers(0, batch, 12)]:
+        assert (f[r] == op.fwd(a[r].copy())).all(), r
+    gp.inv(d)
+    gp.normalize(d)
+    assert (host(d, np.uint32) == a).all()
