@@ -57,6 +57,26 @@ def ncu_traffic(direction):
         return None
 
 
+def ncu_pipes(direction):
+    """integer-pipe utilisation of the same kernel from the committed ncu summary (percent of peak, per launch)"""
+    try:
+        want = "1" if direction == "fwd" else "0"
+        cur, out = None, {}
+        keys = {"sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed": "fmaheavy_pct",
+                "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed": "alu_pct",
+                "sm__issue_active.avg.pct_of_peak_sustained_elapsed": "issue_pct"}
+        for line in open(NCU_SUMMARY):
+            if line.startswith("=="):
+                cur = line.split("<", 1)[1].split(">", 1)[0].split(",")[4].strip()
+            elif cur == want:
+                f = line.split()
+                if f and f[0] in keys:
+                    out[keys[f[0]]] = float(f[1])
+        return out or None
+    except Exception:
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -422,7 +442,9 @@ def run_ours(args):
                          "traffic": ncu_traffic(which), "traffic_source": "profiles/r01_kernels_v4/ncu_ntt64s_2048.txt (ncu --set full, dram read+write bytes per launch)", "kernel": "k_ntt_cta<A64S,11,4> (%s)" % which,
                          "peak_source": peak_src, "ms_per_launch": {"fwd": fwd_ms, "inv": inv_ms},
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_NTT * BATCH,
-                         "note": "integer-issue bound kernel; see DESIGN.md for the integer roofline"},
+                         "int_pipes": ncu_pipes(which),
+                         "note": "integer-pipe bound kernel (multiply pipe and ALU ~65-75 % busy at once, ncu); the integer "
+                                 "ceiling of this butterfly is 80 M NTT/s = 40 % of the HBM ceiling, see DESIGN.md section 4"},
             "extra": extra,
         }
         if world == 1:

@@ -883,6 +883,7 @@ CNTT_API int cntt_native_polymul_host(const cntt_native_plan* pl, void* h_prod, 
 
 // ---- product::Plan (src/product.rs) --------------------------------------------------------------------------
 #include "product_kernels.cuh"
+#include "product_fused.hpp"
 
 struct cntt_product_plan {
     size_t n;
@@ -1025,6 +1026,26 @@ static cudaError_t product_pointwise(const cntt_product_plan* pl, int op, uint64
     return cudaSuccess;
 }
 
+// the hot shape -- two u32 primes of one arithmetic class, N <= 4096 -- runs one fused kernel per call (product_fused.hpp)
+static bool product_fused_args(const cntt_product_plan* pl, ProductFusedArgs* a)
+{
+    const ProductConsts& c = pl->c;
+    if (c.count32 != 2 || c.count64 != 0) return false;
+    const cntt_prime32_plan *q0 = pl->p32[0], *q1 = pl->p32[1];
+    if (!q0 || !q1 || q0->cls != q1->cls || (q0->cls != C32_L4 && q0->cls != C32_L2)) return false;
+    if (!product_fused_supported(q0->cls == C32_L4 ? 0 : 1, q0->logn)) return false;
+    a->cls = q0->cls == C32_L4 ? 0 : 1;
+    a->logn = q0->logn;
+    const cntt_prime32_plan* q[2] = {q0, q1};
+    for (int j = 0; j < 2; j++) {
+        a->tw_fwd[j] = q[j]->d_fwd; a->tw_inv[j] = q[j]->d_inv;
+        a->last_fwd[j] = q[j]->d_fwd_last; a->last_inv[j] = q[j]->d_inv_last;
+        a->mod[j] = q[j]->mod;
+        a->head_fwd[j] = &q[j]->head_fwd; a->head_inv[j] = &q[j]->head_inv;
+    }
+    return true;
+}
+
 // fwd (product.rs:272-353): d_ntt[batch * domain_len] <- d_standard[batch * n]; mode 0 = FwdMode::Generic,
 // 1 = FwdMode::Bounded(bound)
 CNTT_API int cntt_product_fwd(const cntt_product_plan* pl, uint64_t* d_ntt, const uint64_t* d_standard, int mode, uint64_t bound, size_t batch, void* stream)
@@ -1034,6 +1055,11 @@ CNTT_API int cntt_product_fwd(const cntt_product_plan* pl, uint64_t* d_ntt, cons
     if (batch == 0 || pl->c.count32 + pl->c.count64 == 0) return CNTT_OK;
     GUARD(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
+    ProductFusedArgs fa;
+    if (product_fused_args(pl, &fa)) {
+        CU(product_fused_fwd(pl->c, fa, d_ntt, d_standard, mode, bound, batch, st));
+        return CNTT_OK;
+    }
     const unsigned long long ncoef = (unsigned long long)batch * pl->n;
     k_product_reduce<<<(unsigned)((ncoef + 255) / 256), 256, 0, st>>>(pl->c, d_ntt, d_standard, mode, bound, ncoef);
     CU(cudaGetLastError());
@@ -1049,6 +1075,11 @@ CNTT_API int cntt_product_inv(const cntt_product_plan* pl, uint64_t* d_standard,
     if (batch == 0) return CNTT_OK;
     GUARD(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
+    ProductFusedArgs fa;
+    if (product_fused_args(pl, &fa)) {
+        CU(product_fused_inv(pl->c, fa, d_standard, d_ntt, mode, batch, st));
+        return CNTT_OK;
+    }
     CU(product_planes_ntt(pl, d_ntt, batch, false, st));
     const unsigned long long ncoef = (unsigned long long)batch * pl->n;
     k_product_crt<<<(unsigned)((ncoef + 255) / 256), 256, 0, st>>>(pl->c, d_standard, d_ntt, mode, ncoef);

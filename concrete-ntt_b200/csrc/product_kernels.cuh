@@ -55,6 +55,7 @@ __device__ __forceinline__ uint64_t mul_mod(uint64_t a, uint64_t b, uint64_t p, 
 }
 } // namespace pdev
 
+#ifndef CNTT_PRODUCT_HELPERS_ONLY // product_fused.cu needs the constants and helpers, not a second copy of the kernels
 // one thread per coefficient (b, i)
 __global__ void __launch_bounds__(256)
 k_product_reduce(const ProductConsts c, uint64_t* __restrict__ ntt, const uint64_t* __restrict__ standard, int mode, uint64_t bound,
@@ -119,5 +120,6 @@ k_product_crt(const ProductConsts c, uint64_t* __restrict__ standard, const uint
         if (j < np) acc = acc * c.p[j] + v[j];
     standard[idx] = mode == PI_REPLACE ? acc : pdev::add_mod(c.modulus, standard[idx], acc);
 }
+#endif // CNTT_PRODUCT_HELPERS_ONLY
 
 } // namespace cntt

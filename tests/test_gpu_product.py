@@ -179,3 +179,51 @@ def test_product_host_slices(cntt, oracle):
         r = np.zeros(dl, np.uint64)
         op.fwd(r, A[i], op.GENERIC)
         assert (G[i] == r).all()
+
+
+@pytest.mark.parametrize("n", [256, 512, 1024, 4096])
+@pytest.mark.parametrize("hi", [1 << 30, 1 << 31])
+def test_product_fused_two_u32_primes(cntt, oracle, torch_cuda, n, hi):
+    """The fused kernels of the hot shape (two u32 primes of one class, product_fused.hpp), both classes (< 2^30,
+    < 2^31), every fused size, ragged batch: fwd Generic and Bounded, inv Replace (incl. the clobbered ntt) and
+    Accumulate, against the oracle."""
+    torch = torch_cuda
+    f = oracle.largest_prime_in_arithmetic_progression64
+    p0 = f(2 * n, 1, 0, hi)
+    p1 = f(2 * n, 1, 0, p0 - 1)
+    p = p0 * p1
+    op, gp = oracle.Product.try_new(n, p, [p0, p1]), cntt.product.Plan.try_new(n, p, [p0, p1])
+    dl, batch = op.ntt_domain_len(), 11
+    g = rng(n + hi % 1000)
+    std = rand_mod(g, p, (batch, n), np.uint64)
+    std[0, :4] = [0, 1, p - 1, p // 2]
+    ref = np.zeros((batch, dl), dtype=np.uint64)
+    for b in range(batch):
+        op.fwd(ref[b], std[b], op.GENERIC)
+    d = torch.zeros((batch, dl), dtype=torch.int64, device="cuda")
+    gp.fwd(d, dev(torch, std))
+    assert (host(d) == ref).all()
+    small = g.integers(-(1 << 20) + 1, 1 << 20, size=(batch, n))
+    sstd = np.array([[int(x) % p for x in row] for row in small], dtype=np.uint64)
+    refb = np.zeros((batch, dl), dtype=np.uint64)
+    for b in range(batch):
+        op.fwd(refb[b], sstd[b], op.bounded(1 << 20))
+    db = torch.zeros_like(d)
+    gp.fwd(db, dev(torch, sstd), cntt.product.FwdMode.Bounded(1 << 20))
+    assert (host(db) == refb).all()
+    out_ref = np.zeros((batch, n), dtype=np.uint64)
+    keep = ref.copy()
+    for b in range(batch):
+        op.inv(out_ref[b], ref[b], op.REPLACE)
+    dkeep = d.clone()
+    out = torch.zeros((batch, n), dtype=torch.int64, device="cuda")
+    gp.inv(out, d, cntt.product.InvMode.Replace)
+    assert (host(out) == out_ref).all()
+    assert (host(d) == ref).all()                      # inverse transforms left in ntt, like the reference
+    acc0 = rand_mod(g, p, (batch, n), np.uint64)
+    acc_ref = acc0.copy()
+    for b in range(batch):
+        op.inv(acc_ref[b], keep[b], op.ACCUMULATE)
+    dacc = dev(torch, acc0)
+    gp.inv(dacc, dkeep, cntt.product.InvMode.Accumulate)
+    assert (host(dacc) == acc_ref).all()

@@ -16,6 +16,19 @@ g = torch.Generator(device="cuda").manual_seed(1)
 cases = sys.argv[1:] or ["native64:2048:65536"]
 for c in cases:
     kind, n, batch = c.split(":"); n = int(n); batch = int(batch)
+    if kind == "product":   # product::Plan, modulus = two primes just below 2^31 (the tfhe-rs NTT-PBS shape)
+        f = cntt.prime.largest_prime_in_arithmetic_progression64
+        p1 = f(1 << 17, 1, 1 << 30, 1 << 31); p2 = f(1 << 17, 1, 1 << 30, p1 - 1)
+        plan = cntt.product.Plan.try_new(n, p1 * p2, [p1, p2])
+        std = torch.randint(0, p1 * p2, (batch, n), dtype=torch.int64, device="cuda", generator=g)
+        a = torch.empty((batch, plan.ntt_domain_len()), dtype=torch.int64, device="cuda"); b = torch.empty_like(a); acc = torch.zeros_like(a)
+        plan.fwd(b, std)
+        tf = bench(lambda: plan.fwd(a, std)); tm = bench(lambda: plan.mul_accumulate(acc, a, b))
+        ti = bench(lambda: plan.inv(std, a))
+        gb = lambda t, words: words * 8 * batch / t / 1e6
+        print("product(2 x 31-bit primes) n=%d batch=%d: fwd %.3f ms (%.1f M/s)  mul_accumulate %.3f ms (%.0f GB/s)  inv %.3f ms (%.1f M/s)"
+              % (n, batch, tf, batch / tf / 1e3, tm, gb(tm, 4 * plan.ntt_domain_len()), ti, batch / ti / 1e3))
+        continue
     if kind.startswith("native") or kind.startswith("binary"):
         bits = int(kind.replace("native", "").replace("binary", ""))
         mod = getattr(cntt, ("native_binary%d" if kind.startswith("binary") else "native%d") % bits)
