@@ -941,11 +941,20 @@ CNTT_API int cntt_product_plan_new(size_t n, uint64_t modulus, const uint64_t* f
         const int j = c.count32 + c.count64;
         c.p[j] = f;
         c.recip[j] = ~0ull / f;
+        for (int l = 0; l < 2; l++) {
+            const uint64_t cst = l == 0 ? 1 % f : (((uint64_t)1 << 32) % f);
+            c.red32[j][l][0] = f < ((uint64_t)1 << 32) ? (uint32_t)cst : 0;
+            c.red32[j][l][1] = f < ((uint64_t)1 << 32) ? (uint32_t)((cst << 32) / f) : 0;
+        }
         host::Fp fp(f);
         for (int i = 0; i < j; i++) c.inv[j][i] = fp.inv(c.p[i] % f);
         if (f < (1ull << 32)) c.count32++; else c.count64++;
     }
     c.domain_len = (n / 2) * c.count32 + n * c.count64;
+    if (c.count32 == 2 && c.p[1] < (1ull << 31)) {
+        c.inv10_32[0] = (uint32_t)c.inv[1][0];
+        c.inv10_32[1] = (uint32_t)((c.inv[1][0] << 32) / c.p[1]);
+    }
     *out = pl;
     return CNTT_OK;
 }

@@ -47,7 +47,7 @@ k_product_fwd_fused(const ProductConsts c, const __grid_constant__ ProductFusedD
     const uint64_t half = c.modulus / 2;
 #pragma unroll
     for (int j = 0; j < 2; j++) {
-        const uint64_t pj = c.p[j], rj = c.recip[j];
+        const uint64_t pj = c.p[j];
         uint32_t x[1][R];
 #pragma unroll
         for (int k = 0; k < R; k++) {
@@ -55,7 +55,15 @@ k_product_fwd_fused(const ProductConsts c, const __grid_constant__ ProductFusedD
                 const uint32_t s32 = (uint32_t)s[k];
                 x[0][k] = s[k] < half ? s32 : (uint32_t)pj - ((uint32_t)c.modulus - s32);
             } else {
-                x[0][k] = (uint32_t)pdev::rem64(s[k], pj, rj);
+                // s mod p_j, limb by limb: Shoup products in [0, 2p) brought to [0, p) each, sum in [0, 2p) -- inside the
+                // forward transform's input range for both classes; the output is canonicalised after the transform
+                const uint32_t p32 = (uint32_t)pj;
+                const uint32_t lo = (uint32_t)s[k], hi = (uint32_t)(s[k] >> 32);
+                uint32_t a = lo * c.red32[j][0][0] - __umulhi(lo, c.red32[j][0][1]) * p32;
+                uint32_t h = hi * c.red32[j][1][0] - __umulhi(hi, c.red32[j][1][1]) * p32;
+                a = umin32(a, a - p32);
+                h = umin32(h, h - p32);
+                x[0][k] = a + h;
             }
         }
         E::template fwd<1>(x, sm, typename E::TwSrc{fp.tw[j], fp.last[j], &fp.head[j]}, 1u, tid, fp.mod[j]);
@@ -101,13 +109,17 @@ k_product_inv_fused(const ProductConsts c, const __grid_constant__ ProductFusedD
         if (j == 0 && E::P >= 2) __syncthreads();
     }
     if (!active) return;
-    const uint64_t p0 = c.p[0], p1 = c.p[1], inv10 = c.inv[1][0], rc1 = c.recip[1];
+    const uint32_t p0 = (uint32_t)c.p[0], p1 = (uint32_t)c.p[1], i0 = c.inv10_32[0], i1 = c.inv10_32[1];
 #pragma unroll
     for (int k = 0; k < R; k++) {
-        // Knuth 4.3.2 mixed radix, as product.rs:826-869: v0 = r0, v1 = (r1 - v0) p0^-1 mod p1, lift = v1 p0 + v0
-        const uint64_t v0 = r[0][k];
-        const uint64_t v1 = pdev::mul_mod(pdev::sub_mod(p1, r[1][k], v0), inv10, p1, rc1);
-        const uint64_t lift = v1 * p0 + v0;
+        // Knuth 4.3.2 mixed radix, as product.rs:826-869: v0 = r0, v1 = (r1 - v0) p0^-1 mod p1, lift = v1 p0 + v0;
+        // all 32-bit (p0 < p1 < 2^31): the difference is brought to [0, p1), the Shoup product by p0^-1 to [0, p1)
+        const uint32_t v0 = r[0][k];
+        uint32_t d = r[1][k] - v0;
+        d = r[1][k] >= v0 ? d : d + p1;
+        uint32_t v1 = d * i0 - __umulhi(d, i1) * p1;
+        v1 = umin32(v1, v1 - p1);
+        const uint64_t lift = (uint64_t)v1 * p0 + v0;
         uint64_t* o = dst + tid + k * T;
         if (mode == PI_REPLACE) st_data(o, lift);
         else st_data(o, pdev::add_mod(c.modulus, ld_data(o), lift));

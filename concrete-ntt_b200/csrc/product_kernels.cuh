@@ -22,6 +22,10 @@ struct ProductConsts {
     int count32, count64;          // planes, primes sorted ascending (u32 ones first)
     uint64_t p[kProductMaxPrimes]; // the primes
     uint64_t recip[kProductMaxPrimes]; // floor((2^64 - 1) / p): Barrett quotient estimate for x mod p, x < 2^64
+    // u32 primes below 2^31: Shoup pairs {c, floor(c 2^32 / p)} of c = 1 and c = 2^32 mod p, so that a 64-bit word
+    // reduces limb by limb on the 32-bit multiplier (the fused kernels; 64-bit mul.hi is 5x slower on this GPU)
+    uint32_t red32[kProductMaxPrimes][2][2];
+    uint32_t inv10_32[2];          // Shoup pair of inv[1][0] = p_0^-1 mod p_1 when both are u32 primes below 2^31
     uint64_t inv[kProductMaxPrimes][kProductMaxPrimes]; // inv[j][i] = p_i^-1 mod p_j, i < j (product.rs:205-226)
     uint64_t modulus;
     uint64_t n;                    // polynomial size
