@@ -54,6 +54,9 @@ SIGNATURES.update({
     "cntt_native_fwd": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "cntt_native_fwd_binary": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "cntt_native_inv": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "cntt_native_fwd_host": (_int, [_vp, _vp, _vp, _sz, _sz]),
+    "cntt_native_fwd_binary_host": (_int, [_vp, _vp, _vp, _sz, _sz]),
+    "cntt_native_inv_host": (_int, [_vp, _vp, _vp, _sz, _sz]),
     "cntt_native_polymul": (_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
     "cntt_native_polymul_host": (_int, [_vp, _vp, _vp, _vp, _sz, _sz]),
     "cntt_product_plan_new": (_int, [_sz, _u64, C.POINTER(_u64), _sz, _int, C.POINTER(_vp)]),

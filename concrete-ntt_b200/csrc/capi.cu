@@ -881,6 +881,51 @@ CNTT_API int cntt_native_polymul_host(const cntt_native_plan* pl, void* h_prod, 
     return CNTT_OK;
 }
 
+// host-slice flavours of Plan32::fwd / fwd_binary / inv: the reference's call shape (value: n words, mod_p_k: n u32 each;
+// here `batch` of them concatenated, plane k of polynomial b at h_mod_p[(k * batch + b) * n]).  Staged through the plan's
+// arena, synchronous.  inv copies the planes back as well: the reference's inv leaves the inverse transforms in them.
+static int native_split_host(const cntt_native_plan* pl, void* h_value, uint32_t* h_mod_p, size_t len, size_t batch, int what)
+{
+    if (!pl || ((!h_value || !h_mod_p) && len)) return CNTT_NULL_POINTER;
+    if (len != pl->n * batch) return CNTT_LENGTH_MISMATCH; // assert_eq!(value.len(), n) (src/native64.rs:983-989)
+    if (what == 1 && pl->kind < NK_BINARY32) return CNTT_UNSUPPORTED;
+    if (batch == 0) return CNTT_OK;
+    GUARD(pl->device);
+    auto* mpl = const_cast<cntt_native_plan*>(pl);
+    Staging& stg = mpl->stg;
+    std::lock_guard<std::mutex> lk(stg.mu);
+    const size_t vbytes = len * (size_t)native_word_bytes(pl->kind);
+    const size_t pbytes = (size_t)pl->nprimes * len * sizeof(uint32_t);
+    CU(stg.ensure(vbytes + pbytes));
+    char* dv = static_cast<char*>(stg.buf);
+    uint32_t* dp = reinterpret_cast<uint32_t*>(dv + vbytes);
+    cudaStream_t st = stg.stream;
+    if (what <= 1) { // fwd / fwd_binary: value in, planes out
+        CU(cudaMemcpyAsync(dv, h_value, vbytes, cudaMemcpyHostToDevice, st));
+        CU(native_fwd_impl(pl, dv, dp, batch, what == 1, st));
+        CU(cudaMemcpyAsync(h_mod_p, dp, pbytes, cudaMemcpyDeviceToHost, st));
+    } else {         // inv: planes in (clobbered), value out
+        CU(cudaMemcpyAsync(dp, h_mod_p, pbytes, cudaMemcpyHostToDevice, st));
+        CU(native_inv_impl(pl, dv, dp, batch, st));
+        CU(cudaMemcpyAsync(h_value, dv, vbytes, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h_mod_p, dp, pbytes, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return CNTT_OK;
+}
+CNTT_API int cntt_native_fwd_host(const cntt_native_plan* pl, const void* h_value, uint32_t* h_mod_p, size_t len, size_t batch)
+{
+    return native_split_host(pl, const_cast<void*>(h_value), h_mod_p, len, batch, 0);
+}
+CNTT_API int cntt_native_fwd_binary_host(const cntt_native_plan* pl, const void* h_value, uint32_t* h_mod_p, size_t len, size_t batch)
+{
+    return native_split_host(pl, const_cast<void*>(h_value), h_mod_p, len, batch, 1);
+}
+CNTT_API int cntt_native_inv_host(const cntt_native_plan* pl, void* h_value, uint32_t* h_mod_p, size_t len, size_t batch)
+{
+    return native_split_host(pl, h_value, h_mod_p, len, batch, 2);
+}
+
 // ---- product::Plan (src/product.rs) --------------------------------------------------------------------------
 #include "product_kernels.cuh"
 #include "product_fused.hpp"

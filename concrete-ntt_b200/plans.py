@@ -236,27 +236,31 @@ class _NativePlan:
             raise ReferencePanic("residue planes must hold num_primes * batch * n words")
         return b
 
-    def _fwd(self, fn, value, mod_p):
+    def _fwd(self, name, value, mod_p):
         v = self._word_buf(value, "value")
         m = self._planes(mod_p, v.batch)
-        if not (v.is_dev and m.is_dev):
-            raise TypeError("fwd/inv operate on device-resident tensors; use negacyclic_polymul for host slices")
-        check(fn(self._h, v.ptr, m.ptr, v.batch, _stream_of(v.t)))
+        l = _lib.lib()
+        if v.is_dev != m.is_dev:
+            raise TypeError("value and mod_p must be on the same side (both device tensors or both host arrays)")
+        if v.is_dev:   # device-resident, asynchronous on the tensor's stream
+            check(getattr(l, "cntt_native_" + name)(self._h, v.ptr, m.ptr, v.batch, _stream_of(v.t)))
+        else:          # the reference's host-slice call shape, staged through the plan's arena
+            check(getattr(l, "cntt_native_%s_host" % name)(self._h, v.ptr, m.ptr, v.batch * self._n, v.batch))
         return mod_p
 
     def fwd(self, value, mod_p):
         """Plan32::fwd(value, mod_p0, ...): residues of `value` mod each prime, forward-transformed."""
-        return self._fwd(_lib.lib().cntt_native_fwd, value, mod_p)
+        return self._fwd("fwd", value, mod_p)
 
     def fwd_binary(self, value, mod_p):
         """Plan32::fwd_binary (binary plans): `value as u32` without reduction, forward-transformed."""
         if not self._binary:
             raise AttributeError("fwd_binary exists only on native_binary* plans")
-        return self._fwd(_lib.lib().cntt_native_fwd_binary, value, mod_p)
+        return self._fwd("fwd_binary", value, mod_p)
 
     def inv(self, value, mod_p):
         """Plan32::inv(value, mod_p0, ...): inverse transforms (clobbering mod_p) + Garner lift."""
-        return self._fwd(_lib.lib().cntt_native_inv, value, mod_p)
+        return self._fwd("inv", value, mod_p)
 
     def negacyclic_polymul(self, prod, lhs, rhs):
         """Plan32::negacyclic_polymul(prod, lhs, rhs)."""

@@ -139,6 +139,12 @@ int cntt_native_fwd(const cntt_native_plan* plan, const void* d_value, uint32_t*
 int cntt_native_fwd_binary(const cntt_native_plan* plan, const void* d_value, uint32_t* d_mod_p, size_t batch, void* stream);
 /* Plan32::inv(value, mod_p0..)        mod_p planes are clobbered, like in the reference */
 int cntt_native_inv(const cntt_native_plan* plan, void* d_value, uint32_t* d_mod_p, size_t batch, void* stream);
+/* host-slice flavours of fwd / fwd_binary / inv (the reference's call shape; `batch` polynomials concatenated, len =
+ * words in value = n * batch, plane k of polynomial b at h_mod_p[(k * batch + b) * n]); inv also returns the clobbered
+ * planes, which the reference leaves holding the un-normalised inverse transforms (src/native64.rs:1001-1014) */
+int cntt_native_fwd_host(const cntt_native_plan* plan, const void* h_value, uint32_t* h_mod_p, size_t len, size_t batch);
+int cntt_native_fwd_binary_host(const cntt_native_plan* plan, const void* h_value, uint32_t* h_mod_p, size_t len, size_t batch);
+int cntt_native_inv_host(const cntt_native_plan* plan, void* h_value, uint32_t* h_mod_p, size_t len, size_t batch);
 /* Plan32::negacyclic_polymul(prod, lhs, rhs) */
 int cntt_native_polymul(const cntt_native_plan* plan, void* d_prod, const void* d_lhs, const void* d_rhs, size_t batch, void* stream);
 /* host-slice flavour: len = words in each of prod/lhs/rhs; must equal n*batch */

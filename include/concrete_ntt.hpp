@@ -136,6 +136,15 @@ class NativePlan32 {
     // batch extensions
     void negacyclic_polymul_batch(Word* prod, const Word* lhs, const Word* rhs, size_t batch) const { check(cntt_native_polymul_host(h_, prod, lhs, rhs, ntt_size() * batch, batch)); }
     void negacyclic_polymul_device(Word* prod, const Word* lhs, const Word* rhs, size_t batch, void* stream = nullptr) const { check(cntt_native_polymul(h_, prod, lhs, rhs, batch, stream)); }
+    // reference shape (src/native64.rs:971-1038): host slices; mod_p holds num_primes() planes of n u32 each, back to back
+    // (the reference's mod_p0, mod_p1, ... concatenated); inv clobbers mod_p like the reference
+    void fwd(const Word* value, uint32_t* mod_p, size_t len) const { check(cntt_native_fwd_host(h_, value, mod_p, len, 1)); }
+    void fwd_binary(const Word* value, uint32_t* mod_p, size_t len) const
+    {
+        static_assert(BINARY, "fwd_binary exists only on native_binary* plans");
+        check(cntt_native_fwd_binary_host(h_, value, mod_p, len, 1));
+    }
+    void inv(Word* value, uint32_t* mod_p, size_t len) const { check(cntt_native_inv_host(h_, value, mod_p, len, 1)); }
     // fwd / fwd_binary / inv on device residue planes (plane k of polynomial b at mod_p[(k*batch + b)*n])
     void fwd_device(const Word* value, uint32_t* mod_p, size_t batch, void* stream = nullptr) const { check(cntt_native_fwd(h_, value, mod_p, batch, stream)); }
     void fwd_binary_device(const Word* value, uint32_t* mod_p, size_t batch, void* stream = nullptr) const

@@ -306,3 +306,35 @@ def test_extended_n65536_extreme_magnitudes(cntt, oracle, torch_cuda):
         dp = torch_cuda.empty_like(dl)
         gp.negacyclic_polymul(dp, dl, dr)
         assert (host(dp, wdt)[0] == oracle.negacyclic_wrapping(bits, lhs[0], rhs[0])).all(), (bits, binary)
+
+
+@pytest.mark.parametrize("bits,binary", [(32, False), (64, False), (128, False), (64, True)])
+def test_split_fwd_inv_host_slices(cntt, oracle, bits, binary):
+    """The reference's own call shape for Plan32::fwd / fwd_binary / inv: host slices (cntt_native_*_host), one
+    polynomial and a small batch; inv also returns the clobbered residue buffers (src/native64.rs:1001-1014)."""
+    n = 256
+    g = rng(bits * 3 + int(binary))
+    gp, op = plan_pair(cntt, oracle, n, bits, binary)
+    npz = gp.num_primes()
+    for batch in (1, 3):
+        val = rand_words(g, bits, (batch, n))
+        planes = np.zeros((npz, batch, n), np.uint32)
+        gp.fwd(val, planes)
+        ref_planes = np.stack([op.fwd(v) for v in val], axis=1)
+        assert (planes == ref_planes).all()
+        if binary:
+            bval = make_rhs(g, bits, (batch, n), True)
+            gp.fwd_binary(bval, planes)
+            assert (planes == np.stack([op.fwd_binary(v) for v in bval], axis=1)).all()
+            gp.fwd(val, planes)
+        out = np.zeros_like(val)
+        gp.inv(out, planes)
+        ref_out, ref_clobbered = [], []
+        for b in range(batch):
+            pb = np.ascontiguousarray(ref_planes[:, b])
+            ref_out.append(op.inv(pb))
+            ref_clobbered.append(pb)
+        assert (out == np.stack(ref_out)).all()
+        assert (planes == np.stack(ref_clobbered, axis=1)).all()
+    with pytest.raises(cntt.ReferencePanic):
+        gp.fwd(rand_words(g, bits, (1, n // 2)), np.zeros((npz, 1, n // 2), np.uint32))

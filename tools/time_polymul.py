@@ -29,6 +29,18 @@ for c in cases:
         print("product(2 x 31-bit primes) n=%d batch=%d: fwd %.3f ms (%.1f M/s)  mul_accumulate %.3f ms (%.0f GB/s)  inv %.3f ms (%.1f M/s)"
               % (n, batch, tf, batch / tf / 1e3, tm, gb(tm, 4 * plan.ntt_domain_len()), ti, batch / ti / 1e3))
         continue
+    if kind.startswith("split"):   # Plan32::fwd / inv on device residue planes (the NTT-domain-key workflow)
+        bits = int(kind[5:])
+        plan = getattr(cntt, "native%d" % bits).Plan32.try_new(n)
+        dt = torch.int32 if bits == 32 else torch.int64
+        hi = 2**31 - 1 if bits == 32 else 2**63 - 1
+        shape = (batch, n, 2) if bits == 128 else (batch, n)
+        val = torch.randint(-hi - 1, hi, shape, dtype=dt, device="cuda", generator=g)
+        planes = torch.empty((plan.num_primes(), batch, n), dtype=torch.int32, device="cuda")
+        tf = bench(lambda: plan.fwd(val, planes))
+        ti = bench(lambda: plan.inv(val, planes))
+        print("native%d split n=%d batch=%d: fwd %.3f ms (%.1f M/s)  inv %.3f ms (%.1f M/s)" % (bits, n, batch, tf, batch / tf / 1e3, ti, batch / ti / 1e3))
+        continue
     if kind.startswith("native") or kind.startswith("binary"):
         bits = int(kind.replace("native", "").replace("binary", ""))
         mod = getattr(cntt, ("native_binary%d" if kind.startswith("binary") else "native%d") % bits)
