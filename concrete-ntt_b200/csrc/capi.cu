@@ -728,7 +728,10 @@ CNTT_API uint32_t cntt_native_prime(const cntt_native_plan* pl, int i) { return 
 static cudaError_t native_fwd_impl(const cntt_native_plan* pl, const void* value, uint32_t* planes, size_t batch, bool binary_copy, cudaStream_t st)
 {
     const size_t nwords = pl->n * batch;
-    cudaError_t e = native_reduce(pl->dev, value, planes, nwords, nwords, binary_copy, st);
+    cudaError_t e = native_split_fused(pl->dev, const_cast<void*>(value), planes, nwords, batch, binary_copy ? 1 : 0, st);
+    if (e != cudaErrorNotSupported) return e;
+    (void)cudaGetLastError();
+    e = native_reduce(pl->dev, value, planes, nwords, nwords, binary_copy, st);
     if (e != cudaSuccess) return e;
     for (int k = 0; k < pl->nprimes; k++)
         if ((e = ntt_A32L4(pl->dev.sub[k], planes + (size_t)k * nwords, batch, true, st)) != cudaSuccess) return e;

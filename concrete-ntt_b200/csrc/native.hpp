@@ -82,6 +82,11 @@ cudaError_t native_fused_build_last(int logn, const uint2* heap, uint2* out, cud
 cudaError_t native_polymul_fused(const NativePlanDev& pl, void* prod, const void* lhs, const void* rhs, size_t batch,
                                  cudaStream_t st);
 
+// fused split-phase forward kernel (native_split.cu): what = 0 fwd, 1 fwd_binary; cudaErrorNotSupported when no fused
+// variant exists for the plan's size (the caller then composes reduce / transforms / CRT)
+cudaError_t native_split_fused(const NativePlanDev& pl, void* value, uint32_t* planes, size_t plane_stride, size_t batch, int what,
+                               cudaStream_t st);
+
 // three-kernel polymul for 4096 < N <= 65536 (native_large.cuh; 65536 only exists for extended plans).  planes_l / planes_r: nprimes planes of batch * n
 // u32 each (scratch).  Returns cudaErrorNotSupported for other sizes.
 bool native_large_supported(int logn);
