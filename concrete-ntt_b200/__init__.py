@@ -31,6 +31,11 @@ class _Solinas:
     P = 0xFFFFFFFF00000001
 
 
+def _native52(bits, binary):
+    name = "%s%d::Plan52" % ("native_binary" if binary else "native", bits)
+    return type("Plan52", (_plans._Native52Plan,), {"_bits": bits, "_binary": binary, "__doc__": name})
+
+
 def _native(bits, binary):
     return type("Plan32", (_plans._NativePlan,), {"_bits": bits, "_binary": binary,
                 "__doc__": "native%s%d::Plan32" % ("_binary" if binary else "", bits)})
@@ -119,11 +124,11 @@ def _exp_mod64(n, base, power):
 
 prime32 = _module("prime32", Plan=type("Plan", (_plans.Plan32Prime,), {"__doc__": "prime32::Plan"}))
 prime64 = _module("prime64", Plan=type("Plan", (_plans.Plan64Prime,), {"__doc__": "prime64::Plan"}), Solinas=_Solinas)
-native32 = _module("native32", Plan32=_native(32, False), Plan52=_plans.Plan52Unavailable)
-native64 = _module("native64", Plan32=_native(64, False), Plan52=_plans.Plan52Unavailable)
+native32 = _module("native32", Plan32=_native(32, False), Plan52=_native52(32, False))
+native64 = _module("native64", Plan32=_native(64, False), Plan52=_native52(64, False))
 native128 = _module("native128", Plan32=_native(128, False))
-native_binary32 = _module("native_binary32", Plan32=_native(32, True), Plan52=_plans.Plan52Unavailable)
-native_binary64 = _module("native_binary64", Plan32=_native(64, True), Plan52=_plans.Plan52Unavailable)
+native_binary32 = _module("native_binary32", Plan32=_native(32, True), Plan52=_native52(32, True))
+native_binary64 = _module("native_binary64", Plan32=_native(64, True), Plan52=_native52(64, True))
 native_binary128 = _module("native_binary128", Plan32=_native(128, True))
 product = _module("product", Plan=type("Plan", (_plans.ProductPlan,), {"__doc__": "product::Plan"}),
                   FwdMode=_plans.FwdMode, InvMode=_plans.InvMode)

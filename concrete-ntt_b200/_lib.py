@@ -59,6 +59,16 @@ SIGNATURES.update({
     "cntt_native_inv_host": (_int, [_vp, _vp, _vp, _sz, _sz]),
     "cntt_native_polymul": (_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
     "cntt_native_polymul_host": (_int, [_vp, _vp, _vp, _vp, _sz, _sz]),
+    "cntt_native52_plan_new": (_int, [_sz, _int, _int, _int, C.POINTER(_vp)]),
+    "cntt_native52_plan_free": (None, [_vp]),
+    "cntt_native52_ntt_size": (_sz, [_vp]),
+    "cntt_native52_num_primes": (_int, [_vp]),
+    "cntt_native52_prime": (_u64, [_vp, _int]),
+    "cntt_native52_fwd": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "cntt_native52_fwd_binary": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "cntt_native52_inv": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "cntt_native52_polymul": (_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "cntt_native52_polymul_host": (_int, [_vp, _vp, _vp, _vp, _sz, _sz]),
     "cntt_product_plan_new": (_int, [_sz, _u64, C.POINTER(_u64), _sz, _int, C.POINTER(_vp)]),
     "cntt_product_plan_free": (None, [_vp]),
     "cntt_product_ntt_size": (_sz, [_vp]),

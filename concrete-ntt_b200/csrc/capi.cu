@@ -929,6 +929,113 @@ CNTT_API int cntt_native_inv_host(const cntt_native_plan* pl, void* h_value, uin
     return native_split_host(pl, h_value, h_mod_p, len, batch, 2);
 }
 
+// ---- Plan52 twins: native32 / native64 / native_binary32 / native_binary64 ::Plan52 ---------------------------------
+#include "native52_kernels.cuh"
+
+struct cntt_native52_plan {
+    size_t n;
+    int device;
+    int binary;
+    Native52Consts c;
+    cntt_prime64_plan* sub[3];
+    cntt_native_plan* inner; // the Plan32 of the same kind: negacyclic_polymul results are identical (exact product, wrapped)
+};
+
+CNTT_API void cntt_native52_plan_free(cntt_native52_plan* pl)
+{
+    if (!pl) return;
+    for (int k = 0; k < 3; k++)
+        if (pl->sub[k]) cntt_prime64_plan_free(pl->sub[k]);
+    if (pl->inner) cntt_native_plan_free(pl->inner);
+    delete pl;
+}
+CNTT_API int cntt_native52_plan_new(size_t n, int word_bits, int binary, int device, cntt_native52_plan** out)
+{
+    // primes52::P0..P2 (src/lib.rs:600-602)
+    static const uint64_t P52[3] = {0x3FFFFFE770001ull, 0x3FFFFFEB90001ull, 0x3FFFFFEC80001ull};
+    if (!out) return CNTT_NULL_POINTER;
+    *out = nullptr;
+    if (word_bits != 32 && word_bits != 64) return CNTT_UNSUPPORTED; // no 128-bit Plan52 in the reference
+    // native32: P0,P1 (native32.rs:441-445); native64: P0..P2 (native64.rs:1078-1087); binary32: P0
+    // (native_binary32.rs:270-274); binary64: P0,P1 (native_binary64.rs:453-457)
+    const int np = word_bits == 32 ? (binary ? 1 : 2) : (binary ? 2 : 3);
+    cntt_native52_plan* pl = new cntt_native52_plan();
+    pl->n = n; pl->device = device; pl->binary = binary; pl->inner = nullptr;
+    for (int k = 0; k < 3; k++) pl->sub[k] = nullptr;
+    for (int k = 0; k < np; k++) {
+        int st = build_prime64(n, P52[k], device, &pl->sub[k]); // Plan::try_new(n, P_k)?  -> None on the first failure
+        if (st != CNTT_OK) { cntt_native52_plan_free(pl); return st; }
+    }
+    int st = cntt_native_plan_new(n, word_bits, binary, device, &pl->inner);
+    if (st != CNTT_OK) { cntt_native52_plan_free(pl); return st; }
+    Native52Consts& c = pl->c;
+    c.np = np; c.word_bytes = word_bits / 8; c.reduce = word_bits == 64;
+    uint64_t pre = 1;
+    for (int k = 0; k < 3; k++) { c.p[k] = k < np ? P52[k] : 1; c.inv[k] = 0; c.pre[k] = 0; }
+    for (int k = 0; k < np; k++) {
+        c.pre[k] = pre;
+        if (k >= 1) {
+            host::Fp f(P52[k]);
+            uint64_t m = 1;
+            for (int j = 0; j < k; j++) m = f.mul(m, P52[j] % P52[k]);
+            c.inv[k] = f.inv(m);
+        }
+        pre *= P52[k]; // wrapping, like the reference's P0.wrapping_mul(P1) (native64.rs:793-794)
+    }
+    c.full = pre;
+    *out = pl;
+    return CNTT_OK;
+}
+CNTT_API size_t cntt_native52_ntt_size(const cntt_native52_plan* pl) { return pl ? pl->n : 0; }
+CNTT_API int cntt_native52_num_primes(const cntt_native52_plan* pl) { return pl ? pl->c.np : 0; }
+CNTT_API uint64_t cntt_native52_prime(const cntt_native52_plan* pl, int i) { return (pl && i >= 0 && i < pl->c.np) ? pl->c.p[i] : 0; }
+
+static int native52_fwd(const cntt_native52_plan* pl, const void* d_value, uint64_t* d_mod_p, size_t batch, bool copy, cudaStream_t st)
+{
+    if (!pl || ((!d_value || !d_mod_p) && batch)) return CNTT_NULL_POINTER;
+    if (batch == 0) return CNTT_OK;
+    GUARD(pl->device);
+    const unsigned long long nwords = (unsigned long long)pl->n * batch;
+    const unsigned g = (unsigned)std::min<unsigned long long>((nwords + 255) / 256, 148ull * 16ull);
+    if (copy) k_native52_reduce<true><<<g, 256, 0, st>>>(pl->c, d_value, d_mod_p, nwords, nwords);
+    else k_native52_reduce<false><<<g, 256, 0, st>>>(pl->c, d_value, d_mod_p, nwords, nwords);
+    CU(cudaGetLastError());
+    for (int k = 0; k < pl->c.np; k++) CU(run_ntt64(pl->sub[k], d_mod_p + (size_t)k * nwords, batch, true, st));
+    return CNTT_OK;
+}
+CNTT_API int cntt_native52_fwd(const cntt_native52_plan* pl, const void* d_value, uint64_t* d_mod_p, size_t batch, void* stream)
+{
+    return native52_fwd(pl, d_value, d_mod_p, batch, false, (cudaStream_t)stream);
+}
+CNTT_API int cntt_native52_fwd_binary(const cntt_native52_plan* pl, const void* d_value, uint64_t* d_mod_p, size_t batch, void* stream)
+{
+    if (pl && !pl->binary) return CNTT_UNSUPPORTED; // only the native_binary* Plan52 have fwd_binary
+    return native52_fwd(pl, d_value, d_mod_p, batch, true, (cudaStream_t)stream);
+}
+CNTT_API int cntt_native52_inv(const cntt_native52_plan* pl, void* d_value, uint64_t* d_mod_p, size_t batch, void* stream)
+{
+    if (!pl || ((!d_value || !d_mod_p) && batch)) return CNTT_NULL_POINTER;
+    if (batch == 0) return CNTT_OK;
+    GUARD(pl->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned long long nwords = (unsigned long long)pl->n * batch;
+    for (int k = 0; k < pl->c.np; k++) CU(run_ntt64(pl->sub[k], d_mod_p + (size_t)k * nwords, batch, false, st));
+    const unsigned g = (unsigned)std::min<unsigned long long>((nwords + 255) / 256, 148ull * 16ull);
+    k_native52_crt<<<g, 256, 0, st>>>(pl->c, d_value, d_mod_p, nwords, nwords);
+    CU(cudaGetLastError());
+    return CNTT_OK;
+}
+CNTT_API int cntt_native52_polymul(const cntt_native52_plan* pl, void* d_prod, const void* d_lhs, const void* d_rhs, size_t batch, void* stream)
+{
+    if (!pl) return CNTT_NULL_POINTER;
+    return cntt_native_polymul(pl->inner, d_prod, d_lhs, d_rhs, batch, stream);
+}
+CNTT_API int cntt_native52_polymul_host(const cntt_native52_plan* pl, void* h_prod, const void* h_lhs, const void* h_rhs, size_t len, size_t batch)
+{
+    if (!pl) return CNTT_NULL_POINTER;
+    return cntt_native_polymul_host(pl->inner, h_prod, h_lhs, h_rhs, len, batch);
+}
+
 // ---- product::Plan (src/product.rs) --------------------------------------------------------------------------
 #include "product_kernels.cuh"
 #include "product_fused.hpp"

@@ -278,16 +278,97 @@ class _NativePlan:
         return prod
 
 
-class Plan52Unavailable:
-    """native32/native64/native_binary32/native_binary64::Plan52 (src/native64.rs:1072-1165 ...).  In the reference
-    the type exists only with feature = "nightly" on x86-64, and its try_new returns None unless the CPU has
-    AVX-512 IFMA (src/native64.rs:1075-1079).  Its polymul results are identical to Plan32's -- only the public
-    residue format (u64 residues mod ~50-bit primes) differs, and that format is tied to IFMA's 52-bit
-    multiplier, which has no GPU analogue.  This mirror is the no-IFMA behaviour: try_new -> None."""
+class _Native52Plan:
+    """native32 / native64 / native_binary32 / native_binary64 ::Plan52 (src/native64.rs:29-34,1072-1165 and twins): the
+    same plans on 2 / 3 / 1 / 2 ~50-bit primes (primes52) with uint64 residue planes, shape (num_primes, batch..., n).
+    In the reference the type needs feature = "nightly" and try_new is None without AVX-512 IFMA; here it is always
+    available.  fwd / fwd_binary / inv run on device tensors; negacyclic_polymul takes device tensors or host arrays and
+    returns exactly what Plan32 returns."""
+    _bits = None
+    _binary = False
+
+    def __init__(self, handle, n, device):
+        self._h, self._n, self._device = handle, n, device
+        self._np = _lib.lib().cntt_native52_num_primes(handle)
 
     @classmethod
     def try_new(cls, n, device=0):
-        return None
+        h = C.c_void_p()
+        st = _lib.lib().cntt_native52_plan_new(n, cls._bits, int(cls._binary), device, C.byref(h))
+        if st in (_lib.INVALID_SIZE, _lib.INVALID_MODULUS, _lib.NO_ROOT):
+            return None
+        check(st, "try_new")
+        return cls(h, n, device)
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib().cntt_native52_plan_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def ntt_size(self):
+        return _lib.lib().cntt_native52_ntt_size(self._h)
+
+    def num_primes(self):
+        return self._np
+
+    def ntt_modulus(self, i):
+        return _lib.lib().cntt_native52_prime(self._h, i)
+
+    def ntt_i(self, i):
+        """Plan52::ntt_0() .. : the prime64::Plan of the i-th prime"""
+        if not 0 <= i < self._np:
+            raise IndexError(i)
+        cache = self.__dict__.setdefault("_ntt", {})
+        if i not in cache:
+            cache[i] = Plan64Prime.try_new(self._n, self.ntt_modulus(i), device=self._device)
+        return cache[i]
+
+    def _args(self, value, mod_p):
+        v = _Buf(value, self._bits // 8, "value")
+        if len(v.shape) == 0 or v.shape[-1] != self._n:
+            raise ReferencePanic("assert_eq!(n, value.len())")
+        batch = v.words // self._n
+        m = _Buf(mod_p, 8, "mod_p")
+        if m.words != self._np * batch * self._n:
+            raise ReferencePanic("residue planes must hold num_primes * batch * n words")
+        if not (v.is_dev and m.is_dev):
+            raise TypeError("Plan52 fwd/inv operate on device-resident tensors")
+        return v, m, batch
+
+    def fwd(self, value, mod_p):
+        v, m, batch = self._args(value, mod_p)
+        check(_lib.lib().cntt_native52_fwd(self._h, v.ptr, m.ptr, batch, _stream_of(v.t)))
+        return mod_p
+
+    def fwd_binary(self, value, mod_p):
+        if not self._binary:
+            raise AttributeError("fwd_binary exists only on native_binary* plans")
+        v, m, batch = self._args(value, mod_p)
+        check(_lib.lib().cntt_native52_fwd_binary(self._h, v.ptr, m.ptr, batch, _stream_of(v.t)))
+        return mod_p
+
+    def inv(self, value, mod_p):
+        v, m, batch = self._args(value, mod_p)
+        check(_lib.lib().cntt_native52_inv(self._h, v.ptr, m.ptr, batch, _stream_of(v.t)))
+        return value
+
+    def negacyclic_polymul(self, prod, lhs, rhs):
+        bufs = [_Buf(x, self._bits // 8, nm) for x, nm in ((prod, "prod"), (lhs, "lhs"), (rhs, "rhs"))]
+        for b in bufs:
+            if len(b.shape) == 0 or b.shape[-1] != self._n or b.words != bufs[0].words:
+                raise ReferencePanic("assert_eq!(n, lhs.len())")
+        if len({b.is_dev for b in bufs}) != 1:
+            raise TypeError("all arguments must be on the same side (all device or all host)")
+        batch = bufs[0].words // self._n
+        l = _lib.lib()
+        if bufs[0].is_dev:
+            check(l.cntt_native52_polymul(self._h, bufs[0].ptr, bufs[1].ptr, bufs[2].ptr, batch, _stream_of(bufs[0].t)))
+        else:
+            check(l.cntt_native52_polymul_host(self._h, bufs[0].ptr, bufs[1].ptr, bufs[2].ptr, bufs[0].words, batch))
+        return prod
 
 
 class FwdMode:

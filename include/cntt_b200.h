@@ -150,6 +150,24 @@ int cntt_native_polymul(const cntt_native_plan* plan, void* d_prod, const void* 
 /* host-slice flavour: len = words in each of prod/lhs/rhs; must equal n*batch */
 int cntt_native_polymul_host(const cntt_native_plan* plan, void* h_prod, const void* h_lhs, const void* h_rhs, size_t len, size_t batch);
 
+/* ---- Plan52 twins: native32 / native64 / native_binary32 / native_binary64 ::Plan52 ----------------------------
+ * (src/native32.rs:19,435-496; native64.rs:29-34,1072-1165; native_binary32.rs:19,266-330; native_binary64.rs:29,447-521)
+ * The same plans on 2 / 3 / 1 / 2 of the ~50-bit primes52 (src/lib.rs:598-652) with u64 residue planes transformed by
+ * prime64 plans.  In the reference they exist only under feature = "nightly" and try_new is None without AVX-512 IFMA;
+ * here they are always available.  word_bits in {32, 64}.  negacyclic_polymul returns exactly what Plan32 returns. */
+typedef struct cntt_native52_plan cntt_native52_plan;
+int cntt_native52_plan_new(size_t n, int word_bits, int binary, int device, cntt_native52_plan** out);
+void cntt_native52_plan_free(cntt_native52_plan* plan);
+size_t cntt_native52_ntt_size(const cntt_native52_plan* plan);
+int cntt_native52_num_primes(const cntt_native52_plan* plan);
+uint64_t cntt_native52_prime(const cntt_native52_plan* plan, int i);          /* Plan52::ntt_i().modulus() */
+/* Plan52::fwd / fwd_binary / inv: value batch*n words, d_mod_p num_primes planes of batch*n u64 (plane k at k*batch*n) */
+int cntt_native52_fwd(const cntt_native52_plan* plan, const void* d_value, uint64_t* d_mod_p, size_t batch, void* stream);
+int cntt_native52_fwd_binary(const cntt_native52_plan* plan, const void* d_value, uint64_t* d_mod_p, size_t batch, void* stream);
+int cntt_native52_inv(const cntt_native52_plan* plan, void* d_value, uint64_t* d_mod_p, size_t batch, void* stream);
+int cntt_native52_polymul(const cntt_native52_plan* plan, void* d_prod, const void* d_lhs, const void* d_rhs, size_t batch, void* stream);
+int cntt_native52_polymul_host(const cntt_native52_plan* plan, void* h_prod, const void* h_lhs, const void* h_rhs, size_t len, size_t batch);
+
 /* ---- product::Plan (modulus = product of distinct primes, < 2^64)      src/product.rs:139-967 -------------
  * NTT-domain layout of one polynomial = the reference's (product.rs:261-278): the u32 planes (primes < 2^32,
  * ascending) bit-cast into the front of the u64 buffer, then the u64 planes; ntt_domain_len u64 words.  A batch is

@@ -155,11 +155,44 @@ class NativePlan32 {
     void inv_device(Word* value, uint32_t* mod_p, size_t batch, void* stream = nullptr) const { check(cntt_native_inv(h_, value, mod_p, batch, stream)); }
 };
 
-namespace native32 { using Plan32 = NativePlan32<32, false, uint32_t>; }
-namespace native64 { using Plan32 = NativePlan32<64, false, uint64_t>; }
+// native32 / native64 / native_binary32 / native_binary64 ::Plan52 (reference: feature = "nightly" + AVX-512 IFMA only):
+// u64 residue planes over the ~50-bit primes52; negacyclic_polymul returns exactly what Plan32 returns.
+template <int BITS, bool BINARY, class Word>
+class NativePlan52 {
+    cntt_native52_plan* h_ = nullptr;
+    explicit NativePlan52(cntt_native52_plan* h) : h_(h) {}
+
+  public:
+    NativePlan52(NativePlan52&& o) noexcept : h_(std::exchange(o.h_, nullptr)) {}
+    NativePlan52(const NativePlan52&) = delete;
+    ~NativePlan52() { cntt_native52_plan_free(h_); }
+    static std::optional<NativePlan52> try_new(size_t n, int device = 0)
+    {
+        cntt_native52_plan* h = nullptr;
+        int st = cntt_native52_plan_new(n, BITS, BINARY ? 1 : 0, device, &h);
+        if (is_none(st)) return std::nullopt;
+        check(st);
+        return NativePlan52(h);
+    }
+    size_t ntt_size() const { return cntt_native52_ntt_size(h_); }
+    int num_primes() const { return cntt_native52_num_primes(h_); }
+    uint64_t ntt_modulus(int i) const { return cntt_native52_prime(h_, i); }
+    void negacyclic_polymul(Word* prod, const Word* lhs, const Word* rhs, size_t len) const { check(cntt_native52_polymul_host(h_, prod, lhs, rhs, len, 1)); }
+    void negacyclic_polymul_device(Word* prod, const Word* lhs, const Word* rhs, size_t batch, void* stream = nullptr) const { check(cntt_native52_polymul(h_, prod, lhs, rhs, batch, stream)); }
+    void fwd_device(const Word* value, uint64_t* mod_p, size_t batch, void* stream = nullptr) const { check(cntt_native52_fwd(h_, value, mod_p, batch, stream)); }
+    void fwd_binary_device(const Word* value, uint64_t* mod_p, size_t batch, void* stream = nullptr) const
+    {
+        static_assert(BINARY, "fwd_binary exists only on native_binary* plans");
+        check(cntt_native52_fwd_binary(h_, value, mod_p, batch, stream));
+    }
+    void inv_device(Word* value, uint64_t* mod_p, size_t batch, void* stream = nullptr) const { check(cntt_native52_inv(h_, value, mod_p, batch, stream)); }
+};
+
+namespace native32 { using Plan32 = NativePlan32<32, false, uint32_t>; using Plan52 = NativePlan52<32, false, uint32_t>; }
+namespace native64 { using Plan32 = NativePlan32<64, false, uint64_t>; using Plan52 = NativePlan52<64, false, uint64_t>; }
 namespace native128 { using Plan32 = NativePlan32<128, false, unsigned __int128>; }
-namespace native_binary32 { using Plan32 = NativePlan32<32, true, uint32_t>; }
-namespace native_binary64 { using Plan32 = NativePlan32<64, true, uint64_t>; }
+namespace native_binary32 { using Plan32 = NativePlan32<32, true, uint32_t>; using Plan52 = NativePlan52<32, true, uint32_t>; }
+namespace native_binary64 { using Plan32 = NativePlan32<64, true, uint64_t>; using Plan52 = NativePlan52<64, true, uint64_t>; }
 namespace native_binary128 { using Plan32 = NativePlan32<128, true, unsigned __int128>; }
 
 // product::Plan (src/product.rs:139-967): modulus = product of distinct primes.  NTT-domain buffers hold

@@ -301,6 +301,58 @@ class Native:
         self._L.o_native_polymul_batch(self._h, _ptr(prod), _ptr(lhs), _ptr(rhs), batch, nthreads)
 
 
+PRIMES52 = (0x3FFFFFE770001, 0x3FFFFFEB90001, 0x3FFFFFEC80001)   # primes52::P0..P2, src/lib.rs:600-602
+
+
+class Native52:
+    """native32 / native64 / native_binary32 / native_binary64 ::Plan52 (src/native64.rs:1072-1165, native32.rs:435-496,
+    native_binary32.rs:266-330, native_binary64.rs:447-521).  The reference's reconstruct_52bit_* functions exist only as
+    AVX-512-IFMA code (no scalar twin); every intermediate they produce is canonical (mul_mod52_avx512 ends with
+    small_mod, native32.rs:96-107), so they compute the mixed-radix digits v_k of the CRT and
+    v_0 + v_1 P_0 + v_2 P_0 P_1 - (v_top > P_top / 2 ? P_0 .. P_top : 0) wrapped to the word (native64.rs:796-828,
+    native32.rs:237-252, native_binary32.rs:117-124).  Restated here with Python integers; one polynomial per call."""
+
+    def __init__(self, n, bits, binary, plans):
+        self.n, self.bits, self.binary, self.plans = n, bits, binary, plans
+        self.primes = [pl.modulus() for pl in plans]
+
+    @classmethod
+    def try_new(cls, n, bits, binary=False):
+        np_ = (1 if binary else 2) if bits == 32 else (2 if binary else 3)
+        plans = [Plan64.try_new(n, p) for p in PRIMES52[:np_]]
+        if any(pl is None for pl in plans):
+            return None
+        return cls(n, bits, binary, plans)
+
+    def fwd(self, value, binary_copy=False):
+        out = np.empty((len(self.plans), self.n), np.uint64)
+        for k, (pl, p) in enumerate(zip(self.plans, self.primes)):
+            v = value.astype(np.uint64)
+            if self.bits == 64 and not binary_copy:       # native64.rs:1110-1112 `value % P_k`; 32-bit words are < P_k
+                v = v % np.uint64(p)
+            out[k] = pl.fwd(v.copy())
+        return out
+
+    def inv(self, mod_p):
+        res = [pl.inv(mod_p[k].copy()) for k, pl in enumerate(self.plans)]
+        mask = (1 << self.bits) - 1
+        out = np.empty(self.n, np.uint32 if self.bits == 32 else np.uint64)
+        P = self.primes
+        for i in range(self.n):
+            m = [int(r[i]) for r in res]
+            v = [m[0]]
+            partial, pre = m[0], 1
+            for k in range(1, len(P)):
+                pre *= P[k - 1]
+                vk = (m[k] - partial) * pow(pre, -1, P[k]) % P[k]
+                v.append(vk)
+                partial += vk * pre
+            if v[-1] > P[-1] // 2:
+                partial -= pre * P[-1] if len(P) > 1 else P[0]
+            out[i] = partial & mask
+        return out
+
+
 class Product:
     """product::Plan (src/product.rs:139-967), restated on top of the oracle's prime plans.  One polynomial per
     call like the reference: `standard` is a (n,) uint64 array, NTT-domain buffers are (ntt_domain_len,) uint64

@@ -266,10 +266,6 @@ def test_split_phase_key_switch_shape(cntt, oracle, torch_cuda):
     assert (host(out, np.uint64) == ref * np.uint64(n)).all()
 
 
-def test_plan52_is_none_like_a_non_ifma_host(cntt):
-    for mod in (cntt.native32, cntt.native64, cntt.native_binary32, cntt.native_binary64):
-        assert mod.Plan52.try_new(1024) is None      # src/native64.rs:1075-1079 without AVX-512 IFMA
-
 
 @pytest.mark.parametrize("n", [2048, 4096, 32768])
 def test_polymul_extreme_magnitudes(cntt, oracle, torch_cuda, n):
@@ -338,3 +334,55 @@ def test_split_fwd_inv_host_slices(cntt, oracle, bits, binary):
         assert (planes == np.stack(ref_clobbered, axis=1)).all()
     with pytest.raises(cntt.ReferencePanic):
         gp.fwd(rand_words(g, bits, (1, n // 2)), np.zeros((npz, 1, n // 2), np.uint32))
+
+
+@pytest.mark.parametrize("bits,binary", [(32, False), (64, False), (32, True), (64, True)])
+@pytest.mark.parametrize("n", [64, 1024])
+def test_plan52(cntt, oracle, torch_cuda, bits, binary, n):
+    """Plan52 twins (primes52, u64 residue planes over prime64 plans): fwd / fwd_binary planes and inv lift against the
+    oracle restatement, inv on arbitrary canonical residues (sign rule v_top > P_top / 2), and negacyclic_polymul
+    equal to Plan32's (and to the wrapping schoolbook at n = 64)."""
+    torch = torch_cuda
+    mod = getattr(cntt, ("native_binary%d" if binary else "native%d") % bits)
+    gp, op = mod.Plan52.try_new(n), oracle.Native52.try_new(n, bits, binary)
+    assert gp is not None and gp.ntt_size() == n
+    npz = gp.num_primes()
+    assert [gp.ntt_modulus(i) for i in range(npz)] == list(oracle.PRIMES52[:npz]) == op.primes
+    g = rng(52 + bits + n + int(binary))
+    batch = 3
+    wdt = np.uint32 if bits == 32 else np.uint64
+    val = rand_words(g, bits, (batch, n))
+    planes = torch.empty((npz, batch, n), dtype=torch.int64, device="cuda")
+    gp.fwd(dev(torch, val), planes)
+    ref = np.stack([op.fwd(v) for v in val], axis=1)
+    assert (host(planes, np.uint64) == ref).all()
+    if binary:
+        bval = make_rhs(g, bits, (batch, n), True)
+        gp.fwd_binary(dev(torch, bval), planes)
+        assert (host(planes, np.uint64) == np.stack([op.fwd(v, binary_copy=True) for v in bval], axis=1)).all()
+    # inv on arbitrary canonical residues: forward-transform random residue vectors so that inv() returns them
+    res = np.stack([g.integers(0, p, size=(batch, n), dtype=np.uint64) for p in op.primes])
+    res[:, 0, :4] = np.array([[0, 1, p // 2, p - 1] for p in op.primes], dtype=np.uint64)
+    fw = np.stack([np.stack([op.plans[k].fwd(res[k, b].copy()) for b in range(batch)]) for k in range(npz)])
+    out = dev(torch, np.zeros((batch, n), wdt))
+    gp.inv(out, dev(torch, fw))
+    want = np.stack([op.inv(np.ascontiguousarray(fw[:, b])) for b in range(batch)])
+    assert (host(out, wdt) == want).all()
+    # polymul: identical to Plan32 (exact product, wrapped), device and host flavours
+    lhs, rhs = rand_words(g, bits, (batch, n)), make_rhs(g, bits, (batch, n), binary)
+    p32 = oracle.Native.try_new(n, bits, binary=binary).negacyclic_polymul(lhs, rhs)
+    dp = torch.empty_like(dev(torch, lhs))
+    gp.negacyclic_polymul(dp, dev(torch, lhs), dev(torch, rhs))
+    assert (host(dp, wdt) == p32).all()
+    hp = np.empty_like(lhs)
+    gp.negacyclic_polymul(hp, lhs, rhs)
+    assert (hp == p32).all()
+    # and the split path composes to the same product: fwd, mul_assign_normalize per prime, inv
+    pl_, pr_ = torch.empty_like(planes), torch.empty_like(planes)
+    gp.fwd(dev(torch, lhs), pl_)
+    (gp.fwd_binary if binary else gp.fwd)(dev(torch, rhs), pr_)
+    for k in range(npz):
+        gp.ntt_i(k).mul_assign_normalize(pl_[k], pr_[k])
+    out2 = torch.empty_like(dp)
+    gp.inv(out2, pl_)
+    assert (host(out2, wdt) == p32).all()

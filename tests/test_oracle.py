@@ -393,3 +393,21 @@ def test_fast_wrapping_schoolbook_equals_reference_test_oracle(oracle):
     a = g.integers(0, 2**64, size=n, dtype=np.uint64)
     b = g.integers(0, 2**64, size=n, dtype=np.uint64)
     assert (oracle.negacyclic_wrapping(64, a, b) == oracle.Native.try_new(n, 64).negacyclic_polymul(a, b)).all()
+
+
+@pytest.mark.parametrize("bits,binary", [(32, False), (64, False), (32, True), (64, True)])
+def test_plan52_restatement_is_a_polymul(oracle, bits, binary):
+    """Native52 (the Plan52 twins, restated from the AVX-512-only reference code): fwd, per-prime
+    mul_assign_normalize, inv == wrapping negacyclic schoolbook -- the reference's own Plan52 tests
+    (src/native64.rs:1217-1243)."""
+    g = np.random.Generator(np.random.PCG64(520 + bits + int(binary)))
+    for n in (32, 128):
+        op = oracle.Native52.try_new(n, bits, binary)
+        dt = np.uint32 if bits == 32 else np.uint64
+        a = g.integers(0, 2**bits, size=n, dtype=np.uint64).astype(dt)
+        b = g.integers(0, 2 if binary else 2**bits, size=n, dtype=np.uint64).astype(dt)
+        A, B = op.fwd(a), op.fwd(b, binary_copy=binary)
+        for k, pl in enumerate(op.plans):
+            pl.mul_assign_normalize(A[k], B[k])
+        ref = (oracle.schoolbook32 if bits == 32 else oracle.schoolbook64)(0, a, b)
+        assert (op.inv(A) == ref).all()
