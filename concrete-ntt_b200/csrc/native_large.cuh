@@ -80,8 +80,11 @@ k_large_lead_fwd(const NativeConsts c, const LargeParams lp, const void* __restr
 
 // ---- rows: fwd x 2, pointwise, inv --------------------------------------------------------------------------
 // one CTA of 256 threads per (row of a polynomial, prime): blockIdx.x = polynomial * C + row, blockIdx.y = prime
+#ifndef CNTT_LARGE_MID_MINBLK
+#define CNTT_LARGE_MID_MINBLK 0 // minimum resident CTAs the row kernel is compiled for (0: unspecified; 3 and 4 measured within 2 %)
+#endif
 template <int LOGC>
-__global__ void __launch_bounds__(Geo<kLargeRowLog, 4>::T)
+__global__ void __launch_bounds__(Geo<kLargeRowLog, 4>::T, CNTT_LARGE_MID_MINBLK)
 k_large_mid(const NativeConsts c, const LargeParams lp, uint32_t* __restrict__ planes_l, const uint32_t* __restrict__ planes_r,
             size_t plane_stride)
 {

@@ -129,13 +129,23 @@ __device__ __forceinline__ void load_contig(const W* __restrict__ src, W (&x)[R]
 #ifndef CNTT_CTA_MINTHREADS64
 #define CNTT_CTA_MINTHREADS64 768
 #endif
-template <class A, int LOGN, int LOGR, int GP>
+// 32-bit kernels (B200, r01, prime32 batch sweep): a 1024-thread cap (<= 64 registers) speeds the inverse up (N=2048
+// 267 -> 276, N=4096 111 -> 122, N=65536 3.6 -> 4.1 M NTT/s) and slows the whole-transform forward down (N=2048 226 -> 213),
+// whose sub-block flavour (the second level of N > 4096) gains from 1280 (3.5 -> 3.7 M NTT/s at N=65536)
+#ifndef CNTT_CTA_MINTHREADS32_INV
+#define CNTT_CTA_MINTHREADS32_INV 1024
+#endif
+#ifndef CNTT_CTA_MINTHREADS32_FWD_SUB
+#define CNTT_CTA_MINTHREADS32_FWD_SUB 1280
+#endif
+template <class A, int LOGN, int LOGR, int GP, bool FWD, bool HEAD>
 constexpr int cta_min_blocks()
 {
-    return (sizeof(typename A::W) == 8 && CNTT_CTA_MINTHREADS64 > GP * Geo<LOGN, LOGR>::T) ? CNTT_CTA_MINTHREADS64 / (GP * Geo<LOGN, LOGR>::T) : 1;
+    constexpr int want = sizeof(typename A::W) == 8 ? CNTT_CTA_MINTHREADS64 : !FWD ? CNTT_CTA_MINTHREADS32_INV : !HEAD ? CNTT_CTA_MINTHREADS32_FWD_SUB : 0;
+    return want > GP * Geo<LOGN, LOGR>::T ? want / (GP * Geo<LOGN, LOGR>::T) : 0; // 0 = unspecified (not the same as 1: ptxas then keeps its default register heuristic)
 }
 template <class A, int LOGN, int LOGR, int GP, bool FWD, bool HEAD, int NP>
-__global__ void __launch_bounds__(GP * Geo<LOGN, LOGR>::T, cta_min_blocks<A, LOGN, LOGR, GP>())
+__global__ void __launch_bounds__(GP * Geo<LOGN, LOGR>::T, cta_min_blocks<A, LOGN, LOGR, GP, FWD, HEAD>())
 k_ntt_cta(const typename A::Tw* __restrict__ tw, const typename A::Tw* __restrict__ tw_last, const typename A::Mod m,
           typename A::W* __restrict__ data, unsigned long long nvpoly, int log_sub, unsigned long long poly_stride,
           const __grid_constant__ TwHead<typename A::Tw> head)
@@ -208,7 +218,7 @@ k_ntt_cta(const typename A::Tw* __restrict__ tw, const typename A::Tw* __restric
 #define CNTT_PIPE64 0
 #endif
 template <class A, int LOGN, int LOGR, int GP, bool FWD, int NP>
-__global__ void __launch_bounds__(GP * Geo<LOGN, LOGR>::T)
+__global__ void __launch_bounds__(GP * Geo<LOGN, LOGR>::T, cta_min_blocks<A, LOGN, LOGR, GP, FWD, true>())
 k_ntt_cta_pipe(const typename A::Tw* __restrict__ tw, const typename A::Tw* __restrict__ tw_last, const typename A::Mod m,
                typename A::W* __restrict__ data, unsigned long long nvpoly, unsigned long long poly_stride,
                const __grid_constant__ TwHead<typename A::Tw> head)

@@ -17,11 +17,14 @@ struct ProductFusedCfg {
     static constexpr int T = E::T;
     static constexpr int GP = T >= 128 ? 1 : 128 / T;
     static constexpr size_t SMEM_BYTES = (size_t)GP * E::NBUF * E::SMEM_WORDS * sizeof(uint32_t);
+    // N = 4096 (256 threads): capped at 64 registers, four CTAs per SM (B200: fwd 0.398 -> 0.359 ms, inv 0.401 -> 0.377 ms
+    // per 16384); smaller sizes lose 1-2 % with a cap and keep ptxas' default (0 = unspecified)
+    static constexpr int MINBLK = LOGN == 12 ? 4 : 0;
 };
 
 // ---- fwd (product.rs:276-353 for count32 == 2, count64 == 0) ---------------------------------------------------------
 template <class A, int LOGN>
-__global__ void __launch_bounds__(ProductFusedCfg<A, LOGN>::GP * ProductFusedCfg<A, LOGN>::T)
+__global__ void __launch_bounds__(ProductFusedCfg<A, LOGN>::GP * ProductFusedCfg<A, LOGN>::T, ProductFusedCfg<A, LOGN>::MINBLK)
 k_product_fwd_fused(const ProductConsts c, const __grid_constant__ ProductFusedDev fp, uint64_t* __restrict__ ntt,
                     const uint64_t* __restrict__ standard, int mode, uint64_t bound, unsigned long long batch)
 {
@@ -76,7 +79,7 @@ k_product_fwd_fused(const ProductConsts c, const __grid_constant__ ProductFusedD
 
 // ---- inv (product.rs:355-880 for count32 == 2, count64 == 0) ---------------------------------------------------------
 template <class A, int LOGN>
-__global__ void __launch_bounds__(ProductFusedCfg<A, LOGN>::GP * ProductFusedCfg<A, LOGN>::T)
+__global__ void __launch_bounds__(ProductFusedCfg<A, LOGN>::GP * ProductFusedCfg<A, LOGN>::T, ProductFusedCfg<A, LOGN>::MINBLK)
 k_product_inv_fused(const ProductConsts c, const __grid_constant__ ProductFusedDev fp, uint64_t* __restrict__ standard,
                     uint64_t* __restrict__ ntt, int mode, unsigned long long batch)
 {
