@@ -123,6 +123,23 @@ __device__ __forceinline__ void load_contig(const W* __restrict__ src, W (&x)[R]
 // carries NP polynomials loads each twiddle once for NP butterflies: the last pass reads R-1 table entries
 // per thread (2x the bytes of the data itself for u32 Shoup pairs), and L1TEX wavefronts -- 73 % of them
 // global loads, mostly twiddles -- were the limiter of the u32 kernels at NP = 1 (ncu r01).
+// Output staging of the forward kernel.  After the last pass a thread owns 16 consecutive words, and the conflict-free
+// thread -> block map interleaves the blocks of neighbouring warps: written straight from registers, one 128-bit store
+// instruction of a warp touches 32 different 128-byte lines (16 bytes each).  With CNTT_STAGE_OUT the words go through a
+// swizzled shared-memory tile (chunk c of 16 bytes at c ^ ((c >> 3) & 7): conflict-free on both sides) and leave as fully
+// coalesced 512-byte warp stores, for one more barrier per polynomial.  B200, prime32 batch sweep: N=256 1892 -> 2322,
+// N=512 897 -> 937, N=1024 439 -> 461 M NTT/s; N=2048 and 4096 lose 3-4 % (the barrier spans 128 / 256 threads), so
+// the staging is used up to N = 1024.
+#ifndef CNTT_STAGE_OUT
+#define CNTT_STAGE_OUT 1
+#endif
+template <class A, int LOGN, int LOGR, int NP, bool FWD>
+__host__ __device__ constexpr bool cta_stages_out()
+{
+    return CNTT_STAGE_OUT != 0 && FWD && NP == 1 && sizeof(typename A::W) == 4 && LOGR == 4 && Geo<LOGN, LOGR>::P >= 2 && LOGN <= 10;
+}
+// (The mirror image for the inverse kernel's strided 128-bit loads -- coalesced loads into a tile, barrier, pick up --
+// measured slower: prime32 N=1024 inverse 572 -> 509 M NTT/s; loads, unlike stores, are already merged by L1.)
 // resident threads per SM the 64-bit kernels are compiled for (register cap 65536 / this; 0: none).  B200, r01:
 // 768 (<= 85 registers) vs uncapped: Solinas N=4096 inverse 1.52 -> 1.27 ms per 32768, N=2048 +1 %, Shoup-64 +3 %;
 // 896 and 1024 lose on the N=2048 inverse.
@@ -235,6 +252,8 @@ k_ntt_cta_pipe(const typename A::Tw* __restrict__ tw, const typename A::Tw* __re
     const int grp = (GP == 1) ? 0 : (int)(threadIdx.x / T);
     const int tid = (GP == 1) ? (int)threadIdx.x : (int)(threadIdx.x % T);
     W* sm = sm_all + (size_t)grp * NP * E::SMEM_WORDS * E::NBUF;
+    constexpr bool kStage = cta_stages_out<A, LOGN, LOGR, NP, FWD>();
+    uint4* stage = reinterpret_cast<uint4*>(sm_all + (size_t)GP * NP * E::SMEM_WORDS * E::NBUF) + (size_t)grp * (E::N / 4); // kStage only
     const typename E::TwSrc tws = {tw, tw_last, &head};
     const unsigned long long ngroups = (unsigned long long)gridDim.x * GP;
     const unsigned long long ngrp_total = (nvpoly + NP - 1) / NP;
@@ -274,7 +293,25 @@ k_ntt_cta_pipe(const typename A::Tw* __restrict__ tw, const typename A::Tw* __re
 #pragma unroll
                 for (int k = 0; k < R; k++) x[np][k] = A::canon_fwd(x[np][k], m);
                 const unsigned long long vp = g * NP + np;
-                if (vp < nvpoly) store_contig<W, R>(data + vp * poly_stride + E::elem_last(tid, 0), x[np]);
+                if constexpr (kStage) {
+                    const int c0 = E::elem_last(tid, 0) / 4; // first of this thread's four 16-byte chunks
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        const int c = c0 + v;
+                        stage[c ^ ((c >> 3) & 7)] = make_uint4((uint32_t)x[np][4 * v], (uint32_t)x[np][4 * v + 1], (uint32_t)x[np][4 * v + 2], (uint32_t)x[np][4 * v + 3]);
+                    }
+                    __syncthreads();
+                    if (vp < nvpoly) {
+                        uint4* out = reinterpret_cast<uint4*>(data + vp * poly_stride);
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
+                            const int c = r * T + tid;
+                            st_data(out + c, stage[c ^ ((c >> 3) & 7)]);
+                        }
+                    }
+                } else {
+                    if (vp < nvpoly) store_contig<W, R>(data + vp * poly_stride + E::elem_last(tid, 0), x[np]);
+                }
             }
         } else {
             E::template inv<NP>(x, sm, tws, 1u, tid, m);
@@ -456,7 +493,8 @@ cudaError_t launch_cta_np(const PlanDev<A>& pl, typename A::W* data, unsigned lo
     typedef typename CtaCfg<A, LOGN>::E E;
     constexpr int T = E::T;
     constexpr int GP = T >= 128 ? 1 : 128 / T;
-    const size_t smem = (size_t)GP * NP * E::NBUF * E::SMEM_WORDS * sizeof(typename A::W);
+    const size_t smem_xchg = (size_t)GP * NP * E::NBUF * E::SMEM_WORDS * sizeof(typename A::W);
+    const size_t smem = smem_xchg;
     const unsigned long long ngrp = (nvpoly + NP - 1) / NP;
     const unsigned long long nblk = (ngrp + GP - 1) / GP;
     if (nblk == 0) return cudaSuccess;
@@ -479,6 +517,7 @@ cudaError_t launch_cta_np(const PlanDev<A>& pl, typename A::W* data, unsigned lo
         // persistent variant: needs whole transforms and at least two polynomials per resident group to pipeline
         if (log_sub == 0 && head != nullptr) {
             auto kern = k_ntt_cta_pipe<A, LOGN, LOGR, GP, FWD, NP>;
+            const size_t smem = smem_xchg + (cta_stages_out<A, LOGN, LOGR, NP, FWD>() ? (size_t)GP * E::N * sizeof(typename A::W) : 0);
             static int resident[64] = {0}; // CTAs the device holds at once, per device ordinal (0: not queried yet)
             int dev = 0;
             cudaError_t e = cudaGetDevice(&dev);
