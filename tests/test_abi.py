@@ -109,3 +109,17 @@ def test_fastdiv_and_prime_helpers(cntt, oracle):
     assert cntt.prime.mul_mod64(D64.new(p), p - 1, p - 1) == 1
     assert cntt.prime.exp_mod32(D32.new(1062862849), 5, 1062862848) == 1
     assert cntt.prime.mul_mod32(1062862849, 1062862848, 2) == 1062862847
+
+
+def test_rust_ffi_declares_the_whole_header():
+    """rust/src/ffi.rs cannot be compiled here (no toolchain); at least keep its extern block in step with the header:
+    same symbol set, same argument counts."""
+    src = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    rust = dict((m.group(1), m.group(2)) for m in re.finditer(r"pub fn (cntt_[a-z0-9_]+)\(([^)]*)\)", src))
+    hdr_src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    hdr = dict((m.group(1), m.group(2)) for m in re.finditer(r"\b(cntt_[a-z0-9_]+)\s*\(([^)]*)\)", hdr_src))
+    assert sorted(rust) == sorted(hdr), sorted(set(rust) ^ set(hdr))
+    for name, args in hdr.items():
+        n_c = 0 if args.strip() in ("", "void") else len(args.split(","))
+        n_r = 0 if not rust[name].strip() else len(rust[name].split(","))
+        assert n_c == n_r, (name, args, rust[name])
