@@ -16,7 +16,11 @@ struct ProductFusedCfg {
     typedef typename CtaCfg<A, LOGN>::E E;
     static constexpr int T = E::T;
     static constexpr int GP = T >= 128 ? 1 : 128 / T;
-    static constexpr size_t SMEM_BYTES = (size_t)GP * E::NBUF * E::SMEM_WORDS * sizeof(uint32_t);
+    // forward output staged through a swizzled tile for coalesced stores, as in k_ntt_cta_pipe (ntt_kernels.cuh): pays
+    // off up to N = 1024
+    static constexpr bool STAGE = CNTT_STAGE_OUT != 0 && LOGN <= 10 && E::P >= 2 && E::R == 16;
+    static constexpr size_t SMEM_XCHG = (size_t)GP * E::NBUF * E::SMEM_WORDS * sizeof(uint32_t);
+    static constexpr size_t SMEM_FWD = SMEM_XCHG + (STAGE ? (size_t)GP * E::N * sizeof(uint32_t) : 0);
     // N = 4096 (256 threads): capped at 64 registers, four CTAs per SM (B200: fwd 0.398 -> 0.359 ms, inv 0.401 -> 0.377 ms
     // per 16384); smaller sizes lose 1-2 % with a cap and keep ptxas' default (0 = unspecified)
     static constexpr int MINBLK = LOGN == 12 ? 4 : 0;
@@ -72,8 +76,27 @@ k_product_fwd_fused(const ProductConsts c, const __grid_constant__ ProductFusedD
         E::template fwd<1>(x, sm, typename E::TwSrc{fp.tw[j], fp.last[j], &fp.head[j]}, 1u, tid, fp.mod[j]);
 #pragma unroll
         for (int k = 0; k < R; k++) x[0][k] = A::canon_fwd(x[0][k], fp.mod[j]);
-        if (active) store_contig<uint32_t, R>(dom32 + (size_t)j * N + E::elem_last(tid, 0), x[0]);
-        if (j == 0 && E::P >= 2) __syncthreads(); // prime 1's first scatter vs prime 0's last gather
+        if constexpr (Cfg::STAGE) {
+            uint4* stage = reinterpret_cast<uint4*>(smem_raw + Cfg::SMEM_XCHG) + (size_t)grp * (N / 4);
+            const int c0 = E::elem_last(tid, 0) / 4;
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const int cc = c0 + v;
+                stage[cc ^ ((cc >> 3) & 7)] = make_uint4(x[0][4 * v], x[0][4 * v + 1], x[0][4 * v + 2], x[0][4 * v + 3]);
+            }
+            __syncthreads(); // also orders prime 1's first scatter after prime 0's last gather
+            if (active) {
+                uint4* out = reinterpret_cast<uint4*>(dom32 + (size_t)j * N);
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const int cc = r * T + tid;
+                    st_data(out + cc, stage[cc ^ ((cc >> 3) & 7)]);
+                }
+            }
+        } else {
+            if (active) store_contig<uint32_t, R>(dom32 + (size_t)j * N + E::elem_last(tid, 0), x[0]);
+            if (j == 0 && E::P >= 2) __syncthreads(); // prime 1's first scatter vs prime 0's last gather
+        }
     }
 }
 
@@ -149,18 +172,18 @@ static cudaError_t launch_one(const ProductConsts& c, const ProductFusedArgs& a,
     if (nblk > 0x7fffffffull) return cudaErrorInvalidValue;
     if constexpr (FWD) {
         auto kern = k_product_fwd_fused<A, LOGN>;
-        if (Cfg::SMEM_BYTES > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+        if (Cfg::SMEM_FWD > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_FWD);
             if (e != cudaSuccess) return e;
         }
-        kern<<<(unsigned)nblk, Cfg::GP * Cfg::T, Cfg::SMEM_BYTES, st>>>(c, d, ntt, standard, mode, bound, batch);
+        kern<<<(unsigned)nblk, Cfg::GP * Cfg::T, Cfg::SMEM_FWD, st>>>(c, d, ntt, standard, mode, bound, batch);
     } else {
         auto kern = k_product_inv_fused<A, LOGN>;
-        if (Cfg::SMEM_BYTES > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+        if (Cfg::SMEM_XCHG > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_XCHG);
             if (e != cudaSuccess) return e;
         }
-        kern<<<(unsigned)nblk, Cfg::GP * Cfg::T, Cfg::SMEM_BYTES, st>>>(c, d, standard, ntt, mode, batch);
+        kern<<<(unsigned)nblk, Cfg::GP * Cfg::T, Cfg::SMEM_XCHG, st>>>(c, d, standard, ntt, mode, batch);
     }
     return cudaGetLastError();
 }
