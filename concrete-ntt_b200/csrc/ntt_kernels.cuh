@@ -9,6 +9,7 @@
 // concatenated).
 #pragma once
 #include "ntt_engine.cuh"
+#include <atomic>
 
 namespace cntt {
 
@@ -518,20 +519,22 @@ cudaError_t launch_cta_np(const PlanDev<A>& pl, typename A::W* data, unsigned lo
         if (log_sub == 0 && head != nullptr) {
             auto kern = k_ntt_cta_pipe<A, LOGN, LOGR, GP, FWD, NP>;
             const size_t smem = smem_xchg + (cta_stages_out<A, LOGN, LOGR, NP, FWD>() ? (size_t)GP * E::N * sizeof(typename A::W) : 0);
-            static int resident[64] = {0}; // CTAs the device holds at once, per device ordinal (0: not queried yet)
+            static std::atomic<int> resident[64]; // CTAs the device holds at once, per device ordinal (0: not queried yet)
             int dev = 0;
             cudaError_t e = cudaGetDevice(&dev);
             if (e != cudaSuccess) return e;
             if (dev < 0 || dev >= 64) dev = 0;
-            if (resident[dev] == 0) {
+            int res = resident[dev].load(std::memory_order_relaxed);
+            if (res == 0) {
                 if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
                 int per_sm = 0, sms = 0;
                 if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GP * T, smem)) != cudaSuccess) return e;
                 if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-                resident[dev] = per_sm * sms > 0 ? per_sm * sms : 1;
+                res = per_sm * sms > 0 ? per_sm * sms : 1;
+                resident[dev].store(res, std::memory_order_relaxed); // racing threads compute the same value
             }
-            if (nblk >= 2ull * (unsigned long long)resident[dev]) {
-                kern<<<(unsigned)resident[dev], GP * T, smem, st>>>(FWD ? pl.tw_fwd : pl.tw_inv, last, pl.mod, data, nvpoly, poly_stride, *head);
+            if (nblk >= 2ull * (unsigned long long)res) {
+                kern<<<(unsigned)res, GP * T, smem, st>>>(FWD ? pl.tw_fwd : pl.tw_inv, last, pl.mod, data, nvpoly, poly_stride, *head);
                 return cudaGetLastError();
             }
         }
