@@ -688,8 +688,8 @@ static int native_plan_new_impl(size_t n, int word_bits, int binary, int device,
         for (int k = 0; k < pl->nprimes && e == cudaSuccess; k++) {
             uint2* f = pl->d_fused_last + (size_t)(2 * k) * n;
             uint2* i = f + n;
-            if ((e = native_fused_build_last(pl->dev.logn, pl->sub[k]->d_fwd, f, nullptr)) != cudaSuccess) break;
-            if ((e = native_fused_build_last(pl->dev.logn, pl->sub[k]->d_inv, i, nullptr)) != cudaSuccess) break;
+            if ((e = native_fused_build_last(kind, pl->dev.logn, pl->sub[k]->d_fwd, f, nullptr)) != cudaSuccess) break;
+            if ((e = native_fused_build_last(kind, pl->dev.logn, pl->sub[k]->d_inv, i, nullptr)) != cudaSuccess) break;
             pl->dev.fused_fwd_last[k] = f;
             pl->dev.fused_inv_last[k] = i;
         }

@@ -77,7 +77,17 @@ cudaError_t native_crt(const NativePlanDev& pl, void* value, const uint32_t* pla
                        cudaStream_t st);
 // fused kernel: is there a variant for this size, and its engine's last-pass table builder (heap -> out, n entries)
 bool native_fused_supported(int logn);
-cudaError_t native_fused_build_last(int logn, const uint2* heap, uint2* out, cudaStream_t st);
+cudaError_t native_fused_build_last(int kind, int logn, const uint2* heap, uint2* out, cudaStream_t st);
+// Words per thread (log2) of the engine behind the fused polymul and the fused split forward kernel, and therefore of
+// the plan's last-pass twiddle layout.  B200, batch 65536: 16 words per thread beat 8 for the 32/64-bit kinds from
+// N = 2048 on (native64 13.9 -> 14.9, native32 25.9 -> 27.3, binary64 24.8 -> 26.2 M polymul/s; N = 1024 -1 %), and lose
+// for 128-bit words (native128 N = 4096 2.47 -> 2.35).
+constexpr int native_fused_logr(int kind, int logn)
+{
+    const bool wide = kind == NK_NATIVE128 || kind == NK_BINARY128;
+    const int r = (!wide && logn >= 11) ? 4 : 3;
+    return logn < r ? logn : r;
+}
 // fused single-kernel polymul; returns cudaErrorNotSupported when no fused variant exists for (kind, logn)
 cudaError_t native_polymul_fused(const NativePlanDev& pl, void* prod, const void* lhs, const void* rhs, size_t batch,
                                  cudaStream_t st);

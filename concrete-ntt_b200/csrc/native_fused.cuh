@@ -11,9 +11,6 @@
 
 namespace cntt {
 
-#ifndef CNTT_FUSED_LOGR
-#define CNTT_FUSED_LOGR 3
-#endif
 // Per-kind configuration (bit k = NativeKind k; tools/build_variant.sh overrides these for A/B runs):
 //   RELOAD: the operands are re-read from global memory (L2 hits after the first prime) for every prime instead of
 //           living in registers across the prime loop (128-bit words: 64 registers per thread)
@@ -183,7 +180,7 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
 template <int KIND, int LOGN>
 static cudaError_t launch_fused_one(const NativePlanDev& pl, void* prod, const void* lhs, const void* rhs, size_t batch, cudaStream_t st)
 {
-    constexpr int LOGR = LOGN < CNTT_FUSED_LOGR ? LOGN : CNTT_FUSED_LOGR;
+    constexpr int LOGR = native_fused_logr(KIND, LOGN);
     typedef FusedCfg<KIND, LOGN, LOGR> Cfg;
     FusedParams fp;
     for (int k = 0; k < Cfg::NP; k++) {
@@ -223,11 +220,10 @@ static cudaError_t launch_fused_kind(const NativePlanDev& pl, void* prod, const 
     }
 }
 
-template <int LOGN>
+template <int KIND, int LOGN>
 static cudaError_t fused_build_last_one(const uint2* heap, uint2* out, cudaStream_t st)
 {
-    constexpr int LOGR = LOGN < CNTT_FUSED_LOGR ? LOGN : CNTT_FUSED_LOGR;
-    return launch_build_last_e<Engine<A32L4, LOGN, LOGR>>(heap, out, 0, st);
+    return launch_build_last_e<Engine<A32L4, LOGN, native_fused_logr(KIND, LOGN)>>(heap, out, 0, st);
 }
 
 } // namespace cntt

@@ -196,19 +196,26 @@ cudaError_t native_crt(const NativePlanDev& pl, void* value, const uint32_t* pla
 
 namespace cntt {
 bool native_fused_supported(int logn) { return logn >= kFusedMinLogN && logn <= kFusedMaxLogN; }
-cudaError_t native_fused_build_last(int logn, const uint2* heap, uint2* out, cudaStream_t st)
+template <int KIND>
+static cudaError_t fused_build_last_kind(int logn, const uint2* heap, uint2* out, cudaStream_t st)
 {
     switch (logn) {
-    case 5: return fused_build_last_one<5>(heap, out, st);
-    case 6: return fused_build_last_one<6>(heap, out, st);
-    case 7: return fused_build_last_one<7>(heap, out, st);
-    case 8: return fused_build_last_one<8>(heap, out, st);
-    case 9: return fused_build_last_one<9>(heap, out, st);
-    case 10: return fused_build_last_one<10>(heap, out, st);
-    case 11: return fused_build_last_one<11>(heap, out, st);
-    case 12: return fused_build_last_one<12>(heap, out, st);
+    case 5: return fused_build_last_one<KIND, 5>(heap, out, st);
+    case 6: return fused_build_last_one<KIND, 6>(heap, out, st);
+    case 7: return fused_build_last_one<KIND, 7>(heap, out, st);
+    case 8: return fused_build_last_one<KIND, 8>(heap, out, st);
+    case 9: return fused_build_last_one<KIND, 9>(heap, out, st);
+    case 10: return fused_build_last_one<KIND, 10>(heap, out, st);
+    case 11: return fused_build_last_one<KIND, 11>(heap, out, st);
+    case 12: return fused_build_last_one<KIND, 12>(heap, out, st);
     default: return cudaErrorNotSupported;
     }
+}
+cudaError_t native_fused_build_last(int kind, int logn, const uint2* heap, uint2* out, cudaStream_t st)
+{
+    // the layout depends on the kind only through native_fused_logr: one 64-bit and one 128-bit representative
+    const bool wide = kind == NK_NATIVE128 || kind == NK_BINARY128;
+    return wide ? fused_build_last_kind<NK_NATIVE128>(logn, heap, out, st) : fused_build_last_kind<NK_NATIVE64>(logn, heap, out, st);
 }
 cudaError_t native_polymul_fused(const NativePlanDev& pl, void* prod, const void* lhs, const void* rhs, size_t batch,
                                  cudaStream_t st)

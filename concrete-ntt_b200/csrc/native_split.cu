@@ -14,7 +14,7 @@
 namespace cntt {
 
 constexpr int kSplitMinLogN = 8, kSplitMaxLogN = 12;
-constexpr int kSplitLogR = 3; // the fused polymul's engine: its last-pass tables exist in every native plan
+// the engine is the fused polymul's (native_fused_logr): its last-pass twiddle layout exists in every native plan
 
 struct SplitParams {
     const uint2* tw[10];
@@ -24,7 +24,7 @@ struct SplitParams {
 
 template <int KIND, int LOGN>
 struct SplitCfg {
-    typedef Engine<A32L4, LOGN, kSplitLogR> E;
+    typedef Engine<A32L4, LOGN, native_fused_logr(KIND, LOGN)> E;
     static constexpr int NP = dev::KindInfo<KIND>::NP;
     static constexpr int T = E::T;
     static constexpr size_t SMEM_BYTES = (size_t)E::NBUF * E::SMEM_WORDS * sizeof(uint32_t);
