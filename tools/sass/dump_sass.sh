@@ -16,11 +16,11 @@ dump ntt64s_n2048_inv  'k_ntt_ctaINS_4A64SELi11ELi4ELi1ELb0ELb1ELi1'
 dump ntt64l4_n2048_fwd 'k_ntt_ctaINS_5A64L4ELi11ELi4ELi1ELb1ELb1ELi1'
 dump strided32_k4_fwd  'k_ntt_stridedINS_5A32L4ELi4ELb1'
 dump pointwise32_mul_assign_normalize 'k_pointwiseINS_5A32L4ELi0'
-dump polymul_native64_n2048 'k_polymul_fusedILi1ELi11ELi3'
+dump polymul_native64_n2048 'k_polymul_fusedILi1ELi11ELi4'
 dump polymul_native128_n4096 'k_polymul_fusedILi2ELi12ELi3'
 dump large_binary64_lead_fwd_c16 'k_large_lead_fwdILi4ELi4E'
 dump large_mid_c16 'k_large_midILi4E'
 dump large_binary64_lead_inv_c16 'k_large_lead_invILi4ELi4E'
 python tools/sass/pipecount.py $LIB 'k_ntt_ctaINS_5A32L4ELi10ELi4ELi2' > $OUT/pipecount.txt
 python tools/sass/pipecount.py $LIB 'k_ntt_ctaINS_4A64SELi11ELi4ELi1' >> $OUT/pipecount.txt
-python tools/sass/pipecount.py $LIB 'k_polymul_fusedILi1ELi11ELi3' >> $OUT/pipecount.txt
+python tools/sass/pipecount.py $LIB 'k_polymul_fusedILi1ELi11ELi4' >> $OUT/pipecount.txt
