@@ -219,3 +219,44 @@ def test_prime32_persistent_forward_kernel(cntt, oracle, torch_cuda, n, batch):
     gp.inv(d)
     gp.normalize(d)
     assert (host(d, np.uint32) == a).all()
+
+
+def test_concurrent_streams_share_a_plan(cntt, oracle, torch_cuda):
+    """Plans are immutable after creation (the reference's are Send + Sync): four host threads, each on its own CUDA
+    stream and buffer, drive the same prime32 / prime64 / native64 plans concurrently."""
+    import threading
+    torch = torch_cuda
+    n, p32, p64 = 1024, 1062862849, 0xFFFFFFFF00000001
+    g32, o32 = cntt.prime32.Plan.try_new(n, p32), oracle.Plan32.try_new(n, p32)
+    g64, o64 = cntt.prime64.Plan.try_new(n, p64), oracle.Plan64.try_new(n, p64)
+    gn, on = cntt.native64.Plan32.try_new(n), oracle.Native.try_new(n, 64)
+    errors = []
+
+    def worker(seed):
+        try:
+            g = rng(1000 + seed)
+            s = torch.cuda.Stream()
+            a32 = rand_mod(g, p32, (7, n), np.uint32)
+            a64 = rand_mod(g, p64, (5, n), np.uint64)
+            l, r = g.integers(0, 2**64, size=(3, n), dtype=np.uint64), g.integers(0, 2**64, size=(3, n), dtype=np.uint64)
+            with torch.cuda.stream(s):
+                for _ in range(20):
+                    d32, d64 = dev(torch, a32), dev(torch, a64)
+                    dl, dr = dev(torch, l), dev(torch, r)
+                    dp = torch.empty_like(dl)
+                    g32.fwd(d32)
+                    g64.fwd(d64)
+                    gn.negacyclic_polymul(dp, dl, dr)
+                    s.synchronize()
+                    assert (host(d32, np.uint32) == np.stack([o32.fwd(x.copy()) for x in a32])).all()
+                    assert (host(d64, np.uint64) == np.stack([o64.fwd(x.copy()) for x in a64])).all()
+                    assert (host(dp, np.uint64) == on.negacyclic_polymul(l, r)).all()
+        except Exception as e:  # surfaced in the main thread
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
