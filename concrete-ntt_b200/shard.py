@@ -37,3 +37,39 @@ def gather(local, batch, group=None):
     dist.all_gather_into_tensor(out, pad, group=group)
     parts = [out[r * mx: r * mx + (hi - lo)] for r, (lo, hi) in enumerate(sizes)]
     return torch.cat(parts, dim=0)
+
+
+class PeerGather:
+    """Single-device output without a collective after the kernel: the result rows of every rank are written by the
+    kernels THEMSELVES into the root rank's HBM over NVLink peer memory.
+
+    Every rank allocates the same symmetric (batch, n) buffer (torch symmetric memory: CUDA VMM allocations whose
+    handles are exchanged once at construction); `dest()` is this rank's shard [lo, hi) of the ROOT's buffer, mapped
+    into this process -- a plain device pointer, so it can be handed to any out-of-place entry point of the C ABI
+    (`negacyclic_polymul(prod=gather.dest(), ...)`, `cntt_native_polymul`) or be the target of a device copy.  The
+    stores of the kernel then travel through NVSwitch while its butterflies run; `wait()` is a stream-ordered
+    barrier over the group after which `result()` on the root holds the whole batch.  (the
+    gather is optional and never part of a timed NTT step; `gather()` above is the NCCL form of the same thing.)
+    """
+
+    def __init__(self, batch, n, dtype, root=0, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = dist.group.WORLD if group is None else group
+        self.world, self.rank, self.root = dist.get_world_size(self.group), dist.get_rank(self.group), root
+        self.batch, self.n, self.dtype = batch, n, dtype
+        self.local = symm.empty((batch, n), dtype=dtype, device=torch.device("cuda", torch.cuda.current_device()))
+        self.hdl = symm.rendezvous(self.local, self.group)
+        self.lo, self.hi = shard_range(batch, self.world, self.rank)
+        self._dest = self.hdl.get_buffer(root, (self.hi - self.lo, n), dtype, self.lo * n)
+
+    def dest(self):
+        """Rows [lo, hi) of the root's buffer (peer memory unless this rank is the root)."""
+        return self._dest
+
+    def wait(self):
+        """Barrier on the current stream: returns once every rank's preceding work on its stream is visible."""
+        self.hdl.barrier()
+
+    def result(self):
+        """The (batch, n) buffer of this rank; complete on the root after wait()."""
+        return self.local
