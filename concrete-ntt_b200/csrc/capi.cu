@@ -680,7 +680,9 @@ static int native_plan_new_impl(size_t n, int word_bits, int binary, int device,
     pl->dev.nprimes = pl->nprimes;
     pl->dev.prime_set = prime_set;
     for (int k = 0; k < pl->nprimes; k++) pl->dev.sub[k] = dev32<A32L4>(pl->sub[k]);
-    native_lhs_scale(pl->dev.logn, pl->dev.lscale, prime_set, pl->nprimes);
+    // the fused polymul (N <= 4096) may carry the product on fewer primes than the plan owns (native.hpp, native_fused_np)
+    native_lhs_scale(pl->dev.logn, pl->dev.lscale, prime_set,
+                     native_fused_supported(pl->dev.logn) ? native_fused_np(kind, pl->nprimes) : pl->nprimes);
     for (int k = 0; k < 10; k++) pl->dev.fused_fwd_last[k] = pl->dev.fused_inv_last[k] = nullptr;
     if (native_fused_supported(pl->dev.logn)) {
         DeviceGuard g(device);

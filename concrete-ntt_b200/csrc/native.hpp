@@ -24,13 +24,13 @@ struct NativeConsts {
     uint32_t half_single[10]; // floor(P[k] / 2): sign threshold when the top digit decides (np = 2, 3)
     uint32_t half_pair_lo[10], half_pair_hi[10]; // floor(P[k-1] P[k] / 2) = lo + hi * P[k-1] (np = 5, 10)
     // Quotient-estimate CRT of the fused polymul kernels (native_device.cuh, reconstruct_bounded), per prime
-    // count class cls = 0..3 for np = 2, 3, 5, 10 with M = P_0 ... P_{np-1}:
-    uint64_t am[4][10][2];  // (M / P[k]) mod 2^128 as {lo, hi}
-    uint64_t aM[4][2];      // M mod 2^128
-    uint32_t acinv[4][10];  // ((M / P[k]) mod P[k])^-1 mod P[k]: folded into the lhs scale constants
+    // count class cls = 0..4 for np = 2, 3, 5, 10, 9 with M = P_0 ... P_{np-1}:
+    uint64_t am[5][10][2];  // (M / P[k]) mod 2^128 as {lo, hi}
+    uint64_t aM[5][2];      // M mod 2^128
+    uint32_t acinv[5][10];  // ((M / P[k]) mod P[k])^-1 mod P[k]: folded into the lhs scale constants
     float ainv[10];         // 1 / P[k]
 };
-inline int native_np_class(int np) { return np == 2 ? 0 : np == 3 ? 1 : np == 5 ? 2 : 3; }
+__host__ __device__ constexpr int native_np_class(int np) { return np == 2 ? 0 : np == 3 ? 1 : np == 5 ? 2 : np == 9 ? 4 : 3; }
 
 // Prime sets.  Set 0 = the reference's P0..P9.  Set 1 = the "extended" set: the nine primes k 2^17 + 1 in
 // (2^30 - 2^24, 2^30), ascending -- six of them are the reference's P0, P2, P3, P4, P8, P9 -- which admit
@@ -52,6 +52,12 @@ enum NativeKind {            // word_bits / binary            reference reconstr
     NK_BINARY128 = 5,        // 128 / 1  5 primes              native_binary128.rs:12-64
 };
 inline int native_num_primes(int kind) { static const int np[6] = {3, 5, 10, 2, 3, 5}; return np[kind]; }
+// Primes the FUSED polymul (N <= 4096) carries the product on.  A product coefficient is the exact integer
+// sum_i +-a_i b_j, |x| < n 2^(2w), and only x mod 2^w is returned, so any prime set with prod P_k > 2 |x| gives the
+// reference's result.  native128 at n <= 4096: |x| < 2^268 and P_0 ... P_8 = 2^269.92, so nine primes carry it
+// (|x / M| < 0.27, far inside the rounding margin of reconstruct_bounded) and the tenth prime's three transforms,
+// two reductions and CRT term are not computed.  The split fwd / inv API and N > 4096 keep the reference's ten.
+constexpr int native_fused_np(int kind, int np_ref) { return kind == 2 /* NK_NATIVE128 */ ? 9 : np_ref; }
 inline int native_word_bytes(int kind) { static const int wb[6] = {4, 8, 16, 4, 8, 16}; return wb[kind]; }
 
 struct NativePlanDev {

@@ -129,12 +129,11 @@ __device__ __forceinline__ typename KindInfo<KIND>::Word reconstruct(const uint3
 // word -- the value the reference's reconstruct_* returns (src/native64.rs:90-141 etc.) whenever the bound holds,
 // i.e. for every negacyclic_polymul input.  (Plan32::inv on caller-supplied residues keeps the exact Garner
 // chain above: there the bound is the caller's business and the reference's sign rule must be reproduced.)
-template <int KIND>
+template <int KIND, int NP = KindInfo<KIND>::NP>
 __device__ __forceinline__ typename KindInfo<KIND>::Word reconstruct_bounded(const uint32_t* y, const NativeConsts& c)
 {
     typedef typename KindInfo<KIND>::Word Word;
-    constexpr int NP = KindInfo<KIND>::NP;
-    constexpr int CLS = NP == 2 ? 0 : NP == 3 ? 1 : NP == 5 ? 2 : 3;
+    constexpr int CLS = native_np_class(NP);
     float f = 0.0f;
 #pragma unroll
     for (int k = 0; k < NP; k++) f = fmaf(__uint2float_rn(y[k]), c.ainv[k], f);

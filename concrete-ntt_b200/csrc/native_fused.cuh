@@ -40,7 +40,7 @@ struct FusedParams {
 template <int KIND, int LOGN, int LOGR>
 struct FusedCfg {
     typedef Engine<A32L4, LOGN, LOGR> E;
-    static constexpr int NP = dev::KindInfo<KIND>::NP;
+    static constexpr int NP = native_fused_np(KIND, dev::KindInfo<KIND>::NP); // native128: nine of the ten primes (native.hpp)
     static constexpr int T = E::T;
     static constexpr int GP = T >= 128 ? 1 : 128 / T;
     static constexpr int XCHG_WORDS = 2 * E::NBUF * E::SMEM_WORDS;   // two polynomials in flight (lhs, rhs)
@@ -88,7 +88,7 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
 
     // operands: read once and kept in registers for all primes, or (RELOAD) re-read per prime
     constexpr bool RELOAD = Cfg::RELOAD, ACC = Cfg::ACC;
-    constexpr int CLS = NP == 2 ? 0 : NP == 3 ? 1 : NP == 5 ? 2 : 3;
+    constexpr int CLS = native_np_class(NP);
     constexpr int RK = RELOAD ? 1 : R;
     uint64_t llo[RK], rlo[RK];
     uint64_t lhi[(WB == 16 && !RELOAD) ? R : 1], rhi[(WB == 16 && !RELOAD) ? R : 1];
@@ -171,7 +171,7 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
                 uint32_t r[NP];
 #pragma unroll
                 for (int pk = 0; pk < NP; pk++) r[pk] = stash[pk * N + tid + k * T];
-                dev::store_word<KIND>(prod, base + tid + k * T, dev::reconstruct_bounded<KIND>(r, c));
+                dev::store_word<KIND>(prod, base + tid + k * T, dev::reconstruct_bounded<KIND, NP>(r, c));
             }
         }
     }

@@ -46,8 +46,8 @@ static void fill_consts_set(int set)
             c.half_pair_lo[k] = c.half_pair_hi[k] = 0;
         }
     }
-    static const int kNp[4] = {2, 3, 5, 10};
-    for (int cls = 0; cls < 4; cls++) {
+    static const int kNp[5] = {2, 3, 5, 10, 9};
+    for (int cls = 0; cls < 5; cls++) {
         const int np = kNp[cls];
         u128 M = 1; // wrapping mod 2^128 is all the kernels need
         for (int j = 0; j < np; j++) M *= (u128)P[j];
