@@ -13,7 +13,26 @@
 
 namespace cntt {
 
-constexpr int kMaxCtaLogN = 12; // largest transform a single CTA keeps on chip
+constexpr int kMaxCtaLogN = 12; // largest block a CTA keeps on chip when a transform is cut into blocks
+// 32-bit words: N = 8192 still fits one CTA (512 threads x 16 words, 66 KB of exchange buffers), which saves the
+// strided pass through HBM that the block scheme would spend on its single leading level.
+#ifndef CNTT_CTA13
+#define CNTT_CTA13 1
+#endif
+#ifndef CNTT_CTA13_64
+#define CNTT_CTA13_64 0 // the same for 64-bit words: measured on B200 (Solinas, batch 16384) fwd 1.74 -> 1.58 ms with a 64-register
+                        // cap but inv 1.61 -> 1.83 ms (1.84 / 2.02 ms uncapped), so 64-bit words keep the block scheme
+#endif
+#ifndef CNTT_CTA13_64_MINTHREADS
+#define CNTT_CTA13_64_MINTHREADS 0 // 0: the 64-bit default below
+#endif
+// size of the contiguous blocks the CTA kernel transforms for a plan of 2^logn words
+template <class A> constexpr int cta_block_logn(int logn)
+{
+    if (logn <= kMaxCtaLogN) return logn;
+    if (logn == 13 && (sizeof(typename A::W) == 4 ? CNTT_CTA13 : CNTT_CTA13_64)) return 13;
+    return kMaxCtaLogN;
+}
 constexpr int kMaxLogN = 26;    // two-level + repeated strided passes; table memory is the limit
 
 template <class A>
@@ -159,7 +178,7 @@ __host__ __device__ constexpr bool cta_stages_out()
 template <class A, int LOGN, int LOGR, int GP, bool FWD, bool HEAD>
 constexpr int cta_min_blocks()
 {
-    constexpr int want = sizeof(typename A::W) == 8 ? CNTT_CTA_MINTHREADS64 : !FWD ? CNTT_CTA_MINTHREADS32_INV : !HEAD ? CNTT_CTA_MINTHREADS32_FWD_SUB : 0;
+    constexpr int want = sizeof(typename A::W) == 8 ? ((LOGN == 13 && CNTT_CTA13_64_MINTHREADS) ? CNTT_CTA13_64_MINTHREADS : CNTT_CTA_MINTHREADS64) : !FWD ? CNTT_CTA_MINTHREADS32_INV : !HEAD ? CNTT_CTA_MINTHREADS32_FWD_SUB : 0;
     return want > GP * Geo<LOGN, LOGR>::T ? want / (GP * Geo<LOGN, LOGR>::T) : 0; // 0 = unspecified (not the same as 1: ptxas then keeps its default register heuristic)
 }
 template <class A, int LOGN, int LOGR, int GP, bool FWD, bool HEAD, int NP>
@@ -361,7 +380,8 @@ template <class A, int LOGN> constexpr bool cta_uses_last() { return CtaCfg<A, L
 template <class A>
 bool plan_uses_last(int logn)
 {
-    const int l = logn < kMaxCtaLogN ? logn : kMaxCtaLogN;
+    const int l = cta_block_logn<A>(logn);
+    if (l == 13) return cta_uses_last<A, 13>();
     switch (l) {
     case 4: return cta_uses_last<A, 4>();
     case 5: return cta_uses_last<A, 5>();
@@ -379,8 +399,9 @@ bool plan_uses_last(int logn)
 template <class A>
 cudaError_t launch_build_last(int logn, const typename A::Tw* heap, typename A::Tw* out, cudaStream_t st)
 {
-    const int l = logn < kMaxCtaLogN ? logn : kMaxCtaLogN;
+    const int l = cta_block_logn<A>(logn);
     const int log_sub = logn - l;
+    if (l == 13) return launch_build_last_e<typename CtaCfg<A, 13>::E>(heap, out, log_sub, st);
     switch (l) {
     case 4: return launch_build_last_e<typename CtaCfg<A, 4>::E>(heap, out, log_sub, st);
     case 5: return launch_build_last_e<typename CtaCfg<A, 5>::E>(heap, out, log_sub, st);
@@ -560,6 +581,7 @@ cudaError_t launch_cta_one(const PlanDev<A>& pl, typename A::W* data, unsigned l
 template <class A, bool FWD>
 cudaError_t launch_cta(const PlanDev<A>& pl, int logn_sub, typename A::W* data, unsigned long long nvpoly, int log_sub, size_t poly_stride, cudaStream_t st)
 {
+    if (logn_sub == 13) return launch_cta_one<A, 13, FWD>(pl, data, nvpoly, log_sub, poly_stride, st);
     switch (logn_sub) {
     case 4: return launch_cta_one<A, 4, FWD>(pl, data, nvpoly, log_sub, poly_stride, st);
     case 5: return launch_cta_one<A, 5, FWD>(pl, data, nvpoly, log_sub, poly_stride, st);
@@ -605,8 +627,9 @@ cudaError_t launch_ntt(const PlanDev<A>& pl, typename A::W* data, size_t batch, 
 {
     if (batch == 0) return cudaSuccess;
     if (poly_stride == 0) poly_stride = (size_t)1 << pl.logn;
-    if (pl.logn <= kMaxCtaLogN) return launch_cta<A, FWD>(pl, pl.logn, data, batch, 0, poly_stride, st);
-    const int lead = pl.logn - kMaxCtaLogN;
+    const int blk = cta_block_logn<A>(pl.logn);
+    if (pl.logn == blk) return launch_cta<A, FWD>(pl, pl.logn, data, batch, 0, poly_stride, st);
+    const int lead = pl.logn - blk;
     cudaError_t e;
     if constexpr (FWD) {
         int s0 = 0;
@@ -615,9 +638,9 @@ cudaError_t launch_ntt(const PlanDev<A>& pl, typename A::W* data, size_t batch, 
             if ((e = launch_strided<A, true>(pl, k, data, batch, s0, poly_stride, st)) != cudaSuccess) return e;
             s0 += k;
         }
-        return launch_cta<A, true>(pl, kMaxCtaLogN, data, (unsigned long long)batch << lead, lead, poly_stride, st);
+        return launch_cta<A, true>(pl, blk, data, (unsigned long long)batch << lead, lead, poly_stride, st);
     } else {
-        if ((e = launch_cta<A, false>(pl, kMaxCtaLogN, data, (unsigned long long)batch << lead, lead, poly_stride, st)) != cudaSuccess) return e;
+        if ((e = launch_cta<A, false>(pl, blk, data, (unsigned long long)batch << lead, lead, poly_stride, st)) != cudaSuccess) return e;
         // mirror of the forward schedule: last forward chunk first
         int chunks[8], nc = 0, s = 0;
         while (s < lead) { const int k = (lead - s) < 4 ? (lead - s) : 4; chunks[nc++] = k; s += k; }

@@ -200,7 +200,7 @@ def test_full_size_properties(cntt, torch_cuda):
     assert (host(d, np.uint64) == a).all()
 
 
-@pytest.mark.parametrize("n,batch", [(256, 40003), (1024, 20001), (2048, 9999), (4096, 5003)])
+@pytest.mark.parametrize("n,batch", [(256, 40003), (1024, 20001), (2048, 9999), (4096, 5003), (8192, 2501)])
 def test_prime32_persistent_forward_kernel(cntt, oracle, torch_cuda, n, batch):
     """Large ragged batches take the persistent software-pipelined forward kernel (k_ntt_cta_pipe: grid = resident
     CTAs, every group strides over the batch, tail groups clamp): oracle on sampled polynomials incl. the first and
