@@ -424,6 +424,45 @@ def run_ours(args):
     except Exception as e:
         extra["prime32_error"] = repr(e)
 
+    # ---- BASELINE configs[3] and configs[4], device-resident: native128 N=4096 batch 8192 per GPU, and native_binary64
+    #      N=65536 (extended plan) with the batch of 1024 split over the ranks
+    def time_polymul(plan, shape, binary, reps=5):
+        g = torch.Generator(device="cuda").manual_seed(4321 + rank)
+        a = torch.randint(-2**63, 2**63 - 1, shape, dtype=torch.int64, device="cuda", generator=g)
+        b = torch.randint(-2**63, 2**63 - 1, shape, dtype=torch.int64, device="cuda", generator=g)
+        if binary:
+            b &= 1
+        out = torch.empty_like(a)
+        for _ in range(2):
+            plan.negacyclic_polymul(out, a, b)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            plan.negacyclic_polymul(out, a, b)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1) / reps
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+    try:
+        ms = time_polymul(cntt.native128.Plan32.try_new(4096, device=local), (8192, 4096, 2), False)
+        extra["native128_polymul_n4096_b8192"] = {"polymuls_per_s": world * 8192 / (ms * 1e-3), "ms_per_batch": ms,
+                                                  "hbm_frac": (3 * 4096 * 16 * 8192 / (ms * 1e-3) / 1e9) / peaks()[0]}
+    except Exception as e:
+        extra["native128_polymul_error"] = repr(e)
+    try:
+        per = max(1, 1024 // world)
+        ms = time_polymul(cntt.native_binary64.Plan32.try_new_extended(65536, device=local), (per, 65536), True)
+        extra["native_binary64_polymul_n65536_b1024_total"] = {"polymuls_per_s": world * per / (ms * 1e-3), "ms_per_batch": ms,
+                                                               "batch_per_gpu": per, "scaling": "strong",
+                                                               "hbm_frac_per_gpu": (3 * 65536 * 8 * per / (ms * 1e-3) / 1e9) / peaks()[0]}
+    except Exception as e:
+        extra["native_binary64_polymul_error"] = repr(e)
+
     if rank == 0:
         peak, peak_src = peaks()
         slow_ms, which = (fwd_ms, "fwd") if fwd_ms >= inv_ms else (inv_ms, "inv")

@@ -19,6 +19,9 @@ constexpr int kMaxCtaLogN = 12; // largest block a CTA keeps on chip when a tran
 #ifndef CNTT_CTA13
 #define CNTT_CTA13 1
 #endif
+#ifndef CNTT_CTA14
+#define CNTT_CTA14 0 // experiment: N = 16384 (32-bit words) in one CTA of 1024 threads
+#endif
 #ifndef CNTT_CTA13_64
 #define CNTT_CTA13_64 0 // the same for 64-bit words: measured on B200 (Solinas, batch 16384) fwd 1.74 -> 1.58 ms with a 64-register
                         // cap but inv 1.61 -> 1.83 ms (1.84 / 2.02 ms uncapped), so 64-bit words keep the block scheme
@@ -31,6 +34,9 @@ template <class A> constexpr int cta_block_logn(int logn)
 {
     if (logn <= kMaxCtaLogN) return logn;
     if (logn == 13 && (sizeof(typename A::W) == 4 ? CNTT_CTA13 : CNTT_CTA13_64)) return 13;
+#if CNTT_CTA14
+    if (logn == 14 && sizeof(typename A::W) == 4) return 14;
+#endif
     return kMaxCtaLogN;
 }
 constexpr int kMaxLogN = 26;    // two-level + repeated strided passes; table memory is the limit
@@ -382,6 +388,9 @@ bool plan_uses_last(int logn)
 {
     const int l = cta_block_logn<A>(logn);
     if (l == 13) return cta_uses_last<A, 13>();
+#if CNTT_CTA14
+    if constexpr (sizeof(typename A::W) == 4) { if (l == 14) return cta_uses_last<A, 14>(); }
+#endif
     switch (l) {
     case 4: return cta_uses_last<A, 4>();
     case 5: return cta_uses_last<A, 5>();
@@ -402,6 +411,9 @@ cudaError_t launch_build_last(int logn, const typename A::Tw* heap, typename A::
     const int l = cta_block_logn<A>(logn);
     const int log_sub = logn - l;
     if (l == 13) return launch_build_last_e<typename CtaCfg<A, 13>::E>(heap, out, log_sub, st);
+#if CNTT_CTA14
+    if constexpr (sizeof(typename A::W) == 4) { if (l == 14) return launch_build_last_e<typename CtaCfg<A, 14>::E>(heap, out, log_sub, st); }
+#endif
     switch (l) {
     case 4: return launch_build_last_e<typename CtaCfg<A, 4>::E>(heap, out, log_sub, st);
     case 5: return launch_build_last_e<typename CtaCfg<A, 5>::E>(heap, out, log_sub, st);
@@ -582,6 +594,9 @@ template <class A, bool FWD>
 cudaError_t launch_cta(const PlanDev<A>& pl, int logn_sub, typename A::W* data, unsigned long long nvpoly, int log_sub, size_t poly_stride, cudaStream_t st)
 {
     if (logn_sub == 13) return launch_cta_one<A, 13, FWD>(pl, data, nvpoly, log_sub, poly_stride, st);
+#if CNTT_CTA14
+    if constexpr (sizeof(typename A::W) == 4) { if (logn_sub == 14) return launch_cta_one<A, 14, FWD>(pl, data, nvpoly, log_sub, poly_stride, st); }
+#endif
     switch (logn_sub) {
     case 4: return launch_cta_one<A, 4, FWD>(pl, data, nvpoly, log_sub, poly_stride, st);
     case 5: return launch_cta_one<A, 5, FWD>(pl, data, nvpoly, log_sub, poly_stride, st);
