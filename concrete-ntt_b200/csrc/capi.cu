@@ -684,14 +684,17 @@ static int native_plan_new_impl(size_t n, int word_bits, int binary, int device,
     native_lhs_scale(pl->dev.logn, pl->dev.lscale, prime_set,
                      native_fused_supported(pl->dev.logn) ? native_fused_np(kind, pl->nprimes) : pl->nprimes);
     for (int k = 0; k < 10; k++) pl->dev.fused_fwd_last[k] = pl->dev.fused_inv_last[k] = nullptr;
-    if (native_fused_supported(pl->dev.logn)) {
+    const bool fused = native_fused_supported(pl->dev.logn), large = native_large_supported(pl->dev.logn);
+    if (fused || large) {
         DeviceGuard g(device);
         cudaError_t e = g.ok ? cudaMalloc(&pl->d_fused_last, 2 * (size_t)pl->nprimes * n * sizeof(uint2)) : cudaErrorInvalidDevice;
         for (int k = 0; k < pl->nprimes && e == cudaSuccess; k++) {
             uint2* f = pl->d_fused_last + (size_t)(2 * k) * n;
             uint2* i = f + n;
-            if ((e = native_fused_build_last(kind, pl->dev.logn, pl->sub[k]->d_fwd, f, nullptr)) != cudaSuccess) break;
-            if ((e = native_fused_build_last(kind, pl->dev.logn, pl->sub[k]->d_inv, i, nullptr)) != cudaSuccess) break;
+            if ((e = fused ? native_fused_build_last(kind, pl->dev.logn, pl->sub[k]->d_fwd, f, nullptr)
+                           : native_large_build_last(pl->dev.logn, pl->sub[k]->d_fwd, f, nullptr)) != cudaSuccess) break;
+            if ((e = fused ? native_fused_build_last(kind, pl->dev.logn, pl->sub[k]->d_inv, i, nullptr)
+                           : native_large_build_last(pl->dev.logn, pl->sub[k]->d_inv, i, nullptr)) != cudaSuccess) break;
             pl->dev.fused_fwd_last[k] = f;
             pl->dev.fused_inv_last[k] = i;
         }

@@ -67,7 +67,8 @@ struct NativePlanDev {
     int prime_set;          // 0: reference primes, 1: extended set (N up to 65536)
     PlanDev<A32L4> sub[10]; // prime32 sub-plans on P0.. (all < 2^30)
     uint2 lscale[10][4];    // 2^(32 j) * (2^32 / N) * acinv[cls][k] mod P[k] (Shoup pairs): lhs scaling of the fused polymul
-    const uint2* fused_fwd_last[10]; // last-pass twiddle layouts of the fused kernel's engine (Engine::TwSrc::last)
+    const uint2* fused_fwd_last[10]; // last-pass twiddle layouts of the fused kernel's engine (Engine::TwSrc::last); N > 4096: of the
+                                     // large path's 4096-word row engine (native_large_build_last)
     const uint2* fused_inv_last[10];
 };
 
@@ -106,6 +107,7 @@ cudaError_t native_split_fused(const NativePlanDev& pl, void* value, uint32_t* p
 // three-kernel polymul for 4096 < N <= 65536 (native_large.cuh; 65536 only exists for extended plans).  planes_l / planes_r: nprimes planes of batch * n
 // u32 each (scratch).  Returns cudaErrorNotSupported for other sizes.
 bool native_large_supported(int logn);
+cudaError_t native_large_build_last(int logn, const uint2* heap, uint2* out, cudaStream_t st);
 cudaError_t native_polymul_large(const NativePlanDev& pl, void* prod, const void* lhs, const void* rhs, size_t batch,
                                  uint32_t* planes_l, uint32_t* planes_r, cudaStream_t st);
 

@@ -160,7 +160,7 @@ static cudaError_t launch_large_kc(const NativePlanDev& pl, void* prod, const vo
     LargeParams lp;
     for (int k = 0; k < NP; k++) {
         lp.tw_fwd[k] = pl.sub[k].tw_fwd; lp.tw_inv[k] = pl.sub[k].tw_inv;
-        lp.tw_fwd_last[k] = pl.sub[k].tw_fwd_last; lp.tw_inv_last[k] = pl.sub[k].tw_inv_last;
+        lp.tw_fwd_last[k] = pl.fused_fwd_last[k]; lp.tw_inv_last[k] = pl.fused_inv_last[k]; // built for 4096-word rows by native_large_build_last
         if (!lp.tw_fwd_last[k] || !lp.tw_inv_last[k]) return cudaErrorInvalidValue;
         lp.mod[k] = pl.sub[k].mod;
         for (int j = 0; j < 4; j++) lp.lscale[k][j] = pl.lscale[k][j];
@@ -194,6 +194,14 @@ static cudaError_t launch_large_kind(const NativePlanDev& pl, void* prod, const 
         else return cudaErrorNotSupported;
     default: return cudaErrorNotSupported;
     }
+}
+
+// heap (2^logn entries) -> last-pass layouts of Engine<A32L4, 12, 4>, one slice per 4096-word row (n entries in all).
+// The large path owns these tables: the prime32 sub-plans lay theirs out for whatever block size launch_ntt uses.
+cudaError_t native_large_build_last(int logn, const uint2* heap, uint2* out, cudaStream_t st)
+{
+    if (!native_large_supported(logn)) return cudaErrorInvalidValue;
+    return launch_build_last_e<Engine<A32L4, kLargeRowLog, 4>>(heap, out, logn - kLargeRowLog, st);
 }
 
 } // namespace cntt
