@@ -19,6 +19,12 @@ constexpr int kMaxCtaLogN = 12; // largest block a CTA keeps on chip when a tran
 #ifndef CNTT_CTA13
 #define CNTT_CTA13 1
 #endif
+#ifndef CNTT_CTA13_MINTHREADS_FWD
+#define CNTT_CTA13_MINTHREADS_FWD 0 // 0: the 32-bit defaults below
+#endif
+#ifndef CNTT_CTA13_MINTHREADS_INV
+#define CNTT_CTA13_MINTHREADS_INV 0
+#endif
 #ifndef CNTT_CTA14
 #define CNTT_CTA14 0 // experiment: N = 16384 (32-bit words) in one CTA of 1024 threads
 #endif
@@ -184,7 +190,8 @@ __host__ __device__ constexpr bool cta_stages_out()
 template <class A, int LOGN, int LOGR, int GP, bool FWD, bool HEAD>
 constexpr int cta_min_blocks()
 {
-    constexpr int want = sizeof(typename A::W) == 8 ? ((LOGN == 13 && CNTT_CTA13_64_MINTHREADS) ? CNTT_CTA13_64_MINTHREADS : CNTT_CTA_MINTHREADS64) : !FWD ? CNTT_CTA_MINTHREADS32_INV : !HEAD ? CNTT_CTA_MINTHREADS32_FWD_SUB : 0;
+    constexpr int want = sizeof(typename A::W) == 8 ? ((LOGN == 13 && CNTT_CTA13_64_MINTHREADS) ? CNTT_CTA13_64_MINTHREADS : CNTT_CTA_MINTHREADS64) :
+                         (LOGN == 13 && (FWD ? CNTT_CTA13_MINTHREADS_FWD : CNTT_CTA13_MINTHREADS_INV)) ? (FWD ? CNTT_CTA13_MINTHREADS_FWD : CNTT_CTA13_MINTHREADS_INV) : !FWD ? CNTT_CTA_MINTHREADS32_INV : !HEAD ? CNTT_CTA_MINTHREADS32_FWD_SUB : 0;
     return want > GP * Geo<LOGN, LOGR>::T ? want / (GP * Geo<LOGN, LOGR>::T) : 0; // 0 = unspecified (not the same as 1: ptxas then keeps its default register heuristic)
 }
 template <class A, int LOGN, int LOGR, int GP, bool FWD, bool HEAD, int NP>
