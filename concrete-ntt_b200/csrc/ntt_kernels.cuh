@@ -100,10 +100,51 @@ template <class T> __device__ __forceinline__ void st_data(T* p, T v)
 }
 
 // ---- vector helpers -------------------------------------------------------------------------
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256).  A thread's R consecutive words leave in 32-byte pieces, so
+// every store instruction fills whole 32-byte sectors; with 128-bit stores each sector of a thread's chunk was written
+// by two instructions (ncu: 2x excessive L2 sectors on the forward kernels' stores).  Needs 32-byte alignment, which
+// the helpers below test at run time (the C ABI only promises the 16 bytes of cudaMalloc'd sub-buffers).
+#ifndef CNTT_WIDE256
+#define CNTT_WIDE256 1
+#endif
+__device__ __forceinline__ void st256(void* p, const uint32_t (&w)[8])
+{
+#if CNTT_STREAM_LDST
+    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+#else
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+#endif
+                 :: "l"(__cvta_generic_to_global(p)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+__device__ __forceinline__ void ld256(const void* p, uint32_t (&w)[8])
+{
+#if CNTT_STREAM_LDST
+    asm volatile("ld.global.cs.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#endif
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(__cvta_generic_to_global(p)) : "memory");
+}
 template <class W, int R>
 __device__ __forceinline__ void store_contig(W* __restrict__ dst, const W (&x)[R])
 {
     constexpr int BYTES = R * (int)sizeof(W);
+    if constexpr (CNTT_WIDE256 && BYTES % 32 == 0) {
+        if ((reinterpret_cast<uintptr_t>(dst) & 31u) == 0) {
+            constexpr int PER8 = 32 / (int)sizeof(W);
+#pragma unroll
+            for (int v = 0; v < R / PER8; v++) {
+                uint32_t w[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if constexpr (sizeof(W) == 4) w[i] = (uint32_t)x[8 * v + i];
+                    else w[i] = (uint32_t)((uint64_t)x[4 * v + i / 2] >> (32 * (i & 1)));
+                }
+                st256(reinterpret_cast<unsigned char*>(dst) + 32 * v, w);
+            }
+            return;
+        }
+    }
     if constexpr (BYTES % 16 == 0) {
         constexpr int PER = 16 / (int)sizeof(W);
         uint4* d4 = reinterpret_cast<uint4*>(dst);
@@ -127,6 +168,25 @@ template <class W, int R>
 __device__ __forceinline__ void load_contig(const W* __restrict__ src, W (&x)[R])
 {
     constexpr int BYTES = R * (int)sizeof(W);
+    if constexpr (CNTT_WIDE256 && BYTES % 32 == 0) {
+        if ((reinterpret_cast<uintptr_t>(src) & 31u) == 0) {
+            constexpr int PER8 = 32 / (int)sizeof(W);
+#pragma unroll
+            for (int v = 0; v < R / PER8; v++) {
+                uint32_t w[8];
+                ld256(reinterpret_cast<const unsigned char*>(src) + 32 * v, w);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if constexpr (sizeof(W) == 4) x[8 * v + i] = w[i];
+                }
+                if constexpr (sizeof(W) == 8) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) x[4 * v + i] = (uint64_t)w[2 * i] | ((uint64_t)w[2 * i + 1] << 32);
+                }
+            }
+            return;
+        }
+    }
     if constexpr (BYTES % 16 == 0) {
         constexpr int PER = 16 / (int)sizeof(W);
         const uint4* s4 = reinterpret_cast<const uint4*>(src);

@@ -260,3 +260,25 @@ def test_concurrent_streams_share_a_plan(cntt, oracle, torch_cuda):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("bits,n", [(32, 256), (32, 1024), (32, 4096), (32, 8192), (64, 2048), (64, 16384)])
+def test_buffers_aligned_to_16_bytes_only(cntt, oracle, torch_cuda, bits, n):
+    """The kernels move a thread's consecutive words with 256-bit accesses when the batch is 32-byte aligned and fall
+    back to 128-bit ones otherwise: a batch that starts 16 bytes into an allocation must give the same transforms."""
+    torch = torch_cuda
+    p = 1062862849 if bits == 32 else 0xFFFFFFFF00000001
+    dt, tdt = (np.uint32, torch.int32) if bits == 32 else (np.uint64, torch.int64)
+    OP, GP = (oracle.Plan32, cntt.prime32.Plan) if bits == 32 else (oracle.Plan64, cntt.prime64.Plan)
+    batch, skew = 5, 16 // (bits // 8)
+    a = rand_mod(rng(n + bits), p, (batch, n), dt)
+    raw = torch.empty(batch * n + skew, dtype=tdt, device="cuda")
+    d = raw[skew:].view(batch, n)
+    assert d.data_ptr() % 32 == 16
+    d.copy_(dev(torch, a))
+    op, gp = OP.try_new(n, p), GP.try_new(n, p)
+    gp.fwd(d)
+    ref = op.fwd(a.copy())
+    assert (host(d, dt) == ref).all()
+    gp.inv(d)
+    assert (host(d, dt) == op.inv(ref.copy())).all()
