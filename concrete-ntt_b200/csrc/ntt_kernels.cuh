@@ -221,9 +221,11 @@ __device__ __forceinline__ void load_contig(const W* __restrict__ src, W (&x)[R]
 // swizzled shared-memory tile (chunk c of 16 bytes at c ^ ((c >> 3) & 7): conflict-free on both sides) and leave as fully
 // coalesced 512-byte warp stores, for one more barrier per polynomial.  B200, prime32 batch sweep: N=256 1892 -> 2322,
 // N=512 897 -> 937, N=1024 439 -> 461 M NTT/s; N=2048 and 4096 lose 3-4 % (the barrier spans 128 / 256 threads), so
-// the staging is used up to N = 1024.
+// the staging was used up to N = 1024 -- until the 256-bit stores above: with whole-sector stores straight from
+// registers the tile is a loss at every size (N=256 2291 -> 2331, N=512 924 -> 982, N=1024 469 -> 481 M NTT/s without it),
+// so it is off; the code stays for 16-byte-aligned experiments.
 #ifndef CNTT_STAGE_OUT
-#define CNTT_STAGE_OUT 1
+#define CNTT_STAGE_OUT 0
 #endif
 template <class A, int LOGN, int LOGR, int NP, bool FWD>
 __host__ __device__ constexpr bool cta_stages_out()
