@@ -34,7 +34,7 @@ WORKLOAD = "prime64 Plan N=2048 p=2^64-2^32+1 (Solinas) batch 65536 per GPU, fwd
 ALG_BYTES_PER_NTT = 2 * N_POLY * 8
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_ntt_cta<A64S,11> launch over the batch, from the
 # ncu --set full capture committed under profiles/ (parsed at run time; None if the summary is absent)
-NCU_SUMMARY = os.path.join(ROOT, "profiles", "r01_kernels_v5", "ncu_ntt64s_2048.txt")
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r01_kernels_v7", "ncu_ntt64s_2048.txt")
 
 
 def ncu_traffic(direction):
@@ -478,7 +478,7 @@ def run_ours(args):
                     "steps": ke, "api": "cntt_prime64_fwd_inv_host (pinned host slice, chunked double-buffered staging)"},
             "gpu_launches": 2 * K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(which), "traffic_source": "profiles/r01_kernels_v5/ncu_ntt64s_2048.txt (ncu --set full, dram read+write bytes per launch)", "kernel": "k_ntt_cta<A64S,11,4> (%s)" % which,
+                         "traffic": ncu_traffic(which), "traffic_source": "profiles/r01_kernels_v7/ncu_ntt64s_2048.txt (ncu --set full, dram read+write bytes per launch)", "kernel": "k_ntt_cta<A64S,11,4> (%s)" % which,
                          "peak_source": peak_src, "ms_per_launch": {"fwd": fwd_ms, "inv": inv_ms},
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_NTT * BATCH,
                          "int_pipes": ncu_pipes(which),

@@ -1,5 +1,5 @@
 """Small driver for ncu captures: launches one hot-path kernel a few times on a device-resident batch.
-usage: python tools/prof_driver.py {ntt64|ntt32|polymul64|polymul128|polymulb64|polymul32} [batch] [n]"""
+usage: python tools/prof_driver.py {ntt64|ntt64shoup|ntt32|pointwise32|pointwise64|polymul64|polymul128|polymulb64|polymul32|split64} [batch] [n]"""
 import importlib
 import os
 import sys
@@ -58,6 +58,12 @@ elif which in ("polymul64", "polymulb64", "polymul32"):
     prod = torch.empty_like(lhs)
     for _ in range(reps):
         plan.negacyclic_polymul(prod, lhs, rhs)
+elif which == "split64":   # Plan32::fwd / inv on device residue planes
+    plan = cntt.native64.Plan32.try_new(n)
+    val = torch.randint(-2**63, 2**63 - 1, (batch, n), dtype=torch.int64, device="cuda", generator=g)
+    planes = torch.empty((plan.num_primes(), batch, n), dtype=torch.int32, device="cuda")
+    for _ in range(reps):
+        plan.fwd(val, planes)
 elif which == "polymul128":
     plan = cntt.native128.Plan32.try_new(n)
     lhs = torch.randint(-2**63, 2**63 - 1, (batch, n, 2), dtype=torch.int64, device="cuda", generator=g)
