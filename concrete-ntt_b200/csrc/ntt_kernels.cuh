@@ -326,6 +326,9 @@ k_ntt_cta(const typename A::Tw* __restrict__ tw, const typename A::Tw* __restric
 #ifndef CNTT_PIPE32
 #define CNTT_PIPE32 1
 #endif
+#ifndef CNTT_PIPE32_MINLOGN
+#define CNTT_PIPE32_MINLOGN 13
+#endif
 #ifndef CNTT_PIPE64
 #define CNTT_PIPE64 0
 #endif
@@ -615,7 +618,9 @@ cudaError_t launch_cta_np(const PlanDev<A>& pl, typename A::W* data, unsigned lo
     };
     // measured on B200 (prime32, batch 65536): forward +6 % at N = 1024..4096; the inverse loses 14 % (its 128-bit
     // loads were never latency-bound and the second register set costs occupancy), so only the forward pipelines
-    constexpr bool kPipe = FWD && (sizeof(typename A::W) == 4 ? CNTT_PIPE32 : CNTT_PIPE64) != 0;
+    // (re-measured after the 256-bit stores: the one-shot kernel now wins up to N = 4096 -- N=256 2311 -> 2631, N=1024 478 -> 517
+    // M NTT/s, N=2048 / 4096 within 1 % -- and the persistent one keeps N = 8192, 42.3 -> 45.9, where only two CTAs are resident)
+    constexpr bool kPipe = FWD && (sizeof(typename A::W) == 4 ? (CNTT_PIPE32 != 0 && LOGN >= CNTT_PIPE32_MINLOGN) : CNTT_PIPE64 != 0);
     if constexpr (kPipe) {
         // persistent variant: needs whole transforms and at least two polynomials per resident group to pipeline
         if (log_sub == 0 && head != nullptr) {
