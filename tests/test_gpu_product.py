@@ -227,3 +227,33 @@ def test_product_fused_two_u32_primes(cntt, oracle, torch_cuda, n, hi):
     dacc = dev(torch, acc0)
     gp.inv(dacc, dkeep, cntt.product.InvMode.Accumulate)
     assert (host(dacc) == acc_ref).all()
+
+
+@pytest.mark.parametrize("case", ["u64x1", "u32x1", "u32x2", "u30x2"])
+def test_product_n8192(cntt, oracle, torch_cuda, case):
+    """N = 8192: the u32 planes take the single-launch 8192-point kernel with a polynomial stride, the u64 planes the
+    strided level + 4096-word blocks; same packed layout and results as the oracle (src/product.rs:261-353, 355-880)."""
+    torch = torch_cuda
+    n = 8192
+    f = oracle.largest_prime_in_arithmetic_progression64
+    d = 2 * n
+    p0 = f(d, 1, 0, 2**32 - 1)
+    q0 = f(d, 1, 0, 1 << 30)
+    ps = {"u64x1": [f(d, 1, 0, 2**64 - 1)], "u32x1": [p0], "u32x2": [p0, f(d, 1, 0, p0 - 1)], "u30x2": [q0, f(d, 1, 0, q0 - 1)]}[case]
+    p = _prod(ps)
+    op, gp = oracle.Product.try_new(n, p, ps), cntt.product.Plan.try_new(n, p, ps)
+    assert op is not None and gp is not None
+    dl, batch = op.ntt_domain_len(), 3
+    std = rand_mod(rng(8192 + len(case)), p, (batch, n), np.uint64)
+    ref = np.zeros((batch, dl), dtype=np.uint64)
+    out_ref = np.zeros((batch, n), dtype=np.uint64)
+    for b in range(batch):
+        op.fwd(ref[b], std[b], op.GENERIC)
+    da = torch.zeros((batch, dl), dtype=torch.int64, device="cuda")
+    gp.fwd(da, dev(torch, std))
+    assert (host(da) == ref).all(), (case, "fwd")
+    for b in range(batch):
+        op.inv(out_ref[b], ref[b], op.REPLACE)
+    dout = torch.zeros((batch, n), dtype=torch.int64, device="cuda")
+    gp.inv(dout, da, cntt.product.InvMode.Replace)
+    assert (host(dout) == out_ref).all(), (case, "inv")
