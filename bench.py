@@ -482,6 +482,12 @@ def run_ours(args):
                          "peak_source": peak_src, "ms_per_launch": {"fwd": fwd_ms, "inv": inv_ms},
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_NTT * BATCH,
                          "int_pipes": ncu_pipes(which),
+                         # integer-pipe roofline of the same launch: 11 levels x 1024 butterflies per NTT; a Goldilocks butterfly
+                         # occupies the multiply pipe for 41 and the ALU for 38 cycles per warp, i.e. at
+                         # most 4 schedulers x 32 lanes / 41 = 3.1 butterflies per clock and SM
+                         "int_roofline": {"achieved": 11264.0 * BATCH / (slow_ms * 1e-3) / 148 / ((clocks or {}).get("sm_mhz") or 1965.0) / 1e6,
+                                          "peak": 128.0 / 41.0, "unit": "butterflies/clk/SM",
+                                          "frac": 11264.0 * BATCH / (slow_ms * 1e-3) / 148 / ((clocks or {}).get("sm_mhz") or 1965.0) / 1e6 / (128.0 / 41.0)},
                          "note": "integer-pipe bound kernel (multiply pipe and ALU ~65-75 % busy at once, ncu); the integer "
                                  "ceiling of this butterfly is 80 M NTT/s = 40 % of the HBM ceiling, see DESIGN.md section 4"},
             "extra": extra,
