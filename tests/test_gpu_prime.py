@@ -202,9 +202,10 @@ def test_full_size_properties(cntt, torch_cuda):
 
 @pytest.mark.parametrize("n,batch", [(256, 40003), (1024, 20001), (2048, 9999), (4096, 5003), (8192, 2501)])
 def test_prime32_persistent_forward_kernel(cntt, oracle, torch_cuda, n, batch):
-    """Large ragged batches take the persistent software-pipelined forward kernel (k_ntt_cta_pipe: grid = resident
-    CTAs, every group strides over the batch, tail groups clamp): oracle on sampled polynomials incl. the first and
-    the last, canonical range everywhere, and inv + normalize brings the whole batch back."""
+    """Large ragged batches: the one-shot CTA kernel with its tail groups (N <= 4096) and the persistent
+    software-pipelined forward kernel (k_ntt_cta_pipe at N = 8192: grid = resident CTAs, every group strides over the
+    batch, tail groups clamp): oracle on sampled polynomials incl. the first and the last, canonical range everywhere,
+    and inv + normalize brings the whole batch back."""
     torch = torch_cuda
     p = 1062862849
     g = rng(n + batch)
