@@ -206,9 +206,9 @@ static cudaError_t build_last32(cntt_prime32_plan* pl)
         const uint2* heap = dir ? pl->d_inv : pl->d_fwd;
         uint2* o = dir ? pl->d_inv_last : pl->d_fwd_last;
         switch (pl->cls) {
-        case C32_L4: e = build_last_A32L4(pl->logn, heap, o, nullptr); break;
-        case C32_L2: e = build_last_A32L2(pl->logn, heap, o, nullptr); break;
-        default: e = build_last_A32G(pl->logn, heap, o, nullptr); break;
+        case C32_L4: e = build_last_A32L4(pl->logn, dir == 0, heap, o, nullptr); break;
+        case C32_L2: e = build_last_A32L2(pl->logn, dir == 0, heap, o, nullptr); break;
+        default: e = build_last_A32G(pl->logn, dir == 0, heap, o, nullptr); break;
         }
         if (e != cudaSuccess) return e;
     }
@@ -366,10 +366,10 @@ static cudaError_t build_last64(cntt_prime64_plan* pl, size_t bytes)
         const void* heap = dir ? pl->d_inv : pl->d_fwd;
         void* o = dir ? pl->d_inv_last : pl->d_fwd_last;
         switch (pl->cls) {
-        case C64_L4: e = build_last_A64L4(pl->logn, (const ulonglong2*)heap, (ulonglong2*)o, nullptr); break;
-        case C64_L2: e = build_last_A64L2(pl->logn, (const ulonglong2*)heap, (ulonglong2*)o, nullptr); break;
-        case C64_S: e = build_last_A64S(pl->logn, (const uint64_t*)heap, (uint64_t*)o, nullptr); break;
-        default: e = build_last_A64G(pl->logn, (const ulonglong2*)heap, (ulonglong2*)o, nullptr); break;
+        case C64_L4: e = build_last_A64L4(pl->logn, dir == 0, (const ulonglong2*)heap, (ulonglong2*)o, nullptr); break;
+        case C64_L2: e = build_last_A64L2(pl->logn, dir == 0, (const ulonglong2*)heap, (ulonglong2*)o, nullptr); break;
+        case C64_S: e = build_last_A64S(pl->logn, dir == 0, (const uint64_t*)heap, (uint64_t*)o, nullptr); break;
+        default: e = build_last_A64G(pl->logn, dir == 0, (const ulonglong2*)heap, (ulonglong2*)o, nullptr); break;
         }
         if (e != cudaSuccess) return e;
     }

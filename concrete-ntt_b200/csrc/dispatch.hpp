@@ -14,7 +14,7 @@ namespace cntt {
     cudaError_t pointwise_##A(const PlanDev<A>& pl, int op, typename A::W* dst, const typename A::W* a,            \
                               const typename A::W* b, size_t nwords, cudaStream_t st);                             \
     bool uses_last_##A(int logn);                                                                                  \
-    cudaError_t build_last_##A(int logn, const typename A::Tw* heap, typename A::Tw* out, cudaStream_t st);
+    cudaError_t build_last_##A(int logn, bool fwd, const typename A::Tw* heap, typename A::Tw* out, cudaStream_t st);
 
 CNTT_DECLARE_CLASS(A32L4)
 CNTT_DECLARE_CLASS(A32L2)
@@ -26,9 +26,9 @@ CNTT_DECLARE_CLASS(A64G)
 
 #define CNTT_DEFINE_CLASS(A)                                                                                       \
     bool uses_last_##A(int logn) { return plan_uses_last<A>(logn); }                                               \
-    cudaError_t build_last_##A(int logn, const typename A::Tw* heap, typename A::Tw* out, cudaStream_t st)         \
+    cudaError_t build_last_##A(int logn, bool fwd, const typename A::Tw* heap, typename A::Tw* out, cudaStream_t st) \
     {                                                                                                              \
-        return launch_build_last<A>(logn, heap, out, st);                                                          \
+        return launch_build_last<A>(logn, fwd, heap, out, st);                                                          \
     }                                                                                                              \
     cudaError_t ntt_##A(const PlanDev<A>& pl, typename A::W* data, size_t batch, bool fwd, cudaStream_t st)         \
     {                                                                                                              \

@@ -26,7 +26,9 @@ constexpr int kMaxCtaLogN = 12; // largest block a CTA keeps on chip when a tran
 #define CNTT_CTA13_MINTHREADS_INV 0
 #endif
 #ifndef CNTT_CTA14
-#define CNTT_CTA14 0 // experiment: N = 16384 (32-bit words) in one CTA of 1024 threads
+#define CNTT_CTA14 2 // N = 16384 (32-bit words) in one CTA of 1024 threads x 16 words (135 KB of exchange buffers, one CTA per
+                     // SM): 0 off, 1 both directions, 2 forward only.  B200, batch 16384: forward 0.971 -> 0.840 ms; the inverse
+                     // loses 6 % (its phases no longer overlap with a second resident CTA), so it keeps the block scheme
 #endif
 #ifndef CNTT_CTA13_64
 #define CNTT_CTA13_64 0 // the same for 64-bit words: measured on B200 (Solinas, batch 16384) fwd 1.74 -> 1.58 ms with a 64-register
@@ -36,12 +38,12 @@ constexpr int kMaxCtaLogN = 12; // largest block a CTA keeps on chip when a tran
 #define CNTT_CTA13_64_MINTHREADS 0 // 0: the 64-bit default below
 #endif
 // size of the contiguous blocks the CTA kernel transforms for a plan of 2^logn words
-template <class A> constexpr int cta_block_logn(int logn)
+template <class A> constexpr int cta_block_logn(int logn, bool fwd)
 {
     if (logn <= kMaxCtaLogN) return logn;
     if (logn == 13 && (sizeof(typename A::W) == 4 ? CNTT_CTA13 : CNTT_CTA13_64)) return 13;
 #if CNTT_CTA14
-    if (logn == 14 && sizeof(typename A::W) == 4) return 14;
+    if (logn == 14 && sizeof(typename A::W) == 4 && (CNTT_CTA14 == 1 || fwd)) return 14;
 #endif
     return kMaxCtaLogN;
 }
@@ -456,9 +458,8 @@ cudaError_t launch_build_last_e(const typename E::Tw* heap, typename E::Tw* out,
 // does the CTA kernel of a transform of 2^logn words (class A) read a last-pass table?
 template <class A, int LOGN> constexpr bool cta_uses_last() { return CtaCfg<A, LOGN>::E::kLastXp; }
 template <class A>
-bool plan_uses_last(int logn)
+bool cta_uses_last_rt(int l)
 {
-    const int l = cta_block_logn<A>(logn);
     if (l == 13) return cta_uses_last<A, 13>();
 #if CNTT_CTA14
     if constexpr (sizeof(typename A::W) == 4) { if (l == 14) return cta_uses_last<A, 14>(); }
@@ -476,11 +477,13 @@ bool plan_uses_last(int logn)
     default: return false;
     }
 }
+template <class A>
+bool plan_uses_last(int logn) { return cta_uses_last_rt<A>(cta_block_logn<A>(logn, true)) || cta_uses_last_rt<A>(cta_block_logn<A>(logn, false)); }
 // heap (2^logn entries) -> last-pass table (2^logn entries) for the CTA kernel this plan size launches
 template <class A>
-cudaError_t launch_build_last(int logn, const typename A::Tw* heap, typename A::Tw* out, cudaStream_t st)
+cudaError_t launch_build_last(int logn, bool fwd, const typename A::Tw* heap, typename A::Tw* out, cudaStream_t st)
 {
-    const int l = cta_block_logn<A>(logn);
+    const int l = cta_block_logn<A>(logn, fwd);
     const int log_sub = logn - l;
     if (l == 13) return launch_build_last_e<typename CtaCfg<A, 13>::E>(heap, out, log_sub, st);
 #if CNTT_CTA14
@@ -716,7 +719,7 @@ cudaError_t launch_ntt(const PlanDev<A>& pl, typename A::W* data, size_t batch, 
 {
     if (batch == 0) return cudaSuccess;
     if (poly_stride == 0) poly_stride = (size_t)1 << pl.logn;
-    const int blk = cta_block_logn<A>(pl.logn);
+    const int blk = cta_block_logn<A>(pl.logn, FWD);
     if (pl.logn == blk) return launch_cta<A, FWD>(pl, pl.logn, data, batch, 0, poly_stride, st);
     const int lead = pl.logn - blk;
     cudaError_t e;

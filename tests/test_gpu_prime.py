@@ -200,10 +200,10 @@ def test_full_size_properties(cntt, torch_cuda):
     assert (host(d, np.uint64) == a).all()
 
 
-@pytest.mark.parametrize("n,batch", [(256, 40003), (1024, 20001), (2048, 9999), (4096, 5003), (8192, 2501)])
+@pytest.mark.parametrize("n,batch", [(256, 40003), (1024, 20001), (2048, 9999), (4096, 5003), (8192, 2501), (16384, 1201)])
 def test_prime32_persistent_forward_kernel(cntt, oracle, torch_cuda, n, batch):
     """Large ragged batches: the one-shot CTA kernel with its tail groups (N <= 4096) and the persistent
-    software-pipelined forward kernel (k_ntt_cta_pipe at N = 8192: grid = resident CTAs, every group strides over the
+    software-pipelined forward kernel (k_ntt_cta_pipe at N = 8192 and 16384: grid = resident CTAs, every group strides over the
     batch, tail groups clamp): oracle on sampled polynomials incl. the first and the last, canonical range everywhere,
     and inv + normalize brings the whole batch back."""
     torch = torch_cuda
