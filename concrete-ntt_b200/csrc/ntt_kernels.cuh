@@ -31,17 +31,18 @@ constexpr int kMaxCtaLogN = 12; // largest block a CTA keeps on chip when a tran
                      // loses 6 % (its phases no longer overlap with a second resident CTA), so it keeps the block scheme
 #endif
 #ifndef CNTT_CTA13_64
-#define CNTT_CTA13_64 0 // the same for 64-bit words: measured on B200 (Solinas, batch 16384) fwd 1.74 -> 1.58 ms with a 64-register
-                        // cap but inv 1.61 -> 1.83 ms (1.84 / 2.02 ms uncapped), so 64-bit words keep the block scheme
+#define CNTT_CTA13_64 2 // the same for 64-bit words (512 threads x 16 words, one 67 KB exchange buffer): 0 off, 1 both directions,
+                        // 2 forward only.  B200, Solinas, batch 16384, kernel capped to 64 registers (two CTAs per SM): forward
+                        // 1.713 -> 1.549 ms (Shoup-64 1.543 -> 1.495), inverse 1.63 -> 1.83 ms, so only the forward uses it
 #endif
 #ifndef CNTT_CTA13_64_MINTHREADS
-#define CNTT_CTA13_64_MINTHREADS 0 // 0: the 64-bit default below
+#define CNTT_CTA13_64_MINTHREADS 1024 // resident threads the 64-bit N = 8192 kernel is compiled for (0: the 64-bit default below)
 #endif
 // size of the contiguous blocks the CTA kernel transforms for a plan of 2^logn words
 template <class A> constexpr int cta_block_logn(int logn, bool fwd)
 {
     if (logn <= kMaxCtaLogN) return logn;
-    if (logn == 13 && (sizeof(typename A::W) == 4 ? CNTT_CTA13 : CNTT_CTA13_64)) return 13;
+    if (logn == 13 && (sizeof(typename A::W) == 4 ? CNTT_CTA13 != 0 : (CNTT_CTA13_64 == 1 || (CNTT_CTA13_64 == 2 && fwd)))) return 13;
 #if CNTT_CTA14
     if (logn == 14 && sizeof(typename A::W) == 4 && (CNTT_CTA14 == 1 || fwd)) return 14;
 #endif
