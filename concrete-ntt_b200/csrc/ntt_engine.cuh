@@ -62,7 +62,7 @@ template <class W> __device__ __forceinline__ int pad_idx(int i) { return i + (i
 constexpr int kHeadLog = 8;
 constexpr int kHeadEntries = 1 << kHeadLog;
 template <class Tw> struct TwHead { Tw e[kHeadEntries * 8 / (sizeof(Tw) < 8 ? 8 : sizeof(Tw))]; }; // 2 KB of parameter space
-template <class Tw> constexpr int head_log() { return sizeof(Tw) <= 8 ? kHeadLog : kHeadLog - 1; }
+template <class Tw> __host__ __device__ constexpr int head_log() { return sizeof(Tw) <= 8 ? kHeadLog : kHeadLog - 1; }
 
 template <class A, int LOGN, int LOGR>
 struct Engine {
