@@ -13,6 +13,8 @@
  * slices concatenated).  Residue planes of the native plans: plane k of polynomial b is
  * mod_p[(k*batch + b)*n + i] (k-th `mod_pk` slice of the reference, concatenated over the batch).
  * 128-bit words are little-endian {lo:u64, hi:u64} pairs, 16-byte aligned (Rust u128 on x86-64).
+ * Device batches must be 16-byte aligned; 32-byte aligned batches (cudaMalloc gives 256) also get the 256-bit
+ * load / store path of the transform kernels.
  *
  * Results are bit-identical to the reference on the same inputs (same primitive root, same
  * bit-reversed order, canonical residues, same centred CRT lift).
