@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CNTT_B200_LIB", os.path.join(_HERE, "libcntt_b200.so"))  # override: experiments only
 
-OK, INVALID_SIZE, INVALID_MODULUS, NO_ROOT, LENGTH_MISMATCH, CUDA_ERROR, NULL_POINTER, UNSUPPORTED, PANIC_MODULUS = range(9)
+OK, INVALID_SIZE, INVALID_MODULUS, NO_ROOT, LENGTH_MISMATCH, CUDA_ERROR, NULL_POINTER, UNSUPPORTED, PANIC_MODULUS, MISALIGNED = range(10)
 
 _vp, _sz, _int = C.c_void_p, C.c_size_t, C.c_int
 _u32, _u64 = C.c_uint32, C.c_uint64

@@ -44,11 +44,18 @@ CNTT_API const char* cntt_status_string(int s)
     case CNTT_NULL_POINTER: return "null pointer";
     case CNTT_UNSUPPORTED: return "operation not supported by this plan";
     case CNTT_PANIC_MODULUS: return "modulus <= 1 (reference: Div::new assert panic)";
+    case CNTT_MISALIGNED: return "device buffer is not 16-byte aligned";
     default: return "unknown status";
     }
 }
 CNTT_API const char* cntt_last_cuda_error(void) { return t_cuda_err.c_str(); }
 CNTT_API const char* cntt_version(void) { return "cntt_b200 0.1 (sm_100a; concrete-ntt 0.2.0 semantics)"; }
+
+// device batches are accessed with 128-bit (and, when they allow it, 256-bit) loads and stores
+static inline bool misaligned16(const void* a, const void* b = nullptr, const void* c = nullptr)
+{
+    return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15u) != 0;
+}
 
 struct DeviceGuard {
     int prev = -1;
@@ -110,15 +117,37 @@ struct Staging {
     cudaEvent_t ev_down[4] = {nullptr, nullptr, nullptr, nullptr}; // download of slot s done
     void* buf = nullptr;
     size_t cap = 0;
+    bool ready = false; // set only after every stream and event exists
+    cudaError_t create_objects()
+    {
+        cudaError_t e;
+        if ((e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        for (auto* arr : {ev, ev_up, ev_down})
+            for (int i = 0; i < 4; i++)
+                if ((e = cudaEventCreateWithFlags(&arr[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+        return cudaSuccess;
+    }
+    void destroy_objects()
+    {
+        for (auto* arr : {ev, ev_up, ev_down})
+            for (int i = 0; i < 4; i++) {
+                if (arr[i]) cudaEventDestroy(arr[i]);
+                arr[i] = nullptr;
+            }
+        if (stream) cudaStreamDestroy(stream);
+        if (stream2) cudaStreamDestroy(stream2);
+        stream = stream2 = nullptr;
+    }
     cudaError_t ensure(size_t bytes)
     {
         cudaError_t e;
-        if (!stream) {
-            if ((e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
-            if ((e = cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking)) != cudaSuccess) return e;
-            for (auto* arr : {ev, ev_up, ev_down})
-                for (int i = 0; i < 4; i++)
-                    if ((e = cudaEventCreateWithFlags(&arr[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+        if (!ready) {
+            if ((e = create_objects()) != cudaSuccess) {
+                destroy_objects(); // failure-atomic: the next call starts from scratch instead of using half a set
+                return e;
+            }
+            ready = true;
         }
         if (bytes > cap) {
             if (buf) cudaFree(buf);
@@ -132,11 +161,10 @@ struct Staging {
     void release()
     {
         if (buf) cudaFree(buf);
-        for (auto* arr : {ev, ev_up, ev_down})
-            for (int i = 0; i < 4; i++)
-                if (arr[i]) cudaEventDestroy(arr[i]);
-        if (stream) cudaStreamDestroy(stream);
-        if (stream2) cudaStreamDestroy(stream2);
+        buf = nullptr;
+        cap = 0;
+        destroy_objects();
+        ready = false;
     }
 };
 
@@ -180,9 +208,10 @@ static int validate(size_t n, uint64_t p, size_t min_n, uint64_t* psi, int* logn
     if (n < min_n || (n & (n - 1)) != 0) return CNTT_INVALID_SIZE;
     int lg = 0;
     while (((size_t)1 << lg) < n) ++lg;
-    if (lg > kMaxLogN) return CNTT_INVALID_SIZE;
     if (!host::is_prime_u64(p)) return CNTT_INVALID_MODULUS;
-    if (!host::primitive_root_pow2(p, 2 * (uint64_t)n, psi)) return CNTT_NO_ROOT;
+    if (lg >= 63 || !host::primitive_root_pow2(p, 2 * (uint64_t)n, psi)) return CNTT_NO_ROOT;
+    // an implementation limit (table memory), not one of the reference's None cases: reported as such, after them
+    if (lg > kMaxLogN) return CNTT_UNSUPPORTED;
     *logn = lg;
     return CNTT_OK;
 }
@@ -302,6 +331,7 @@ static cudaError_t run_pw32(const cntt_prime32_plan* pl, int op, uint32_t* dst, 
 CNTT_API int cntt_prime32_fwd(const cntt_prime32_plan* pl, uint32_t* d_buf, size_t batch, void* stream)
 {
     if (!pl || (!d_buf && batch)) return CNTT_NULL_POINTER;
+    if (misaligned16(d_buf)) return CNTT_MISALIGNED;
     GUARD(pl->device);
     CU(run_ntt32(pl, d_buf, batch, true, (cudaStream_t)stream));
     return CNTT_OK;
@@ -309,6 +339,7 @@ CNTT_API int cntt_prime32_fwd(const cntt_prime32_plan* pl, uint32_t* d_buf, size
 CNTT_API int cntt_prime32_inv(const cntt_prime32_plan* pl, uint32_t* d_buf, size_t batch, void* stream)
 {
     if (!pl || (!d_buf && batch)) return CNTT_NULL_POINTER;
+    if (misaligned16(d_buf)) return CNTT_MISALIGNED;
     GUARD(pl->device);
     CU(run_ntt32(pl, d_buf, batch, false, (cudaStream_t)stream));
     return CNTT_OK;
@@ -319,6 +350,7 @@ CNTT_API int cntt_prime32_inv(const cntt_prime32_plan* pl, uint32_t* d_buf, size
 CNTT_API int cntt_prime32_mul_assign_normalize(const cntt_prime32_plan* pl, uint32_t* l, const uint32_t* r, size_t nwords, void* stream)
 {
     if (!pl || ((!l || !r) && nwords)) return CNTT_NULL_POINTER;
+    if (misaligned16(l, r)) return CNTT_MISALIGNED;
     if (nwords % 4) return CNTT_LENGTH_MISMATCH;
     GUARD(pl->device);
     CU(run_pw32(pl, OP_MUL_ASSIGN_NORMALIZE, l, r, nullptr, nwords, (cudaStream_t)stream));
@@ -327,6 +359,7 @@ CNTT_API int cntt_prime32_mul_assign_normalize(const cntt_prime32_plan* pl, uint
 CNTT_API int cntt_prime32_normalize(const cntt_prime32_plan* pl, uint32_t* v, size_t nwords, void* stream)
 {
     if (!pl || (!v && nwords)) return CNTT_NULL_POINTER;
+    if (misaligned16(v)) return CNTT_MISALIGNED;
     if (nwords % 4) return CNTT_LENGTH_MISMATCH;
     GUARD(pl->device);
     CU(run_pw32(pl, OP_NORMALIZE, v, nullptr, nullptr, nwords, (cudaStream_t)stream));
@@ -335,6 +368,7 @@ CNTT_API int cntt_prime32_normalize(const cntt_prime32_plan* pl, uint32_t* v, si
 CNTT_API int cntt_prime32_mul_accumulate(const cntt_prime32_plan* pl, uint32_t* acc, const uint32_t* l, const uint32_t* r, size_t nwords, void* stream)
 {
     if (!pl || ((!acc || !l || !r) && nwords)) return CNTT_NULL_POINTER;
+    if (misaligned16(acc, l, r)) return CNTT_MISALIGNED;
     if (nwords % 4) return CNTT_LENGTH_MISMATCH;
     GUARD(pl->device);
     CU(run_pw32(pl, OP_MUL_ACCUMULATE, acc, l, r, nwords, (cudaStream_t)stream));
@@ -482,6 +516,7 @@ static cudaError_t run_pw64(const cntt_prime64_plan* pl, int op, uint64_t* dst, 
 CNTT_API int cntt_prime64_fwd(const cntt_prime64_plan* pl, uint64_t* d_buf, size_t batch, void* stream)
 {
     if (!pl || (!d_buf && batch)) return CNTT_NULL_POINTER;
+    if (misaligned16(d_buf)) return CNTT_MISALIGNED;
     GUARD(pl->device);
     CU(run_ntt64(pl, d_buf, batch, true, (cudaStream_t)stream));
     return CNTT_OK;
@@ -489,6 +524,7 @@ CNTT_API int cntt_prime64_fwd(const cntt_prime64_plan* pl, uint64_t* d_buf, size
 CNTT_API int cntt_prime64_inv(const cntt_prime64_plan* pl, uint64_t* d_buf, size_t batch, void* stream)
 {
     if (!pl || (!d_buf && batch)) return CNTT_NULL_POINTER;
+    if (misaligned16(d_buf)) return CNTT_MISALIGNED;
     GUARD(pl->device);
     CU(run_ntt64(pl, d_buf, batch, false, (cudaStream_t)stream));
     return CNTT_OK;
@@ -496,6 +532,7 @@ CNTT_API int cntt_prime64_inv(const cntt_prime64_plan* pl, uint64_t* d_buf, size
 CNTT_API int cntt_prime64_mul_assign_normalize(const cntt_prime64_plan* pl, uint64_t* l, const uint64_t* r, size_t nwords, void* stream)
 {
     if (!pl || ((!l || !r) && nwords)) return CNTT_NULL_POINTER;
+    if (misaligned16(l, r)) return CNTT_MISALIGNED;
     if (nwords % 2) return CNTT_LENGTH_MISMATCH;
     GUARD(pl->device);
     CU(run_pw64(pl, OP_MUL_ASSIGN_NORMALIZE, l, r, nullptr, nwords, (cudaStream_t)stream));
@@ -504,6 +541,7 @@ CNTT_API int cntt_prime64_mul_assign_normalize(const cntt_prime64_plan* pl, uint
 CNTT_API int cntt_prime64_normalize(const cntt_prime64_plan* pl, uint64_t* v, size_t nwords, void* stream)
 {
     if (!pl || (!v && nwords)) return CNTT_NULL_POINTER;
+    if (misaligned16(v)) return CNTT_MISALIGNED;
     if (nwords % 2) return CNTT_LENGTH_MISMATCH;
     GUARD(pl->device);
     CU(run_pw64(pl, OP_NORMALIZE, v, nullptr, nullptr, nwords, (cudaStream_t)stream));
@@ -512,6 +550,7 @@ CNTT_API int cntt_prime64_normalize(const cntt_prime64_plan* pl, uint64_t* v, si
 CNTT_API int cntt_prime64_mul_accumulate(const cntt_prime64_plan* pl, uint64_t* acc, const uint64_t* l, const uint64_t* r, size_t nwords, void* stream)
 {
     if (!pl || ((!acc || !l || !r) && nwords)) return CNTT_NULL_POINTER;
+    if (misaligned16(acc, l, r)) return CNTT_MISALIGNED;
     if (nwords % 2) return CNTT_LENGTH_MISMATCH;
     GUARD(pl->device);
     CU(run_pw64(pl, OP_MUL_ACCUMULATE, acc, l, r, nwords, (cudaStream_t)stream));
@@ -754,6 +793,7 @@ static cudaError_t native_inv_impl(const cntt_native_plan* pl, void* value, uint
 CNTT_API int cntt_native_fwd(const cntt_native_plan* pl, const void* d_value, uint32_t* d_mod_p, size_t batch, void* stream)
 {
     if (!pl || ((!d_value || !d_mod_p) && batch)) return CNTT_NULL_POINTER;
+    if (misaligned16(d_value, d_mod_p)) return CNTT_MISALIGNED;
     GUARD(pl->device);
     CU(native_fwd_impl(pl, d_value, d_mod_p, batch, false, (cudaStream_t)stream));
     return CNTT_OK;
@@ -761,6 +801,7 @@ CNTT_API int cntt_native_fwd(const cntt_native_plan* pl, const void* d_value, ui
 CNTT_API int cntt_native_fwd_binary(const cntt_native_plan* pl, const void* d_value, uint32_t* d_mod_p, size_t batch, void* stream)
 {
     if (!pl || ((!d_value || !d_mod_p) && batch)) return CNTT_NULL_POINTER;
+    if (misaligned16(d_value, d_mod_p)) return CNTT_MISALIGNED;
     if (pl->kind < NK_BINARY32) return CNTT_UNSUPPORTED; // only native_binary* have fwd_binary
     GUARD(pl->device);
     CU(native_fwd_impl(pl, d_value, d_mod_p, batch, true, (cudaStream_t)stream));
@@ -769,6 +810,7 @@ CNTT_API int cntt_native_fwd_binary(const cntt_native_plan* pl, const void* d_va
 CNTT_API int cntt_native_inv(const cntt_native_plan* pl, void* d_value, uint32_t* d_mod_p, size_t batch, void* stream)
 {
     if (!pl || ((!d_value || !d_mod_p) && batch)) return CNTT_NULL_POINTER;
+    if (misaligned16(d_value, d_mod_p)) return CNTT_MISALIGNED;
     GUARD(pl->device);
     CU(native_inv_impl(pl, d_value, d_mod_p, batch, (cudaStream_t)stream));
     return CNTT_OK;
@@ -850,6 +892,7 @@ static cudaError_t native_polymul_impl(const cntt_native_plan* pl, void* prod, c
 CNTT_API int cntt_native_polymul(const cntt_native_plan* pl, void* d_prod, const void* d_lhs, const void* d_rhs, size_t batch, void* stream)
 {
     if (!pl || ((!d_prod || !d_lhs || !d_rhs) && batch)) return CNTT_NULL_POINTER;
+    if (misaligned16(d_prod, d_lhs, d_rhs)) return CNTT_MISALIGNED;
     GUARD(pl->device);
     CU(native_polymul_impl(pl, d_prod, d_lhs, d_rhs, batch, (cudaStream_t)stream));
     return CNTT_OK;
@@ -998,6 +1041,7 @@ CNTT_API uint64_t cntt_native52_prime(const cntt_native52_plan* pl, int i) { ret
 static int native52_fwd(const cntt_native52_plan* pl, const void* d_value, uint64_t* d_mod_p, size_t batch, bool copy, cudaStream_t st)
 {
     if (!pl || ((!d_value || !d_mod_p) && batch)) return CNTT_NULL_POINTER;
+    if (misaligned16(d_value, d_mod_p)) return CNTT_MISALIGNED;
     if (batch == 0) return CNTT_OK;
     GUARD(pl->device);
     const unsigned long long nwords = (unsigned long long)pl->n * batch;
@@ -1020,6 +1064,7 @@ CNTT_API int cntt_native52_fwd_binary(const cntt_native52_plan* pl, const void* 
 CNTT_API int cntt_native52_inv(const cntt_native52_plan* pl, void* d_value, uint64_t* d_mod_p, size_t batch, void* stream)
 {
     if (!pl || ((!d_value || !d_mod_p) && batch)) return CNTT_NULL_POINTER;
+    if (misaligned16(d_value, d_mod_p)) return CNTT_MISALIGNED;
     if (batch == 0) return CNTT_OK;
     GUARD(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -1086,7 +1131,13 @@ CNTT_API int cntt_product_plan_new(size_t n, uint64_t modulus, const uint64_t* f
         if (prod >> 64) return CNTT_INVALID_MODULUS; // checked_mul overflow
     }
     if ((uint64_t)prod != modulus) return CNTT_INVALID_MODULUS;
-    if (pr.size() > (size_t)kProductMaxPrimes) return CNTT_UNSUPPORTED; // cannot happen for accepted sizes
+    for (uint64_t f : pr) { // every None of the reference first (host-only checks) ...
+        uint64_t psi;
+        int lg;
+        const int st = validate(n, f, f < (1ull << 32) ? 32 : 16, &psi, &lg);
+        if (st != CNTT_OK) return st;
+    }
+    if (pr.size() > (size_t)kProductMaxPrimes) return CNTT_UNSUPPORTED; // ... then the implementation limit (cannot happen for accepted sizes)
     cntt_product_plan* pl = new cntt_product_plan();
     pl->n = n; pl->modulus = modulus; pl->device = device;
     for (int k = 0; k < kProductMaxPrimes; k++) { pl->p32[k] = nullptr; pl->p64[k] = nullptr; }
@@ -1220,6 +1271,7 @@ static bool product_fused_args(const cntt_product_plan* pl, ProductFusedArgs* a)
 CNTT_API int cntt_product_fwd(const cntt_product_plan* pl, uint64_t* d_ntt, const uint64_t* d_standard, int mode, uint64_t bound, size_t batch, void* stream)
 {
     if (!pl || ((!d_ntt || !d_standard) && batch)) return CNTT_NULL_POINTER;
+    if (misaligned16(d_ntt, d_standard)) return CNTT_MISALIGNED;
     if (mode != PF_GENERIC && mode != PF_BOUNDED) return CNTT_UNSUPPORTED;
     if (batch == 0 || pl->c.count32 + pl->c.count64 == 0) return CNTT_OK;
     GUARD(pl->device);
@@ -1240,6 +1292,7 @@ CNTT_API int cntt_product_fwd(const cntt_product_plan* pl, uint64_t* d_ntt, cons
 CNTT_API int cntt_product_inv(const cntt_product_plan* pl, uint64_t* d_standard, uint64_t* d_ntt, int mode, size_t batch, void* stream)
 {
     if (!pl || ((!d_ntt || !d_standard) && batch)) return CNTT_NULL_POINTER;
+    if (misaligned16(d_ntt, d_standard)) return CNTT_MISALIGNED;
     if (mode != PI_REPLACE && mode != PI_ACCUMULATE) return CNTT_UNSUPPORTED;
     if (batch == 0) return CNTT_OK;
     GUARD(pl->device);
@@ -1258,6 +1311,7 @@ CNTT_API int cntt_product_inv(const cntt_product_plan* pl, uint64_t* d_standard,
 CNTT_API int cntt_product_mul_assign_normalize(const cntt_product_plan* pl, uint64_t* d_lhs, const uint64_t* d_rhs, size_t batch, void* stream)
 {
     if (!pl || ((!d_lhs || !d_rhs) && batch)) return CNTT_NULL_POINTER;
+    if (misaligned16(d_lhs, d_rhs)) return CNTT_MISALIGNED;
     GUARD(pl->device);
     CU(product_pointwise(pl, OP_MUL_ASSIGN_NORMALIZE, d_lhs, d_rhs, nullptr, batch, (cudaStream_t)stream));
     return CNTT_OK;
@@ -1265,6 +1319,7 @@ CNTT_API int cntt_product_mul_assign_normalize(const cntt_product_plan* pl, uint
 CNTT_API int cntt_product_normalize(const cntt_product_plan* pl, uint64_t* d_values, size_t batch, void* stream)
 {
     if (!pl || (!d_values && batch)) return CNTT_NULL_POINTER;
+    if (misaligned16(d_values)) return CNTT_MISALIGNED;
     GUARD(pl->device);
     CU(product_pointwise(pl, OP_NORMALIZE, d_values, nullptr, nullptr, batch, (cudaStream_t)stream));
     return CNTT_OK;
@@ -1272,6 +1327,7 @@ CNTT_API int cntt_product_normalize(const cntt_product_plan* pl, uint64_t* d_val
 CNTT_API int cntt_product_mul_accumulate(const cntt_product_plan* pl, uint64_t* d_acc, const uint64_t* d_lhs, const uint64_t* d_rhs, size_t batch, void* stream)
 {
     if (!pl || ((!d_acc || !d_lhs || !d_rhs) && batch)) return CNTT_NULL_POINTER;
+    if (misaligned16(d_acc, d_lhs, d_rhs)) return CNTT_MISALIGNED;
     GUARD(pl->device);
     CU(product_pointwise(pl, OP_MUL_ACCUMULATE, d_acc, d_lhs, d_rhs, batch, (cudaStream_t)stream));
     return CNTT_OK;

@@ -194,10 +194,7 @@ static cudaError_t launch_fused_one(const NativePlanDev& pl, void* prod, const v
     }
     auto kern = k_polymul_fused<KIND, LOGN, LOGR>;
     if (Cfg::SMEM_BYTES > 227 * 1024) return cudaErrorNotSupported;
-    if (Cfg::SMEM_BYTES > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-    }
+    if (cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES); e != cudaSuccess) return e;
     const unsigned long long nblk = (batch + Cfg::GP - 1) / Cfg::GP;
     if (nblk > 0x7fffffffull) return cudaErrorInvalidValue;
     kern<<<(unsigned)nblk, Cfg::GP * Cfg::T, Cfg::SMEM_BYTES, st>>>(native_consts(pl.prime_set), fp, prod, lhs, rhs, batch);

@@ -174,7 +174,7 @@ static cudaError_t launch_large_kc(const NativePlanDev& pl, void* prod, const vo
     if (e != cudaSuccess) return e;
     const size_t smem = (size_t)2 * E::NBUF * E::SMEM_WORDS * sizeof(uint32_t);
     auto mid = k_large_mid<LOGC>;
-    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    if ((e = ensure_dyn_smem(reinterpret_cast<const void*>(mid), smem)) != cudaSuccess) return e;
     mid<<<dim3((unsigned)(batch << LOGC), NP), E::T, smem, st>>>(c, lp, planes_l, planes_r, plane_stride);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     k_large_lead_inv<KIND, LOGC><<<(unsigned)((ncols + 127) / 128), 128, 0, st>>>(c, lp, prod, planes_l, plane_stride, ncols);

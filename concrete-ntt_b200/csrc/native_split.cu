@@ -84,10 +84,8 @@ static cudaError_t launch_split(const NativePlanDev& pl, void* value, uint32_t* 
     const NativeConsts& c = native_consts(pl.prime_set);
     auto go = [&](auto kern, size_t smem, int threads) -> cudaError_t {
         if (smem > (size_t)227 * 1024) return cudaErrorNotSupported;
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-        }
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem);
+        if (e != cudaSuccess) return e;
         kern<<<(unsigned)batch, threads, smem, st>>>(c, sp, value, planes, plane_stride, (unsigned long long)batch);
         return cudaGetLastError();
     };

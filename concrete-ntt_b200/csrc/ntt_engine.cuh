@@ -21,8 +21,40 @@
 //   (recursion_depth, recursion_half) call (prime32/shoup.rs:597,686-706).
 #pragma once
 #include "arith.cuh"
+#include <atomic>
 
 namespace cntt {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-function, per-device property: set it the first time a kernel that
+// needs more than 48 KB is launched on a device, not on every launch (r01: 27.6 us per fwd + inv round trip at batch 1
+// through two calls against 4.6 us under a graph -- most of the gap was this call).  Lock-free open-addressing table
+// keyed by the kernel's address; a lost race just sets the attribute twice.
+inline cudaError_t ensure_dyn_smem(const void* kern, size_t smem)
+{
+    if (smem <= 48 * 1024) return cudaSuccess;
+    constexpr unsigned kSlots = 1024;
+    static std::atomic<const void*> key[kSlots];
+    static std::atomic<unsigned long long> devmask[kSlots];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = (dev >= 0 && dev < 64) ? 1ull << dev : 0ull;
+    unsigned h = (unsigned)((reinterpret_cast<uintptr_t>(kern) >> 4) * 2654435761u) % kSlots;
+    for (unsigned probe = 0; probe < kSlots; probe++, h = (h + 1) % kSlots) {
+        const void* k = key[h].load(std::memory_order_acquire);
+        if (k == nullptr) {
+            const void* expect = nullptr;
+            if (!key[h].compare_exchange_strong(expect, kern, std::memory_order_acq_rel) && expect != kern) continue;
+            k = kern;
+        }
+        if (k != kern) continue;
+        if (bit && (devmask[h].load(std::memory_order_acquire) & bit)) return cudaSuccess;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess && bit) devmask[h].fetch_or(bit, std::memory_order_acq_rel);
+        return e;
+    }
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); // table full: uncached
+}
 
 template <int LOGN, int LOGR>
 struct Geo {
@@ -58,6 +90,11 @@ template <class W> __device__ __forceinline__ int pad_idx(int i) { return i + (i
 #endif
 #ifndef CNTT_HEAD_MINS
 #define CNTT_HEAD_MINS 16
+#endif
+// ping-pong exchange buffers only while both fit in this many bytes per polynomial: beyond N = 4096 x u32 (2 x 16.9 KB) the
+// second buffer costs resident CTAs, which are worth more than the saved barrier (ntt_kernels.cuh, CNTT_R32_MINLOGN)
+#ifndef CNTT_NBUF2_MAXBYTES
+#define CNTT_NBUF2_MAXBYTES 40000
 #endif
 constexpr int kHeadLog = 8;
 constexpr int kHeadEntries = 1 << kHeadLog;
@@ -97,7 +134,8 @@ struct Engine {
     }
     static constexpr bool kXor = any_wants_perm<0>() && !kPermFeasible;
     static constexpr int SMEM_WORDS = kXor ? N : padded_words<W>(N); // per polynomial, per buffer
-    static constexpr int NBUF = (P >= 3 && !(sizeof(W) == 8 && CNTT_NBUF64 == 1) && !(sizeof(W) == 4 && CNTT_NBUF32 == 1)) ? 2 : 1; // ping-pong when >1 exchange
+    static constexpr int NBUF = (P >= 3 && !(sizeof(W) == 8 && CNTT_NBUF64 == 1) && !(sizeof(W) == 4 && CNTT_NBUF32 == 1) &&
+                                 2 * SMEM_WORDS * (int)sizeof(W) <= CNTT_NBUF2_MAXBYTES) ? 2 : 1; // ping-pong when >1 exchange
 
     template <int Q> static __device__ __forceinline__ void decomp(int tid, int& blk, int& o)
     {

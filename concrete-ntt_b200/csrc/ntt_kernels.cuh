@@ -38,10 +38,28 @@ constexpr int kMaxCtaLogN = 12; // largest block a CTA keeps on chip when a tran
 #ifndef CNTT_CTA13_64_MINTHREADS
 #define CNTT_CTA13_64_MINTHREADS 1024 // resident threads the 64-bit N = 8192 kernel is compiled for (0: the 64-bit default below)
 #endif
+// 32-bit words, 32 words per thread (LOGR = 5) for N = 2^CNTT_R32_MINLOGN .. 2^CNTT_R32_MAXBLK (0 = off, the r01 scheme): three
+// register passes (two exchanges) instead of four, 256 / 512 threads per polynomial, ONE exchange buffer (two barriers per
+// exchange) so that four / two CTAs stay resident, and no persistent software-pipelined forward variant (its second register
+// set halves the resident CTAs).  B200, r02 (profiles/r02_experiments.txt), M NTT/s fwd / inv:
+//   N = 8192   45.8 / 46.1 -> 47.7 / 54.8      N = 16384  19.5 / 17.4 -> 20.5 / 21.6
+// With two exchange buffers the same kernels lose (32.2 / 43.8 at N = 8192).  N = 32768 also fits one CTA this way (1024 threads,
+// one 135 KB buffer: a single launch that reads and writes every word once) but runs at 8.1 / 8.5 against 8.1 / 8.9 for the
+// two-pass scheme -- one resident CTA per SM cannot overlap its load, compute and store phases (ncu: issue 40 %, lg_throttle the
+// top stall) -- and as the 32768-word block of N = 65536 it is slower (2.7 against 4.0), so blocks stop at 16384 words.
+#ifndef CNTT_R32_MINLOGN
+#define CNTT_R32_MINLOGN 13
+#endif
+#ifndef CNTT_R32_MAXBLK
+#define CNTT_R32_MAXBLK 14
+#endif
+constexpr bool kR32 = CNTT_R32_MINLOGN != 0;
+template <class A, int LOGN> constexpr bool r32_size() { return kR32 && sizeof(typename A::W) == 4 && LOGN >= CNTT_R32_MINLOGN && LOGN <= CNTT_R32_MAXBLK; }
 // size of the contiguous blocks the CTA kernel transforms for a plan of 2^logn words
 template <class A> constexpr int cta_block_logn(int logn, bool fwd)
 {
     if (logn <= kMaxCtaLogN) return logn;
+    if (sizeof(typename A::W) == 4 && kR32) return (logn >= CNTT_R32_MINLOGN && logn <= CNTT_R32_MAXBLK) ? logn : kMaxCtaLogN;
     if (logn == 13 && (sizeof(typename A::W) == 4 ? CNTT_CTA13 != 0 : (CNTT_CTA13_64 == 1 || (CNTT_CTA13_64 == 2 && fwd)))) return 13;
 #if CNTT_CTA14
     if (logn == 14 && sizeof(typename A::W) == 4 && (CNTT_CTA14 == 1 || fwd)) return 14;
@@ -73,7 +91,7 @@ struct PlanDev {
 #define CNTT_LOGR32 4
 #endif
 template <class A, int LOGN> struct CtaCfg {
-    static constexpr int LOGR_MAX = sizeof(typename A::W) == 8 ? CNTT_LOGR64 : CNTT_LOGR32;
+    static constexpr int LOGR_MAX = sizeof(typename A::W) == 8 ? CNTT_LOGR64 : r32_size<A, LOGN>() ? 5 : CNTT_LOGR32;
     static constexpr int LOGR = LOGN < LOGR_MAX ? LOGN : LOGR_MAX;
     typedef Engine<A, LOGN, LOGR> E;
 };
@@ -332,6 +350,9 @@ k_ntt_cta(const typename A::Tw* __restrict__ tw, const typename A::Tw* __restric
 #ifndef CNTT_PIPE32_MINLOGN
 #define CNTT_PIPE32_MINLOGN 13
 #endif
+#ifndef CNTT_PIPE32_MAXLOGN
+#define CNTT_PIPE32_MAXLOGN 14 // the second register set does not fit the 64 registers of a 1024-thread CTA (N = 32768)
+#endif
 #ifndef CNTT_PIPE64
 #define CNTT_PIPE64 0
 #endif
@@ -462,9 +483,10 @@ template <class A>
 bool cta_uses_last_rt(int l)
 {
     if (l == 13) return cta_uses_last<A, 13>();
-#if CNTT_CTA14
-    if constexpr (sizeof(typename A::W) == 4) { if (l == 14) return cta_uses_last<A, 14>(); }
-#endif
+    if constexpr (sizeof(typename A::W) == 4) {
+        if (l == 14) return cta_uses_last<A, 14>();
+        if constexpr (r32_size<A, 15>()) { if (l == 15) return cta_uses_last<A, 15>(); }
+    }
     switch (l) {
     case 4: return cta_uses_last<A, 4>();
     case 5: return cta_uses_last<A, 5>();
@@ -487,9 +509,10 @@ cudaError_t launch_build_last(int logn, bool fwd, const typename A::Tw* heap, ty
     const int l = cta_block_logn<A>(logn, fwd);
     const int log_sub = logn - l;
     if (l == 13) return launch_build_last_e<typename CtaCfg<A, 13>::E>(heap, out, log_sub, st);
-#if CNTT_CTA14
-    if constexpr (sizeof(typename A::W) == 4) { if (l == 14) return launch_build_last_e<typename CtaCfg<A, 14>::E>(heap, out, log_sub, st); }
-#endif
+    if constexpr (sizeof(typename A::W) == 4) {
+        if (l == 14) return launch_build_last_e<typename CtaCfg<A, 14>::E>(heap, out, log_sub, st);
+        if constexpr (r32_size<A, 15>()) { if (l == 15) return launch_build_last_e<typename CtaCfg<A, 15>::E>(heap, out, log_sub, st); }
+    }
     switch (l) {
     case 4: return launch_build_last_e<typename CtaCfg<A, 4>::E>(heap, out, log_sub, st);
     case 5: return launch_build_last_e<typename CtaCfg<A, 5>::E>(heap, out, log_sub, st);
@@ -613,10 +636,8 @@ cudaError_t launch_cta_np(const PlanDev<A>& pl, typename A::W* data, unsigned lo
     if (E::kLastXp && last == nullptr) return cudaErrorInvalidValue; // plan built without its last-pass table
     const TwHead<typename A::Tw>* head = FWD ? pl.head_fwd : pl.head_inv;
     auto launch = [&](auto kern, const TwHead<typename A::Tw>& h) -> cudaError_t {
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-        }
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem);
+        if (e != cudaSuccess) return e;
         kern<<<(unsigned)nblk, GP * T, smem, st>>>(FWD ? pl.tw_fwd : pl.tw_inv, last, pl.mod, data, nvpoly, log_sub, poly_stride, h);
         return cudaGetLastError();
     };
@@ -624,7 +645,7 @@ cudaError_t launch_cta_np(const PlanDev<A>& pl, typename A::W* data, unsigned lo
     // loads were never latency-bound and the second register set costs occupancy), so only the forward pipelines
     // (re-measured after the 256-bit stores: the one-shot kernel now wins up to N = 4096 -- N=256 2311 -> 2631, N=1024 478 -> 517
     // M NTT/s, N=2048 / 4096 within 1 % -- and the persistent one keeps N = 8192, 42.3 -> 45.9, where only two CTAs are resident)
-    constexpr bool kPipe = FWD && (sizeof(typename A::W) == 4 ? (CNTT_PIPE32 != 0 && LOGN >= CNTT_PIPE32_MINLOGN) : CNTT_PIPE64 != 0);
+    constexpr bool kPipe = FWD && (sizeof(typename A::W) == 4 ? (CNTT_PIPE32 != 0 && LOGN >= CNTT_PIPE32_MINLOGN && LOGN <= CNTT_PIPE32_MAXLOGN && !r32_size<A, LOGN>()) : CNTT_PIPE64 != 0);
     if constexpr (kPipe) {
         // persistent variant: needs whole transforms and at least two polynomials per resident group to pipeline
         if (log_sub == 0 && head != nullptr) {
@@ -637,7 +658,7 @@ cudaError_t launch_cta_np(const PlanDev<A>& pl, typename A::W* data, unsigned lo
             if (dev < 0 || dev >= 64) dev = 0;
             int res = resident[dev].load(std::memory_order_relaxed);
             if (res == 0) {
-                if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+                if ((e = ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem)) != cudaSuccess) return e;
                 int per_sm = 0, sms = 0;
                 if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GP * T, smem)) != cudaSuccess) return e;
                 if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
@@ -672,9 +693,10 @@ template <class A, bool FWD>
 cudaError_t launch_cta(const PlanDev<A>& pl, int logn_sub, typename A::W* data, unsigned long long nvpoly, int log_sub, size_t poly_stride, cudaStream_t st)
 {
     if (logn_sub == 13) return launch_cta_one<A, 13, FWD>(pl, data, nvpoly, log_sub, poly_stride, st);
-#if CNTT_CTA14
-    if constexpr (sizeof(typename A::W) == 4) { if (logn_sub == 14) return launch_cta_one<A, 14, FWD>(pl, data, nvpoly, log_sub, poly_stride, st); }
-#endif
+    if constexpr (sizeof(typename A::W) == 4) {
+        if (logn_sub == 14) return launch_cta_one<A, 14, FWD>(pl, data, nvpoly, log_sub, poly_stride, st);
+        if constexpr (r32_size<A, 15>()) { if (logn_sub == 15) return launch_cta_one<A, 15, FWD>(pl, data, nvpoly, log_sub, poly_stride, st); }
+    }
     switch (logn_sub) {
     case 4: return launch_cta_one<A, 4, FWD>(pl, data, nvpoly, log_sub, poly_stride, st);
     case 5: return launch_cta_one<A, 5, FWD>(pl, data, nvpoly, log_sub, poly_stride, st);

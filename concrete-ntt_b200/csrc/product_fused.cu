@@ -172,17 +172,13 @@ static cudaError_t launch_one(const ProductConsts& c, const ProductFusedArgs& a,
     if (nblk > 0x7fffffffull) return cudaErrorInvalidValue;
     if constexpr (FWD) {
         auto kern = k_product_fwd_fused<A, LOGN>;
-        if (Cfg::SMEM_FWD > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_FWD);
-            if (e != cudaSuccess) return e;
-        }
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_FWD);
+        if (e != cudaSuccess) return e;
         kern<<<(unsigned)nblk, Cfg::GP * Cfg::T, Cfg::SMEM_FWD, st>>>(c, d, ntt, standard, mode, bound, batch);
     } else {
         auto kern = k_product_inv_fused<A, LOGN>;
-        if (Cfg::SMEM_XCHG > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_XCHG);
-            if (e != cudaSuccess) return e;
-        }
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_XCHG);
+        if (e != cudaSuccess) return e;
         kern<<<(unsigned)nblk, Cfg::GP * Cfg::T, Cfg::SMEM_XCHG, st>>>(c, d, standard, ntt, mode, batch);
     }
     return cudaGetLastError();

@@ -31,15 +31,21 @@ def _stream_of(t):
 class _Buf:
     """Pointer + shape facts of one argument."""
 
-    def __init__(self, x, itemsize, name):
+    def __init__(self, plan_device, x, itemsize, name):
         self.is_dev = _is_torch(x)
         if self.is_dev:
             if not x.is_cuda:
                 raise TypeError("%s: torch tensors must live on a CUDA device (use numpy for host slices)" % name)
+            if x.is_floating_point() or x.is_complex() or x.dtype == torch.bool:
+                raise TypeError("%s: expected an integer tensor of %d-byte words, got %s" % (name, itemsize, x.dtype))
+            if x.device.index != plan_device:
+                raise TypeError("%s lives on cuda:%s but the plan was created for cuda:%s" % (name, x.device.index, plan_device))
             if not x.is_contiguous():
                 raise ValueError("%s must be contiguous" % name)
             if x.element_size() != itemsize:
                 raise TypeError("%s: expected %d-byte words" % (name, itemsize))
+            if x.data_ptr() % 16:
+                raise ValueError("%s: device batches must be 16-byte aligned (include/cntt_b200.h)" % name)
             self.ptr = x.data_ptr()
             self.shape = tuple(x.shape)
             self.device = x.device.index
@@ -49,6 +55,8 @@ class _Buf:
                 raise TypeError("%s must be a numpy array or a torch CUDA tensor" % name)
             if not x.flags.c_contiguous:
                 raise ValueError("%s must be C-contiguous" % name)
+            if x.dtype.kind not in "ui":
+                raise TypeError("%s: expected an integer array of %d-byte words, got %s" % (name, itemsize, x.dtype))
             if x.dtype.itemsize != itemsize:
                 raise TypeError("%s: expected %d-byte words" % (name, itemsize))
             self.ptr = x.ctypes.data
@@ -92,7 +100,7 @@ class _PrimePlan:
         return self._fn("modulus")(self._h)
 
     def _ntt(self, name, buf):
-        b = _Buf(buf, self._bits // 8, "buf")
+        b = _Buf(self._device, buf, self._bits // 8, "buf")
         if len(b.shape) == 0 or b.shape[-1] != self._n:
             raise ReferencePanic("assert_eq!(buf.len(), self.ntt_size())")
         batch = b.words // self._n
@@ -112,7 +120,7 @@ class _PrimePlan:
 
     def fwd_inv(self, buf):
         """fwd then inv with one upload/download (host slices) -- the round trip of BASELINE config 1/2."""
-        b = _Buf(buf, self._bits // 8, "buf")
+        b = _Buf(self._device, buf, self._bits // 8, "buf")
         if len(b.shape) == 0 or b.shape[-1] != self._n:
             raise ReferencePanic("assert_eq!(buf.len(), self.ntt_size())")
         batch = b.words // self._n
@@ -124,7 +132,7 @@ class _PrimePlan:
         return buf
 
     def _pw(self, name, *arrs):
-        bufs = [_Buf(a, self._bits // 8, "arg%d" % i) for i, a in enumerate(arrs)]
+        bufs = [_Buf(self._device, a, self._bits // 8, "arg%d" % i) for i, a in enumerate(arrs)]
         # izip! truncates to the shortest slice (prime32.rs:397); whole vectors only (prime32.rs:348)
         nwords = min(b.words for b in bufs)
         dev = bufs[0].is_dev
@@ -223,7 +231,7 @@ class _NativePlan:
         return _lib.lib().cntt_native_prime(self._h, i)
 
     def _word_buf(self, x, name):
-        b = _Buf(x, 8 if self._bits == 128 else self._bits // 8, name)
+        b = _Buf(self._device, x, 8 if self._bits == 128 else self._bits // 8, name)
         tail = (self._n, 2) if self._bits == 128 else (self._n,)
         if b.shape[len(b.shape) - len(tail):] != tail:
             raise ReferencePanic("assert_eq!(n, %s.len())" % name)
@@ -231,7 +239,7 @@ class _NativePlan:
         return b
 
     def _planes(self, x, batch):
-        b = _Buf(x, 4, "mod_p")
+        b = _Buf(self._device, x, 4, "mod_p")
         if b.words != self._np * batch * self._n:
             raise ReferencePanic("residue planes must hold num_primes * batch * n words")
         return b
@@ -327,11 +335,11 @@ class _Native52Plan:
         return cache[i]
 
     def _args(self, value, mod_p):
-        v = _Buf(value, self._bits // 8, "value")
+        v = _Buf(self._device, value, self._bits // 8, "value")
         if len(v.shape) == 0 or v.shape[-1] != self._n:
             raise ReferencePanic("assert_eq!(n, value.len())")
         batch = v.words // self._n
-        m = _Buf(mod_p, 8, "mod_p")
+        m = _Buf(self._device, mod_p, 8, "mod_p")
         if m.words != self._np * batch * self._n:
             raise ReferencePanic("residue planes must hold num_primes * batch * n words")
         if not (v.is_dev and m.is_dev):
@@ -356,7 +364,7 @@ class _Native52Plan:
         return value
 
     def negacyclic_polymul(self, prod, lhs, rhs):
-        bufs = [_Buf(x, self._bits // 8, nm) for x, nm in ((prod, "prod"), (lhs, "lhs"), (rhs, "rhs"))]
+        bufs = [_Buf(self._device, x, self._bits // 8, nm) for x, nm in ((prod, "prod"), (lhs, "lhs"), (rhs, "rhs"))]
         for b in bufs:
             if len(b.shape) == 0 or b.shape[-1] != self._n or b.words != bufs[0].words:
                 raise ReferencePanic("assert_eq!(n, lhs.len())")
@@ -439,14 +447,14 @@ class ProductPlan:
         return [_lib.lib().cntt_product_prime(self._h, i) for i in range(c32.value + c64.value)]
 
     def _std(self, x, name):
-        b = _Buf(x, 8, name)
+        b = _Buf(self._device, x, 8, name)
         if len(b.shape) == 0 or b.shape[-1] != self._n:
             raise ReferencePanic("assert_eq!(standard.len(), self.ntt_size())")
         b.batch = b.words // self._n
         return b
 
     def _dom(self, x, name, like=None):
-        b = _Buf(x, 8, name)
+        b = _Buf(self._device, x, 8, name)
         if self._dl == 0:
             b.batch = like.batch if like is not None else 0
             if b.words != 0:

@@ -13,8 +13,9 @@
  * slices concatenated).  Residue planes of the native plans: plane k of polynomial b is
  * mod_p[(k*batch + b)*n + i] (k-th `mod_pk` slice of the reference, concatenated over the batch).
  * 128-bit words are little-endian {lo:u64, hi:u64} pairs, 16-byte aligned (Rust u128 on x86-64).
- * Device batches must be 16-byte aligned; 32-byte aligned batches (cudaMalloc gives 256) also get the 256-bit
- * load / store path of the transform kernels.
+ * Device batches must be 16-byte aligned (CNTT_MISALIGNED otherwise; n >= 16 words keeps every polynomial and residue
+ * plane of an aligned batch aligned); 32-byte aligned batches (cudaMalloc gives 256) also get the 256-bit load / store
+ * path of the transform kernels.
  *
  * Results are bit-identical to the reference on the same inputs (same primitive root, same
  * bit-reversed order, canonical residues, same centred CRT lift).
@@ -42,7 +43,8 @@ typedef enum cntt_status {
     CNTT_CUDA_ERROR = 5,
     CNTT_NULL_POINTER = 6,
     CNTT_UNSUPPORTED = 7,
-    CNTT_PANIC_MODULUS = 8    /* p in {0,1}: the reference panics before validating */
+    CNTT_PANIC_MODULUS = 8,   /* p in {0,1}: the reference panics before validating */
+    CNTT_MISALIGNED = 9       /* a device batch pointer is not 16-byte aligned (checked before any launch) */
 } cntt_status;
 
 const char* cntt_status_string(int status);

@@ -59,31 +59,33 @@ def test_prime64_fwd_inv_all_classes(cntt, oracle, torch_cuda, n):
             assert (host(d, np.uint64) == ref_i).all(), (name, n, batch, "inv")
 
 
-@pytest.mark.parametrize("n,bits", [(8192, 32), (16384, 32), (32768, 32), (65536, 32), (8192, 64), (16384, 64), (65536, 64)])
+@pytest.mark.parametrize("n,bits", [(8192, 32), (16384, 32), (32768, 32), (65536, 32), (131072, 32), (8192, 64), (16384, 64), (32768, 64), (65536, 64)])
 def test_large_n_two_level(cntt, oracle, torch_cuda, n, bits):
-    """N > 4096: strided leading stages + CTA kernel on contiguous blocks == the reference's depth-first
-    recursion (prime32/shoup.rs:637-708).  P0 has v2(P0-1) = 17, Solinas 32."""
+    """N > 4096: one CTA per polynomial (32-bit words up to N = 32768) or strided leading stages + CTA kernel on
+    contiguous blocks == the reference's depth-first recursion (prime32/shoup.rs:637-708).  Every bit class of the
+    reference's dispatch, with primes k 2^17 + 1 (k 2^18 + 1 at N = 131072) so that the 2N-th roots exist."""
     g = rng(n + bits)
+    f = oracle.largest_prime_in_arithmetic_progression64
+    step = 2 * n if n > 32768 else 1 << 17
     if bits == 32:
-        cases = [(1062862849, oracle.Plan32, cntt.prime32.Plan, np.uint32)]
-        if n <= 32768:
-            cases.append((primes32(oracle)["lt31"], oracle.Plan32, cntt.prime32.Plan, np.uint32))
+        windows = [(1 << 29, 1 << 30), (1 << 30, 1 << 31), (1 << 31, 1 << 32)]
+        cases = [(1062862849, oracle.Plan32, cntt.prime32.Plan, np.uint32)] if n <= 65536 else []
+        cases += [(f(step, 1, lo, hi), oracle.Plan32, cntt.prime32.Plan, np.uint32) for lo, hi in windows]
     else:
+        windows = [(1 << 61, 1 << 62), (1 << 62, 1 << 63), (1 << 63, (1 << 64) - 1)]
         cases = [(0xFFFFFFFF00000001, oracle.Plan64, cntt.prime64.Plan, np.uint64)]
-        if n <= 32768:
-            cases.append((primes64(oracle)["lt62"], oracle.Plan64, cntt.prime64.Plan, np.uint64))
+        cases += [(f(step, 1, lo, hi), oracle.Plan64, cntt.prime64.Plan, np.uint64) for lo, hi in windows]
     for p, OP, GP, dt in cases:
         op, gp = OP.try_new(n, p), GP.try_new(n, p)
-        assert (op is None) == (gp is None)
-        if op is None:
-            continue
-        a = rand_mod(g, p, (3, n), dt)
-        ref_f = op.fwd(a.copy())
-        d = dev(torch_cuda, a)
-        gp.fwd(d)
-        assert (host(d, dt) == ref_f).all(), (p, n, "fwd")
-        gp.inv(d)
-        assert (host(d, dt) == op.inv(ref_f.copy())).all(), (p, n, "inv")
+        assert op is not None and gp is not None, (p, n)
+        for batch in (1, 3):
+            a = rand_mod(g, p, (batch, n), dt)
+            ref_f = op.fwd(a.copy())
+            d = dev(torch_cuda, a)
+            gp.fwd(d)
+            assert (host(d, dt) == ref_f).all(), (p, n, "fwd")
+            gp.inv(d)
+            assert (host(d, dt) == op.inv(ref_f.copy())).all(), (p, n, "inv")
 
 
 def test_very_large_n_solinas(cntt, oracle, torch_cuda):
