@@ -57,26 +57,6 @@ def ncu_traffic(direction):
         return None
 
 
-def ncu_pipes(direction):
-    """integer-pipe utilisation of the same kernel from the committed ncu summary (percent of peak, per launch)"""
-    try:
-        want = "1" if direction == "fwd" else "0"
-        cur, out = None, {}
-        keys = {"sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed": "fmaheavy_pct",
-                "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed": "alu_pct",
-                "sm__issue_active.avg.pct_of_peak_sustained_elapsed": "issue_pct"}
-        for line in open(NCU_SUMMARY):
-            if line.startswith("=="):
-                cur = line.split("<", 1)[1].split(">", 1)[0].split(",")[4].strip()
-            elif cur == want:
-                f = line.split()
-                if f and f[0] in keys:
-                    out[keys[f[0]]] = float(f[1])
-        return out or None
-    except Exception:
-        return None
-
-
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -207,20 +187,37 @@ def make_inputs(rank, batch, n, p):
 
 
 # ------------------------------------------------------------------------------------------------------------
-def run_reference(args):
-    """The reference's own CPU algorithm for the path (oracle port: no Rust toolchain exists to build the crate),
-    all host threads, bounded sample of the same workload per step."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+CONFIG = {"workload": WORKLOAD, "n": N_POLY, "batch_per_gpu": BATCH, "prime": "0xFFFFFFFF00000001",
+          "l2": "the 1 GiB batch per GPU is streamed every launch and exceeds the 126 MB L2 (no flush needed)"}
+
+
+def cpu_plan():
+    """The CPU arm's implementation of the path: the AVX-512 / AVX2 port of the reference's SIMD stage loops when the host has
+    the ISA (oracle/cntt_simd.c, bit-checked against the scalar restatement in tests/test_oracle_simd.py), else the scalar
+    restatement.  Returns (plan, description)."""
     from oracle import oracle as O
     try:
         O.build(native=True)
         native = True
     except Exception:
         native = False
-    threads = host_threads()
     plan = O.Plan64.try_new(N_POLY, SOLINAS_P, native=native)
+    isa = getattr(O, "simd_isa", lambda native=False: "scalar")(native)
+    desc = ("C port of concrete-ntt's Solinas path, %s (oracle/%s, gcc -O3 -march=%s, OpenMP over polynomials); the crate itself "
+            "cannot be built here (no cargo)" % ({"avx512": "AVX-512 stage loops as in src/prime64/generic_solinas.rs:132-446",
+                                                 "avx2": "AVX2 stage loops as in src/prime64/generic_solinas.rs:132-446",
+                                                 "scalar": "scalar restatement"}.get(isa, isa),
+                                                "cntt_simd.c" if isa != "scalar" else "cntt_oracle.c", "native" if native else "x86-64-v3"))
+    return plan, desc, isa
+
+
+def run_reference(args):
+    """The reference's own CPU algorithm for the path, all host threads, bounded sample of the same workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    plan, desc, isa = cpu_plan()
     sample = 4096
     buf = make_inputs(0, sample, N_POLY, SOLINAS_P)
     for _ in range(max(1, args.warmup)):
@@ -236,11 +233,9 @@ def run_reference(args):
         "impl": "reference", "metric": "NTTs/sec", "value": value, "unit": "NTT/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n": N_POLY, "batch_per_step": sample, "prime": "0xFFFFFFFF00000001"},
-        "cpu_baseline": {"value": value, "unit": "NTT/s", "cores": threads, "kind": "port",
-                         "sample": "%d polynomials of the workload per step (fwd+inv), C restatement of concrete-ntt's scalar "
-                                   "Solinas path (oracle/cntt_oracle.c, gcc -O3 -march=%s, OpenMP over polynomials)"
-                                   % (sample, "native" if native else "x86-64-v3")},
+        "config": dict(CONFIG), "sample_batch_per_step": sample,
+        "cpu_baseline": {"value": value, "unit": "NTT/s", "cores": threads, "kind": "port", "isa": isa,
+                         "sample": "%d polynomials of the workload per step (fwd+inv); %s" % (sample, desc)},
         "e2e": {"value": value, "unit": "NTT/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -249,14 +244,8 @@ def run_reference(args):
 
 def cpu_baseline_leg():
     """Bounded sample of the workload on the host cores (rank 0, N=1 only): ~10-20 core-seconds."""
-    from oracle import oracle as O
-    try:
-        O.build(native=True)
-        native = True
-    except Exception:
-        native = False
     threads = host_threads()
-    plan = O.Plan64.try_new(N_POLY, SOLINAS_P, native=native)
+    plan, desc, isa = cpu_plan()
     probe = make_inputs(7, 256, N_POLY, SOLINAS_P)
     t0 = time.perf_counter()
     plan.fwd_batch(probe, threads)
@@ -268,10 +257,8 @@ def cpu_baseline_leg():
     plan.fwd_batch(buf, threads)
     plan.inv_batch(buf, threads)
     dt = time.perf_counter() - t0
-    return {"value": 2.0 * sample / dt, "unit": "NTT/s", "cores": threads, "kind": "port",
-            "sample": "%d of the %d polynomials, fwd+inv once (%.1f core-s); C restatement of concrete-ntt's scalar Solinas "
-                      "path (oracle/cntt_oracle.c, gcc -O3 -march=%s, OpenMP over polynomials)"
-                      % (sample, BATCH, dt * threads, "native" if native else "x86-64-v3")}
+    return {"value": 2.0 * sample / dt, "unit": "NTT/s", "cores": threads, "kind": "port", "isa": isa,
+            "sample": "%d of the %d polynomials, fwd+inv once (%.1f core-s); %s" % (sample, BATCH, dt * threads, desc)}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -290,23 +277,18 @@ def run_ours(args):
     cntt = importlib.import_module("concrete-ntt_b200")
     plan = cntt.prime64.Plan.try_new(N_POLY, SOLINAS_P, device=local)
     assert plan is not None
+    peak, peak_src = peaks()
 
     host = make_inputs(rank, BATCH, N_POLY, SOLINAS_P)
     pinned = torch.empty((BATCH, N_POLY), dtype=torch.int64).pin_memory()
     pinned.numpy().view(np.uint64)[...] = host
     d = pinned.cuda(non_blocking=False)
+    d_orig = d.clone()
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
     lib = cntt._lib.lib()
     h = plan._h
     dptr = d.data_ptr()
-
-    def step():
-        st = lib.cntt_prime64_fwd(h, dptr, BATCH, sptr)
-        st |= lib.cntt_prime64_inv(h, dptr, BATCH, sptr)
-        if st:
-            raise RuntimeError("kernel launch failed: " + lib.cntt_last_cuda_error().decode())
-        # keep values in [0, p): inv(fwd(x)) = N x is canonical already, so the next step is a valid input
 
     def barrier():
         torch.cuda.synchronize()
@@ -314,8 +296,30 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
-        step()
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    def verify(buf, rounds, what):
+        """inv(fwd(x)) = N x, so after `rounds` round trips `rounds` normalisations must give the input back, bit for bit:
+        a launch that wrote garbage cannot produce a bench line."""
+        for _ in range(rounds):
+            plan.normalize(buf)
+        torch.cuda.synchronize()
+        if not torch.equal(buf, d_orig):
+            bad = int((buf != d_orig).sum().item())
+            raise RuntimeError("bench.py: %s does not round-trip (%d of %d words differ after %d fwd+inv steps)" % (what, bad, buf.numel(), rounds))
+        return "%d x (fwd, inv) then %d x normalize == input, all %d words" % (rounds, rounds, buf.numel())
+
+    W = max(3, args.warmup)
+    for _ in range(W):
+        st = lib.cntt_prime64_fwd(h, dptr, BATCH, sptr)
+        st |= lib.cntt_prime64_inv(h, dptr, BATCH, sptr)
+        if st:
+            raise RuntimeError("kernel launch failed: " + lib.cntt_last_cuda_error().decode())
     barrier()
 
     sampler = ClockSampler(local)
@@ -340,30 +344,48 @@ def run_ours(args):
     fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     inv_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+    total_ms = max_over_ranks(total_ms)
     value = world * 2.0 * BATCH * K / (total_ms * 1e-3)
+    checked = {"device_resident": verify(d, W + K, "the timed device buffer")}
 
-    # ---- end to end through the host-slice C-ABI call: pinned host -> H2D -> fwd -> inv -> D2H, every step
+    # ---- end to end through the reference's call shape: plan.fwd(buf); plan.inv(buf) on a HOST slice -- two C-ABI calls per
+    #      step, each staging its own H2D and D2H (cntt_prime64_fwd_host, cntt_prime64_inv_host).  The fused
+    #      cntt_prime64_fwd_inv_host (one upload + one download for both transforms, an extension) is reported beside it.
     hview = pinned.numpy().view(np.uint64)
-    hview[...] = host
-    ke = max(2, min(K, 6))
-    plan.fwd_inv(hview)
-    hview[...] = host
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(ke):
-        plan.fwd_inv(hview)       # synchronous: returns after the D2H of the last chunk
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * 2.0 * BATCH * ke / e2e_s
     nbytes = BATCH * N_POLY * 8
+    ke = max(2, min(K, 4))
+
+    def e2e(fn, rounds_per_call):
+        hview[...] = host
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            fn()                   # synchronous: returns after the D2H of the last chunk
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        d.copy_(pinned)
+        return world * 2.0 * BATCH * ke / dt, verify(d, (ke + 1) * rounds_per_call, "the end-to-end host buffer")
+
+    def two_calls():
+        plan.fwd(hview)
+        plan.inv(hview)
+
+    e2e_value, checked["e2e"] = e2e(two_calls, 1)
+    e2e_fused, checked["e2e_fused"] = e2e(lambda: plan.fwd_inv(hview), 1)
+    del d_orig
+
+    def timeit(fn, reps, warm=3):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1) / reps)
 
     # ---- secondary figure of the same metric line: native64 polymul (BASELINE configs[2]), device-resident
     extra = {}
@@ -373,22 +395,7 @@ def run_ours(args):
         lhs = torch.randint(-2**63, 2**63 - 1, (BATCH, N_POLY), dtype=torch.int64, device="cuda", generator=g)
         rhs = torch.randint(-2**63, 2**63 - 1, (BATCH, N_POLY), dtype=torch.int64, device="cuda", generator=g)
         prod = torch.empty_like(lhs)
-        for _ in range(2):
-            npl.negacyclic_polymul(prod, lhs, rhs)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kp = 5
-        e0.record(stream)
-        for _ in range(kp):
-            npl.negacyclic_polymul(prod, lhs, rhs)
-        e1.record(stream)
-        barrier()
-        pm_ms = e0.elapsed_time(e1) / kp
-        if world > 1:
-            t = torch.tensor([pm_ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            pm_ms = float(t.item())
-        peak, _ = peaks()
+        pm_ms = timeit(lambda: npl.negacyclic_polymul(prod, lhs, rhs), 5, 2)
         extra["native64_polymul_n2048_b65536"] = {
             "polymuls_per_s": world * BATCH / (pm_ms * 1e-3), "ms_per_batch": pm_ms,
             "hbm_frac": (3 * N_POLY * 8 * BATCH / (pm_ms * 1e-3) / 1e9) / peak,
@@ -403,55 +410,29 @@ def run_ours(args):
         pl32 = cntt.prime32.Plan.try_new(1024, p0, device=local)
         g = torch.Generator(device="cuda").manual_seed(99 + rank)
         d32 = torch.randint(0, p0, (BATCH, 1024), dtype=torch.int32, device="cuda", generator=g)
-        res = {}
-        for name, fn in (("fwd", pl32.fwd), ("inv", pl32.inv)):
-            for _ in range(3):
-                fn(d32)
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for _ in range(10):
-                fn(d32)
-            e1.record(stream)
-            barrier()
-            res[name] = e0.elapsed_time(e1) / 10
-        peak, _ = peaks()
+        res = {"fwd": timeit(lambda: pl32.fwd(d32), 10), "inv": timeit(lambda: pl32.inv(d32), 10)}
         extra["prime32_n1024_p0_b65536"] = {
             "fwd_ntts_per_s": BATCH / (res["fwd"] * 1e-3), "inv_ntts_per_s": BATCH / (res["inv"] * 1e-3),
             "hbm_frac_fwd": 2 * 1024 * 4 * BATCH / (res["fwd"] * 1e-3) / 1e9 / peak,
-            "hbm_frac_inv": 2 * 1024 * 4 * BATCH / (res["inv"] * 1e-3) / 1e9 / peak, "per": "GPU (rank 0)"}
+            "hbm_frac_inv": 2 * 1024 * 4 * BATCH / (res["inv"] * 1e-3) / 1e9 / peak, "per": "GPU"}
         del d32
     except Exception as e:
         extra["prime32_error"] = repr(e)
 
     # ---- BASELINE configs[3] and configs[4], device-resident: native128 N=4096 batch 8192 per GPU, and native_binary64
     #      N=65536 (extended plan) with the batch of 1024 split over the ranks
-    def time_polymul(plan, shape, binary, reps=5):
+    def time_polymul(pplan, shape, binary, reps=5):
         g = torch.Generator(device="cuda").manual_seed(4321 + rank)
         a = torch.randint(-2**63, 2**63 - 1, shape, dtype=torch.int64, device="cuda", generator=g)
         b = torch.randint(-2**63, 2**63 - 1, shape, dtype=torch.int64, device="cuda", generator=g)
         if binary:
             b &= 1
         out = torch.empty_like(a)
-        for _ in range(2):
-            plan.negacyclic_polymul(out, a, b)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(reps):
-            plan.negacyclic_polymul(out, a, b)
-        e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1) / reps
-        if world > 1:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return timeit(lambda: pplan.negacyclic_polymul(out, a, b), reps, 2)
     try:
         ms = time_polymul(cntt.native128.Plan32.try_new(4096, device=local), (8192, 4096, 2), False)
         extra["native128_polymul_n4096_b8192"] = {"polymuls_per_s": world * 8192 / (ms * 1e-3), "ms_per_batch": ms,
-                                                  "hbm_frac": (3 * 4096 * 16 * 8192 / (ms * 1e-3) / 1e9) / peaks()[0]}
+                                                  "hbm_frac": (3 * 4096 * 16 * 8192 / (ms * 1e-3) / 1e9) / peak}
     except Exception as e:
         extra["native128_polymul_error"] = repr(e)
     try:
@@ -459,37 +440,80 @@ def run_ours(args):
         ms = time_polymul(cntt.native_binary64.Plan32.try_new_extended(65536, device=local), (per, 65536), True)
         extra["native_binary64_polymul_n65536_b1024_total"] = {"polymuls_per_s": world * per / (ms * 1e-3), "ms_per_batch": ms,
                                                                "batch_per_gpu": per, "scaling": "strong",
-                                                               "hbm_frac_per_gpu": (3 * 65536 * 8 * per / (ms * 1e-3) / 1e9) / peaks()[0]}
+                                                               "hbm_frac_per_gpu": (3 * 65536 * 8 * per / (ms * 1e-3) / 1e9) / peak}
     except Exception as e:
         extra["native_binary64_polymul_error"] = repr(e)
 
+    # ---- the metric over N = 2^10 .. 2^16 (BASELINE.json "metric"): prime32 (P0), prime64 Solinas and native64 polymul, device-
+    #      resident, 2^27 words per batch (2^26 for the polymul operands), per GPU, with the HBM fraction of each.  Every rank
+    #      runs it (weak scaling: the figures are per GPU, max time over ranks).
+    sweep = {}
+    for logn in range(10, 17):
+        n = 1 << logn
+        row = {}
+        try:
+            b32 = (1 << 27) >> logn
+            pl = cntt.prime32.Plan.try_new(n, 1062862849, device=local)
+            g = torch.Generator(device="cuda").manual_seed(7 + rank)
+            x = torch.randint(0, 1062862849, (b32, n), dtype=torch.int32, device="cuda", generator=g)
+            f, i = timeit(lambda: pl.fwd(x), 5), timeit(lambda: pl.inv(x), 5)
+            row["prime32"] = {"batch": b32, "fwd_ntts_per_s": b32 / (f * 1e-3), "inv_ntts_per_s": b32 / (i * 1e-3),
+                              "hbm_frac_fwd": 2 * n * 4 * b32 / (f * 1e-3) / 1e9 / peak, "hbm_frac_inv": 2 * n * 4 * b32 / (i * 1e-3) / 1e9 / peak}
+            del x, pl
+            pl = cntt.prime64.Plan.try_new(n, SOLINAS_P, device=local)
+            x = torch.randint(0, 2**62, (b32, n), dtype=torch.int64, device="cuda", generator=g)
+            f, i = timeit(lambda: pl.fwd(x), 5), timeit(lambda: pl.inv(x), 5)
+            row["prime64_solinas"] = {"batch": b32, "fwd_ntts_per_s": b32 / (f * 1e-3), "inv_ntts_per_s": b32 / (i * 1e-3),
+                                      "hbm_frac_fwd": 2 * n * 8 * b32 / (f * 1e-3) / 1e9 / peak, "hbm_frac_inv": 2 * n * 8 * b32 / (i * 1e-3) / 1e9 / peak}
+            del x, pl
+            bp = (1 << 26) >> logn
+            pp = cntt.native64.Plan32.try_new(n, device=local)
+            ext = pp is None
+            if ext:   # the reference has no native64 plan at N = 65536 (P1 - 1 = 2^16 odd): extended prime set, DESIGN.md section 8
+                pp = cntt.native64.Plan32.try_new_extended(n, device=local)
+            a = torch.randint(-2**63, 2**63 - 1, (bp, n), dtype=torch.int64, device="cuda", generator=g)
+            b = torch.randint(-2**63, 2**63 - 1, (bp, n), dtype=torch.int64, device="cuda", generator=g)
+            o = torch.empty_like(a)
+            ms = timeit(lambda: pp.negacyclic_polymul(o, a, b), 3, 2)
+            row["native64_polymul"] = {"batch": bp, "polymuls_per_s": bp / (ms * 1e-3), "hbm_frac": 3 * n * 8 * bp / (ms * 1e-3) / 1e9 / peak,
+                                       "butterflies_per_clk_per_sm": 15 * (n // 2) * logn * bp / (ms * 1e-3) / 148 / 1.965e9, "extended_primes": ext}
+            del a, b, o, pp
+        except Exception as e:
+            row["error"] = repr(e)
+        sweep["n%d" % n] = row
+    extra["sweep_per_gpu"] = sweep
+
     if rank == 0:
-        peak, peak_src = peaks()
         slow_ms, which = (fwd_ms, "fwd") if fwd_ms >= inv_ms else (inv_ms, "inv")
         achieved = ALG_BYTES_PER_NTT * BATCH / (slow_ms * 1e-3) / 1e9
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        bf = 11264.0 * BATCH / (slow_ms * 1e-3) / 148 / (mhz * 1e6)
         line = {
-            "metric": "NTTs/sec", "value": value, "unit": "NTT/s", "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
+            "metric": "NTTs/sec", "value": value, "unit": "NTT/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n": N_POLY, "batch_per_gpu": BATCH, "prime": "0xFFFFFFFF00000001",
-                       "l2": "the 1 GiB batch per GPU is streamed every launch and exceeds the 126 MB L2 (no flush needed)"},
+            "dtype": "u64", "data": "synthetic", "config": dict(CONFIG),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "NTT/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-                    "steps": ke, "api": "cntt_prime64_fwd_inv_host (pinned host slice, chunked double-buffered staging)"},
+            "e2e": {"value": e2e_value, "unit": "NTT/s", "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": 2 * nbytes, "steps": ke,
+                    "api": "the reference's call shape, plan.fwd(buf); plan.inv(buf) on a pinned host slice = cntt_prime64_fwd_host + "
+                           "cntt_prime64_inv_host (each stages its own chunked, double-buffered H2D and D2H)"},
+            "e2e_fused": {"value": e2e_fused, "unit": "NTT/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": ke,
+                          "api": "cntt_prime64_fwd_inv_host (extension: both transforms between one upload and one download)"},
+            "checked": checked,
             "gpu_launches": 2 * K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(which), "traffic_source": "profiles/r01_kernels_v7/ncu_ntt64s_2048.txt (ncu --set full, dram read+write bytes per launch)", "kernel": "k_ntt_cta<A64S,11,4> (%s)" % which,
+                         "traffic": ncu_traffic(which), "traffic_source": os.path.relpath(NCU_SUMMARY, ROOT) + " (ncu --set full, dram read+write bytes per launch)",
+                         "kernel": "k_ntt_cta<A64S,11,4> (%s)" % which,
                          "peak_source": peak_src, "ms_per_launch": {"fwd": fwd_ms, "inv": inv_ms},
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_NTT * BATCH,
-                         "int_pipes": ncu_pipes(which),
-                         # integer-pipe roofline of the same launch: 11 levels x 1024 butterflies per NTT; a Goldilocks butterfly
-                         # occupies the multiply pipe for 41 and the ALU for 38 cycles per warp, i.e. at
-                         # most 4 schedulers x 32 lanes / 41 = 3.1 butterflies per clock and SM
-                         "int_roofline": {"achieved": 11264.0 * BATCH / (slow_ms * 1e-3) / 148 / ((clocks or {}).get("sm_mhz") or 1965.0) / 1e6,
-                                          "peak": 128.0 / 41.0, "unit": "butterflies/clk/SM",
-                                          "frac": 11264.0 * BATCH / (slow_ms * 1e-3) / 148 / ((clocks or {}).get("sm_mhz") or 1965.0) / 1e6 / (128.0 / 41.0)},
-                         "note": "integer-pipe bound kernel (multiply pipe and ALU ~65-75 % busy at once, ncu); the integer "
-                                 "ceiling of this butterfly is 80 M NTT/s = 40 % of the HBM ceiling, see DESIGN.md section 4"},
+                         # integer roofline of the same launch (11 levels x 1024 butterflies per NTT).  Peak = the multiply floor: a
+                         # 64 x 64 -> 128-bit product is four 32 x 32 -> 64 products and IMAD.WIDE.U32 issues at 24.4 per clock and SM
+                         # (profiles/r01_ubench_int_pipes.txt), i.e. 6.1 butterflies per clock and SM if nothing else cost anything.  The
+                         # butterfly as shipped, alone in registers, reaches 2.40 (profiles/r02_ubench_gold_bf.txt).
+                         "int_roofline": {"achieved": bf, "peak": 24.4 / 4, "unit": "butterflies/clk/SM", "frac": bf / (24.4 / 4),
+                                          "peak_source": "4-product multiply floor, measured IMAD.WIDE.U32 rate / 4",
+                                          "butterfly_alone": 2.40, "frac_of_butterfly_alone": bf / 2.40},
+                         "note": "integer-bound kernel: ALU and multiply pipe ~70-75 % busy at once (ncu summary under profiles/); "
+                                 "the HBM fraction cannot exceed ~0.4 for this prime on CUDA cores, see DESIGN.md section 4"},
             "extra": extra,
         }
         if world == 1:

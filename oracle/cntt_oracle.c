@@ -1408,17 +1408,23 @@ EXPORT void o_plan32_inv_batch(const o_plan32 *pl, u32 *buf, size_t batch, int n
     PAR_FOR
     for (long b = 0; b < (long)batch; b++) o_plan32_inv(pl, buf + (size_t)b * pl->n);
 }
+/* CPU-baseline legs of bench.py: the SIMD port of the reference's vector path where the host has the ISA (cntt_simd.c) */
+#include "cntt_simd.c"
+static int g_batch_isa = -1; /* -1 best available, 0 scalar, 2 AVX2, 3 AVX-512 */
+EXPORT void o_set_batch_isa(int isa) { g_batch_isa = isa; }
 EXPORT void o_plan64_fwd_batch(const o_plan64 *pl, u64 *buf, size_t batch, int nthreads)
 {
     (void)nthreads;
+    const int isa = g_batch_isa;
     PAR_FOR
-    for (long b = 0; b < (long)batch; b++) o_plan64_fwd(pl, buf + (size_t)b * pl->n);
+    for (long b = 0; b < (long)batch; b++) o_plan64_fwd_simd(pl, buf + (size_t)b * pl->n, isa);
 }
 EXPORT void o_plan64_inv_batch(const o_plan64 *pl, u64 *buf, size_t batch, int nthreads)
 {
     (void)nthreads;
+    const int isa = g_batch_isa;
     PAR_FOR
-    for (long b = 0; b < (long)batch; b++) o_plan64_inv(pl, buf + (size_t)b * pl->n);
+    for (long b = 0; b < (long)batch; b++) o_plan64_inv_simd(pl, buf + (size_t)b * pl->n, isa);
 }
 EXPORT void o_native_polymul_batch(const o_native *nt, void *prod, const void *lhs, const void *rhs, size_t batch,
                                    int nthreads)

@@ -18,8 +18,8 @@ def build(native=False):
     """Compile the oracle if the shared object is missing (gcc is in the image)."""
     name = "libcntt_oracle_native.so" if native else "libcntt_oracle.so"
     path = os.path.join(_HERE, name)
-    src = os.path.join(_HERE, "cntt_oracle.c")
-    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("cntt_oracle.c", "cntt_simd.c")]
+    if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "native" if native else "all"],
                               stdout=subprocess.DEVNULL)
     return path
@@ -79,6 +79,10 @@ def _load(native=False):
         "o_plan32_inv_batch": (None, [vp, vp, sz, C.c_int]),
         "o_plan64_fwd_batch": (None, [vp, vp, sz, C.c_int]),
         "o_plan64_inv_batch": (None, [vp, vp, sz, C.c_int]),
+        "o_simd_isa": (C.c_int, []),
+        "o_set_batch_isa": (None, [C.c_int]),
+        "o_plan64_fwd_simd": (None, [vp, vp, C.c_int]),
+        "o_plan64_inv_simd": (None, [vp, vp, C.c_int]),
         "o_native_polymul_batch": (None, [vp, vp, vp, vp, sz, C.c_int]),
     }
     for name, (res, args) in sig.items():
@@ -228,6 +232,34 @@ class Plan64(_PrimePlan):
     """prime64::Plan (src/prime64.rs:222-1129)"""
     _pre = "o_plan64"
     _dt = np.dtype(np.uint64)
+
+    def _simd(self, name, buf, isa):
+        self._chk(buf)
+        assert buf.shape[-1] == self.n
+        fn = getattr(self._L, "o_plan64_%s_simd" % name)
+        for row in buf.reshape(-1, self.n):
+            fn(self._h, _ptr(row), ISA_CODES[isa])
+        return buf
+
+    def fwd_simd(self, buf, isa="best"):
+        """Plan::fwd through the AVX-512 / AVX2 port of the reference's vector path (cntt_simd.c; Solinas only)"""
+        return self._simd("fwd", buf, isa)
+
+    def inv_simd(self, buf, isa="best"):
+        return self._simd("inv", buf, isa)
+
+
+ISA_CODES = {"best": -1, "scalar": 0, "avx2": 2, "avx512": 3}
+
+
+def simd_isa(native=False):
+    """widest ISA of cntt_simd.c this host can run: 'avx512', 'avx2' or 'scalar'"""
+    return {3: "avx512", 2: "avx2"}.get(lib(native).o_simd_isa(), "scalar")
+
+
+def set_batch_isa(isa, native=False):
+    """ISA used by the *_batch entry points (the CPU-baseline legs of bench.py): 'best', 'scalar', 'avx2', 'avx512'"""
+    lib(native).o_set_batch_isa(ISA_CODES[isa])
 
 
 SOLINAS_P = 0xFFFFFFFF00000001
