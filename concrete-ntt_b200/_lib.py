@@ -67,6 +67,9 @@ SIGNATURES.update({
     "cntt_native52_fwd": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "cntt_native52_fwd_binary": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "cntt_native52_inv": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "cntt_native52_fwd_host": (_int, [_vp, _vp, _vp, _sz, _sz]),
+    "cntt_native52_fwd_binary_host": (_int, [_vp, _vp, _vp, _sz, _sz]),
+    "cntt_native52_inv_host": (_int, [_vp, _vp, _vp, _sz, _sz]),
     "cntt_native52_polymul": (_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
     "cntt_native52_polymul_host": (_int, [_vp, _vp, _vp, _vp, _sz, _sz]),
     "cntt_product_plan_new": (_int, [_sz, _u64, C.POINTER(_u64), _sz, _int, C.POINTER(_vp)]),

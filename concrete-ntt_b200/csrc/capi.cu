@@ -1075,6 +1075,50 @@ CNTT_API int cntt_native52_inv(const cntt_native52_plan* pl, void* d_value, uint
     CU(cudaGetLastError());
     return CNTT_OK;
 }
+// host-slice flavours of Plan52::fwd / fwd_binary / inv (the reference's call shape, src/native64.rs:1108-1141), staged through
+// the arena of the inner Plan32 handle: what = 0 fwd, 1 fwd_binary, 2 inv (planes clobbered and returned, like cntt_native_inv_host)
+static int native52_split_host(const cntt_native52_plan* pl, void* h_value, uint64_t* h_mod_p, size_t len, size_t batch, int what)
+{
+    if (!pl || ((!h_value || !h_mod_p) && len)) return CNTT_NULL_POINTER;
+    if (len != pl->n * batch) return CNTT_LENGTH_MISMATCH;
+    if (what == 1 && !pl->binary) return CNTT_UNSUPPORTED;
+    if (batch == 0) return CNTT_OK;
+    GUARD(pl->device);
+    Staging& stg = pl->inner->stg;
+    std::lock_guard<std::mutex> lk(stg.mu);
+    const size_t vbytes = len * (size_t)native_word_bytes(pl->inner->kind);
+    const size_t vpad = (vbytes + 15) & ~(size_t)15;
+    const size_t pbytes = (size_t)pl->c.np * len * sizeof(uint64_t);
+    CU(stg.ensure(vpad + pbytes));
+    char* dv = static_cast<char*>(stg.buf);
+    uint64_t* dp = reinterpret_cast<uint64_t*>(dv + vpad);
+    cudaStream_t st = stg.stream;
+    int rc;
+    if (what <= 1) {
+        CU(cudaMemcpyAsync(dv, h_value, vbytes, cudaMemcpyHostToDevice, st));
+        if ((rc = native52_fwd(pl, dv, dp, batch, what == 1, st)) != CNTT_OK) return rc;
+        CU(cudaMemcpyAsync(h_mod_p, dp, pbytes, cudaMemcpyDeviceToHost, st));
+    } else {
+        CU(cudaMemcpyAsync(dp, h_mod_p, pbytes, cudaMemcpyHostToDevice, st));
+        if ((rc = cntt_native52_inv(pl, dv, dp, batch, st)) != CNTT_OK) return rc;
+        CU(cudaMemcpyAsync(h_value, dv, vbytes, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h_mod_p, dp, pbytes, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return CNTT_OK;
+}
+CNTT_API int cntt_native52_fwd_host(const cntt_native52_plan* pl, const void* h_value, uint64_t* h_mod_p, size_t len, size_t batch)
+{
+    return native52_split_host(pl, const_cast<void*>(h_value), h_mod_p, len, batch, 0);
+}
+CNTT_API int cntt_native52_fwd_binary_host(const cntt_native52_plan* pl, const void* h_value, uint64_t* h_mod_p, size_t len, size_t batch)
+{
+    return native52_split_host(pl, const_cast<void*>(h_value), h_mod_p, len, batch, 1);
+}
+CNTT_API int cntt_native52_inv_host(const cntt_native52_plan* pl, void* h_value, uint64_t* h_mod_p, size_t len, size_t batch)
+{
+    return native52_split_host(pl, h_value, h_mod_p, len, batch, 2);
+}
 CNTT_API int cntt_native52_polymul(const cntt_native52_plan* pl, void* d_prod, const void* d_lhs, const void* d_rhs, size_t batch, void* stream)
 {
     if (!pl) return CNTT_NULL_POINTER;

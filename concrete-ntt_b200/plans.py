@@ -290,8 +290,7 @@ class _Native52Plan:
     """native32 / native64 / native_binary32 / native_binary64 ::Plan52 (src/native64.rs:29-34,1072-1165 and twins): the
     same plans on 2 / 3 / 1 / 2 ~50-bit primes (primes52) with uint64 residue planes, shape (num_primes, batch..., n).
     In the reference the type needs feature = "nightly" and try_new is None without AVX-512 IFMA; here it is always
-    available.  fwd / fwd_binary / inv run on device tensors; negacyclic_polymul takes device tensors or host arrays and
-    returns exactly what Plan32 returns."""
+    available.  Every method takes device tensors or host arrays; negacyclic_polymul returns exactly what Plan32 returns."""
     _bits = None
     _binary = False
 
@@ -342,25 +341,30 @@ class _Native52Plan:
         m = _Buf(self._device, mod_p, 8, "mod_p")
         if m.words != self._np * batch * self._n:
             raise ReferencePanic("residue planes must hold num_primes * batch * n words")
-        if not (v.is_dev and m.is_dev):
-            raise TypeError("Plan52 fwd/inv operate on device-resident tensors")
+        if v.is_dev != m.is_dev:
+            raise TypeError("value and mod_p must be on the same side (both device tensors or both host arrays)")
         return v, m, batch
 
-    def fwd(self, value, mod_p):
+    def _run(self, name, value, mod_p):
         v, m, batch = self._args(value, mod_p)
-        check(_lib.lib().cntt_native52_fwd(self._h, v.ptr, m.ptr, batch, _stream_of(v.t)))
+        l = _lib.lib()
+        if v.is_dev:
+            check(getattr(l, "cntt_native52_" + name)(self._h, v.ptr, m.ptr, batch, _stream_of(v.t)))
+        else:   # the reference's host-slice call shape (src/native64.rs:1108-1141)
+            check(getattr(l, "cntt_native52_%s_host" % name)(self._h, v.ptr, m.ptr, batch * self._n, batch))
+
+    def fwd(self, value, mod_p):
+        self._run("fwd", value, mod_p)
         return mod_p
 
     def fwd_binary(self, value, mod_p):
         if not self._binary:
             raise AttributeError("fwd_binary exists only on native_binary* plans")
-        v, m, batch = self._args(value, mod_p)
-        check(_lib.lib().cntt_native52_fwd_binary(self._h, v.ptr, m.ptr, batch, _stream_of(v.t)))
+        self._run("fwd_binary", value, mod_p)
         return mod_p
 
     def inv(self, value, mod_p):
-        v, m, batch = self._args(value, mod_p)
-        check(_lib.lib().cntt_native52_inv(self._h, v.ptr, m.ptr, batch, _stream_of(v.t)))
+        self._run("inv", value, mod_p)
         return value
 
     def negacyclic_polymul(self, prod, lhs, rhs):

@@ -169,6 +169,11 @@ uint64_t cntt_native52_prime(const cntt_native52_plan* plan, int i);          /*
 int cntt_native52_fwd(const cntt_native52_plan* plan, const void* d_value, uint64_t* d_mod_p, size_t batch, void* stream);
 int cntt_native52_fwd_binary(const cntt_native52_plan* plan, const void* d_value, uint64_t* d_mod_p, size_t batch, void* stream);
 int cntt_native52_inv(const cntt_native52_plan* plan, void* d_value, uint64_t* d_mod_p, size_t batch, void* stream);
+/* host-slice flavours (the reference's call shape): len = words in value = n * batch, plane k of polynomial b at
+ * h_mod_p[(k * batch + b) * n]; inv returns the clobbered planes too */
+int cntt_native52_fwd_host(const cntt_native52_plan* plan, const void* h_value, uint64_t* h_mod_p, size_t len, size_t batch);
+int cntt_native52_fwd_binary_host(const cntt_native52_plan* plan, const void* h_value, uint64_t* h_mod_p, size_t len, size_t batch);
+int cntt_native52_inv_host(const cntt_native52_plan* plan, void* h_value, uint64_t* h_mod_p, size_t len, size_t batch);
 int cntt_native52_polymul(const cntt_native52_plan* plan, void* d_prod, const void* d_lhs, const void* d_rhs, size_t batch, void* stream);
 int cntt_native52_polymul_host(const cntt_native52_plan* plan, void* h_prod, const void* h_lhs, const void* h_rhs, size_t len, size_t batch);
 

@@ -14,6 +14,7 @@ pub const CUDA_ERROR: c_int = 5;
 pub const NULL_POINTER: c_int = 6;
 pub const UNSUPPORTED: c_int = 7;
 pub const PANIC_MODULUS: c_int = 8; // Div32::new / Div64::new assert (divisor > 1) -> panic
+pub const MISALIGNED: c_int = 9; // a device batch pointer is not 16-byte aligned
 
 pub type Stream = *mut c_void; // cudaStream_t
 
@@ -86,6 +87,9 @@ extern "C" {
     pub fn cntt_native52_fwd(plan: *const Native52Plan, d_value: *const c_void, d_mod_p: *mut u64, batch: usize, stream: Stream) -> c_int;
     pub fn cntt_native52_fwd_binary(plan: *const Native52Plan, d_value: *const c_void, d_mod_p: *mut u64, batch: usize, stream: Stream) -> c_int;
     pub fn cntt_native52_inv(plan: *const Native52Plan, d_value: *mut c_void, d_mod_p: *mut u64, batch: usize, stream: Stream) -> c_int;
+    pub fn cntt_native52_fwd_host(plan: *const Native52Plan, h_value: *const c_void, h_mod_p: *mut u64, len: usize, batch: usize) -> c_int;
+    pub fn cntt_native52_fwd_binary_host(plan: *const Native52Plan, h_value: *const c_void, h_mod_p: *mut u64, len: usize, batch: usize) -> c_int;
+    pub fn cntt_native52_inv_host(plan: *const Native52Plan, h_value: *mut c_void, h_mod_p: *mut u64, len: usize, batch: usize) -> c_int;
     pub fn cntt_native52_polymul(plan: *const Native52Plan, d_prod: *mut c_void, d_lhs: *const c_void, d_rhs: *const c_void, batch: usize, stream: Stream) -> c_int;
     pub fn cntt_native52_polymul_host(plan: *const Native52Plan, h_prod: *mut c_void, h_lhs: *const c_void, h_rhs: *const c_void, len: usize, batch: usize) -> c_int;
 

@@ -337,7 +337,7 @@ def test_split_fwd_inv_host_slices(cntt, oracle, bits, binary):
 
 
 @pytest.mark.parametrize("bits,binary", [(32, False), (64, False), (32, True), (64, True)])
-@pytest.mark.parametrize("n", [64, 1024])
+@pytest.mark.parametrize("n", [32, 64, 1024, 4096, 16384])
 def test_plan52(cntt, oracle, torch_cuda, bits, binary, n):
     """Plan52 twins (primes52, u64 residue planes over prime64 plans): fwd / fwd_binary planes and inv lift against the
     oracle restatement, inv on arbitrary canonical residues (sign rule v_top > P_top / 2), and negacyclic_polymul
@@ -386,3 +386,16 @@ def test_plan52(cntt, oracle, torch_cuda, bits, binary, n):
     out2 = torch.empty_like(dp)
     gp.inv(out2, pl_)
     assert (host(out2, wdt) == p32).all()
+    # host-slice flavours (the reference's call shape): same planes, same lift, planes clobbered like the device call
+    hplanes = np.zeros((npz, batch, n), np.uint64)
+    gp.fwd(val, hplanes)
+    assert (hplanes == ref).all()
+    if binary:
+        gp.fwd_binary(bval, hplanes)
+        assert (hplanes == np.stack([op.fwd(v, binary_copy=True) for v in bval], axis=1)).all()
+    hfw, hout = fw.copy(), np.zeros((batch, n), wdt)
+    gp.inv(hout, hfw)
+    assert (hout == want).all()
+    dfw = dev(torch, fw)
+    gp.inv(torch.empty_like(out), dfw)
+    assert (hfw == host(dfw, np.uint64)).all()
