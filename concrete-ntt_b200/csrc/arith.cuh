@@ -170,6 +170,7 @@ struct Mod64 {
     uint64_t n_inv, n_inv_shoup;
     uint64_t p_barrett;
     uint32_t big_q_m1;
+    uint32_t shift_head; // Solinas: the plan's first heap entries are the powers of two the shift butterflies assume (checked at plan time)
 };
 
 __device__ __forceinline__ uint64_t shoup64(uint64_t a, ulonglong2 t, const Mod64& m)
@@ -381,6 +382,72 @@ struct A64S {
             : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)));
         return pack(r0, r1);
     }
+    // ---- power-of-two twiddles.  2 has order 192 modulo p (2^96 = -1), so every 64-th root of unity is +-2^k, k < 96: the twiddles
+    //      of the first five levels of ANY transform (level j uses primitive 2^(j+2)-th roots).  The reference's root search starts
+    //      from -1 and takes square roots (roots.rs:68-91), so those entries do not depend on N: tw[h] = 2^kShiftExp[h] for the heap
+    //      nodes h < 16 (levels 0..3; checked against the real table when a plan is built).  x * 2^(32a+b) with x = (x1:x0), y = x << b
+    //      = (y2:y1:y0) and phi = 2^32 (phi^2 = phi - 1, phi^3 = -1):
+    //        a = 0:  (y1:y0) + y2 EPS  =  (y1:y0) - [(~y2) : (y2 + 1)]  (+ p on borrow)     [(~y2):(y2+1) = p - y2 EPS]
+    //        a = 1:  (y0:0) - y2 + y1 EPS                                                    the generic 128 -> 64 reduction
+    //        a = 2:  y0 EPS - (y2:y1)                                                         (+ p on borrow)
+    //      each result is <= p for ANY 64-bit x (what add_lazy / sub_lazy need).  B200, registers only (tools/ubench/gold_bf.cu):
+    //      3.24 against 2.40 butterflies/clk/SM forward, 2.97 against 2.30 inverse -- the multiply goes, the 64-bit modular add / sub on
+    //      the ALU stays (profiles/r02_experiments.txt).
+    template <int B> static __device__ __forceinline__ W shl_a0(W x)
+    {
+        const uint32_t y2 = (uint32_t)(x >> (64 - B));
+        return sub_lazy(x << B, ((uint64_t)(~y2) << 32) | (uint64_t)(y2 + 1u));
+    }
+    template <int B> static __device__ __forceinline__ W shl_a2(W x)
+    {
+        const uint32_t y0 = (uint32_t)x << B;
+        return sub_lazy((uint64_t)y0 * EPS, x >> (32 - B));
+    }
+    template <int B> static __device__ __forceinline__ W shl_a1(W x)
+    {
+        const uint32_t y0 = (uint32_t)x << B, y1 = (uint32_t)(x >> (32 - B)), y2 = (uint32_t)(x >> (64 - B));
+        uint32_t r0, r1;
+        asm("{\n\t"
+            ".reg .u32 m;\n\t"
+            ".reg .pred q;\n\t"
+            "sub.cc.u32      %0, 0, %4;\n\t"
+            "subc.cc.u32     %1, %2, 0;\n\t"
+            "subc.u32        m, 0, 0;\n\t"
+            "sub.cc.u32      %0, %0, m;\n\t"
+            "subc.u32        %1, %1, 0;\n\t"
+            "mad.lo.cc.u32   %0, %3, 0xFFFFFFFF, %0;\n\t"
+            "madc.hi.cc.u32  %1, %3, 0xFFFFFFFF, %1;\n\t"
+            "addc.u32        m, 0, 0;\n\t"
+            "setp.eq.u32     q, %1, 0xFFFFFFFF;\n\t"
+            "setp.ne.and.u32 q, %0, 0, q;\n\t"
+            "setp.ne.or.u32  q, m, 0, q;\n\t"
+            "@q add.cc.u32   %0, %0, 0xFFFFFFFF;\n\t"
+            "@q addc.u32     %1, %1, 0;\n\t"
+            "}"
+            : "=&r"(r0), "=&r"(r1) : "r"(y0), "r"(y1), "r"(y2));
+        return pack(r0, r1);
+    }
+    template <int K> static __device__ __forceinline__ W shl_mod(W x) // |x * 2^K|: the sign of 2^K (K >= 96) is left to the caller
+    {
+        constexpr int k = K % 96, a = k / 32, b = k % 32;
+        static_assert(b != 0 || k == 0, "limb-aligned shifts do not occur among the 64-th roots of unity");
+        if constexpr (k == 0) return x;
+        else if constexpr (a == 0) return shl_a0<b>(x);
+        else if constexpr (a == 1) return shl_a1<b>(x);
+        else return shl_a2<b>(x);
+    }
+    template <int K> static __device__ __forceinline__ void fwd_bf_shift(W& z0, W& z1) // fwd_bf with twiddle 2^K
+    {
+        const W t = shl_mod<K>(z1);
+        const W a = add_lazy(z0, t), b = sub_lazy(z0, t);
+        if constexpr ((K % 192) >= 96) { z0 = b; z1 = a; } else { z0 = a; z1 = b; }
+    }
+    template <int K> static __device__ __forceinline__ void inv_bf_shift(W& z0, W& z1) // inv_bf with twiddle 2^K, canonical in / out
+    {
+        const W a = add(z0, z1);
+        const W d = (K % 192) >= 96 ? sub_lazy(z1, z0) : sub_lazy(z0, z1);
+        z0 = a; z1 = shl_mod<K>(d); // every shl_a* result is < p (see above), d is canonical
+    }
     static __device__ __forceinline__ void fwd_bf(W& z0, W& z1, Tw t, const Mod&)
     {
         const W x = mul(z1, t);
@@ -441,5 +508,21 @@ struct A64G {
     static __device__ __forceinline__ W norm(W v, const Mod& m) { return mulmod(v, m.n_inv, m); }
     static __device__ __forceinline__ W mul_acc(W acc, W a, W b, const Mod& m) { return add(acc, mulmod(a, b, m), m); }
 };
+
+// log2 of the Solinas plan's forward twiddles at heap nodes 1..15 (levels 0..3): tw[h] = 2^kShiftExp[h] mod p, inverse table
+// 2^(192 - kShiftExp[h]).  Derived from the reference's root chain (-1, sqrt, sqrt, ...) and verified per plan (capi.cu).
+__host__ __device__ constexpr int shift_exp(int h)
+{
+    constexpr int e[16] = {0, 48, 120, 168, 156, 12, 84, 132, 78, 126, 6, 54, 42, 90, 162, 18};
+    return e[h & 15];
+}
+template <class A> struct ShiftHead { static constexpr bool value = false; };
+#ifndef CNTT_SHIFT_HEAD
+#define CNTT_SHIFT_HEAD 1
+#endif
+template <> struct ShiftHead<A64S> { static constexpr bool value = CNTT_SHIFT_HEAD != 0; };
+#ifndef CNTT_FIRST_FULL_64S
+#define CNTT_FIRST_FULL_64S 1 // Solinas: full first pass (four shift levels), short last pass -- ntt_engine.cuh, Geo
+#endif
 
 } // namespace cntt

@@ -431,6 +431,17 @@ static int build_prime64(size_t n, uint64_t p, int device, cntt_prime64_plan** o
     const int big_q = host::ilog2(p) + 1;                           // prime64.rs:754
     m.big_q_m1 = (uint32_t)(big_q - 1);
     m.p_barrett = (uint64_t)((((u128)1) << (big_q + 63)) / p);      // prime64.rs:755-756 (unused when p >= 2^63)
+    m.shift_head = 0;
+    if (cls == C64_S) { // the shift butterflies of the leading levels assume tw[h] = 2^shift_exp(h): check it against the real table
+        bool ok = true;
+        for (size_t h = 1; h < 16 && h < n; h++) {
+            uint64_t want = 1, wanti = 1;
+            for (int k = 0; k < shift_exp((int)h); k++) want = fp.mul(want, 2);
+            for (int k = 0; k < (192 - shift_exp((int)h)) % 192; k++) wanti = fp.mul(wanti, 2);
+            ok = ok && f[h] == want && iv[h] == wanti;
+        }
+        m.shift_head = ok ? 1u : 0u;
+    }
     pl->d_fwd = pl->d_inv = pl->d_fwd_last = pl->d_inv_last = nullptr;
     cudaError_t e;
     size_t bytes;

@@ -22,6 +22,7 @@
 #pragma once
 #include "arith.cuh"
 #include <atomic>
+#include <utility>
 
 namespace cntt {
 
@@ -56,17 +57,28 @@ inline cudaError_t ensure_dyn_smem(const void* kern, size_t smem)
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); // table full: uncached
 }
 
-template <int LOGN, int LOGR>
+// FF ("first full"): when LOGN is not a multiple of LOGR one pass is short.  By default it is pass 0 (R1 < LOGR levels); with FF
+// pass 0 runs LOGR levels and the LAST pass is the short one: it keeps the last-pass layout (R consecutive words per thread) and
+// simply skips the first LOGR - RL levels of its LOGR-level frame, i.e. it handles 2^(LOGR-RL) adjacent blocks of 2^RL words.
+// Used for the Solinas class, whose pass-0 levels are multiplier-free (ShiftHead): N = 2048 then has four of them instead of three.
+template <int LOGN, int LOGR, bool FF = false>
 struct Geo {
     static_assert(LOGN >= LOGR, "need at least R words per polynomial");
     static constexpr int N = 1 << LOGN;
     static constexpr int R = 1 << LOGR;
     static constexpr int T = N / R;                           // threads per polynomial
     static constexpr int P = (LOGN + LOGR - 1) / LOGR;        // passes
-    static constexpr int R1 = LOGN - (P - 1) * LOGR;          // levels in pass 0
-    static __host__ __device__ constexpr int s0(int q) { return q == 0 ? 0 : R1 + (q - 1) * LOGR; }
-    static __host__ __device__ constexpr int levels(int q) { return q == 0 ? R1 : LOGR; }
+    static constexpr int RX = LOGN - (P - 1) * LOGR;          // levels of the short pass
+    static constexpr bool kFF = FF && P >= 2 && RX < LOGR;
+    static constexpr int R1 = kFF ? LOGR : RX;                // levels in pass 0
+    static constexpr int RL = P == 1 ? RX : kFF ? RX : LOGR;  // levels in the last pass
+    static __host__ __device__ constexpr int s0(int q) { return q == 0 ? 0 : kFF ? (q == P - 1 ? LOGN - LOGR : q * LOGR) : R1 + (q - 1) * LOGR; }
+    static __host__ __device__ constexpr int levels(int q) { return q == 0 ? R1 : q == P - 1 ? RL : LOGR; }
+    // first level of pass q inside its LOGR-level frame (level j of the frame pairs slots R >> (j + 1) apart)
+    static __host__ __device__ constexpr int jlo(int q) { return (kFF && q == P - 1) ? LOGR - RL : 0; }
 };
+template <class A> struct FirstFull { static constexpr bool value = false; };
+template <> struct FirstFull<A64S> { static constexpr bool value = CNTT_FIRST_FULL_64S != 0; };
 
 // shared-memory padding: one extra word per 128-byte row makes every power-of-two stride
 // (<= one row) conflict-free for both the scatter and the gather side of an exchange.
@@ -103,7 +115,7 @@ template <class Tw> __host__ __device__ constexpr int head_log() { return sizeof
 
 template <class A, int LOGN, int LOGR>
 struct Engine {
-    typedef Geo<LOGN, LOGR> G;
+    typedef Geo<LOGN, LOGR, FirstFull<A>::value> G;
     typedef typename A::W W;
     typedef typename A::Tw Tw;
     typedef typename A::Mod Mod;
@@ -245,9 +257,9 @@ struct Engine {
     template <int Q, int NP>
     static __device__ __forceinline__ void fwd_pass(W (&x)[NP][R], const TwSrc& tw, unsigned nu, int tid, const Mod& m)
     {
-        constexpr int L = G::levels(Q);
+        constexpr int L = G::levels(Q), J0 = G::jlo(Q);
 #pragma unroll
-        for (int j = 0; j < L; j++) {
+        for (int j = J0; j < J0 + L; j++) {
             const int half = R >> (j + 1);
 #pragma unroll
             for (int g = 0; g < (1 << j); g++) {
@@ -263,9 +275,9 @@ struct Engine {
     template <int Q, int NP>
     static __device__ __forceinline__ void inv_pass(W (&x)[NP][R], const TwSrc& tw, unsigned nu, int tid, const Mod& m)
     {
-        constexpr int L = G::levels(Q);
+        constexpr int L = G::levels(Q), J0 = G::jlo(Q);
 #pragma unroll
-        for (int j = L - 1; j >= 0; j--) {
+        for (int j = J0 + L - 1; j >= J0; j--) {
             const int half = R >> (j + 1);
 #pragma unroll
             for (int g = 0; g < (1 << j); g++) {
@@ -361,11 +373,11 @@ struct Engine {
         }
     }
     template <int NP>
-    static __device__ __forceinline__ void levels_fwd(W (&x)[NP][R], const Tw* __restrict__ tw, unsigned nu, int L, const Mod& m)
+    static __device__ __forceinline__ void levels_fwd(W (&x)[NP][R], const Tw* __restrict__ tw, unsigned nu, int jlo, int jhi, const Mod& m)
     {
 #pragma unroll
         for (int j = 0; j < LOGR; j++) {
-            if (G::R1 == LOGR || j < L) {
+            if (G::RX == LOGR || (j >= jlo && j < jhi)) {
                 const int half = R >> (j + 1);
 #pragma unroll
                 for (int g = 0; g < (1 << j); g++) {
@@ -379,11 +391,11 @@ struct Engine {
         }
     }
     template <int NP>
-    static __device__ __forceinline__ void levels_inv(W (&x)[NP][R], const Tw* __restrict__ tw, unsigned nu, int L, const Mod& m)
+    static __device__ __forceinline__ void levels_inv(W (&x)[NP][R], const Tw* __restrict__ tw, unsigned nu, int jlo, int jhi, const Mod& m)
     {
 #pragma unroll
         for (int j = LOGR - 1; j >= 0; j--) {
-            if (G::R1 == LOGR || j < L) {
+            if (G::RX == LOGR || (j >= jlo && j < jhi)) {
                 const int half = R >> (j + 1);
 #pragma unroll
                 for (int g = 0; g < (1 << j); g++) {
@@ -396,22 +408,68 @@ struct Engine {
             }
         }
     }
+    // ---- pass 0 of a whole Solinas transform: the twiddles of levels 0 .. R1-1 (heap nodes < 2^R1 <= 16) are compile-time powers
+    //      of two, so the butterflies are shift butterflies (arith.cuh, A64S::fwd_bf_shift) emitted once, outside the pass loop
+    static constexpr bool kShiftHead = ShiftHead<A>::value && kLoopPasses && G::R1 <= 4;
+    template <int J, int GI, bool FWD, int NP>
+    static __device__ __forceinline__ void shift_group(W (&x)[NP][R])
+    {
+        constexpr int half = R >> (J + 1);
+        constexpr int K = FWD ? shift_exp((1 << J) + GI) : (192 - shift_exp((1 << J) + GI)) % 192;
+#pragma unroll
+        for (int u = 0; u < half; u++)
+#pragma unroll
+            for (int np = 0; np < NP; np++) {
+                if constexpr (FWD) A::template fwd_bf_shift<K>(x[np][2 * half * GI + u], x[np][2 * half * GI + u + half]);
+                else A::template inv_bf_shift<K>(x[np][2 * half * GI + u], x[np][2 * half * GI + u + half]);
+            }
+    }
+    template <int J, bool FWD, int NP, int... GI>
+    static __device__ __forceinline__ void shift_level(W (&x)[NP][R], std::integer_sequence<int, GI...>)
+    {
+        (shift_group<J, GI, FWD, NP>(x), ...);
+    }
+    template <int NP, int... J>
+    static __device__ __forceinline__ void shift_levels_fwd(W (&x)[NP][R], std::integer_sequence<int, J...>)
+    {
+        (shift_level<J, true, NP>(x, std::make_integer_sequence<int, (1 << J)>{}), ...);
+    }
+    template <int NP, int... J>
+    static __device__ __forceinline__ void shift_levels_inv(W (&x)[NP][R], std::integer_sequence<int, J...>)
+    {
+        (shift_level<G::R1 - 1 - J, false, NP>(x, std::make_integer_sequence<int, (1 << (G::R1 - 1 - J))>{}), ...);
+    }
     template <int NP>
     static __device__ __forceinline__ void fwd_loop(W (&x)[NP][R], W* sm, const Tw* __restrict__ tw, unsigned nu0, int tid, const Mod& m)
     {
+        int q0 = 0;
+        if constexpr (kShiftHead) {
+            if (nu0 == 1u && m.shift_head) { // whole transform on the verified table: uniform branch
+                shift_levels_fwd<NP>(x, std::make_integer_sequence<int, G::R1>{});
+                xchg_rt<0, NP, true>(0, x, sm, tid);
+                q0 = 1;
+            }
+        }
 #pragma unroll 1
-        for (int q = 0; q < P; q++) {
-            levels_fwd<NP>(x, tw, node_rt<0>(q, tid, nu0), q == 0 ? G::R1 : LOGR, m);
+        for (int q = q0; q < P; q++) {
+            levels_fwd<NP>(x, tw, node_rt<0>(q, tid, nu0), G::jlo(q), G::jlo(q) + G::levels(q), m);
             xchg_rt<0, NP, true>(q, x, sm, tid);
         }
     }
     template <int NP>
     static __device__ __forceinline__ void inv_loop(W (&x)[NP][R], W* sm, const Tw* __restrict__ tw, unsigned nu0, int tid, const Mod& m)
     {
+        int qend = 0;
+        if constexpr (kShiftHead) {
+            if (nu0 == 1u && m.shift_head) qend = 1;
+        }
 #pragma unroll 1
-        for (int q = P - 1; q >= 0; q--) {
-            levels_inv<NP>(x, tw, node_rt<0>(q, tid, nu0), q == 0 ? G::R1 : LOGR, m);
+        for (int q = P - 1; q >= qend; q--) {
+            levels_inv<NP>(x, tw, node_rt<0>(q, tid, nu0), G::jlo(q), G::jlo(q) + G::levels(q), m);
             xchg_rt<0, NP, false>(q - 1, x, sm, tid);
+        }
+        if constexpr (kShiftHead) {
+            if (qend == 1) shift_levels_inv<NP>(x, std::make_integer_sequence<int, G::R1>{});
         }
     }
 

@@ -3,14 +3,16 @@
 scatter / gather of an exchange for a given (LOGN, LOGR, word bytes).  usage: bank_model.py LOGN LOGR WORDBYTES"""
 import sys
 
-def model(LOGN, LOGR, WB, verbose=True):
+def model(LOGN, LOGR, WB, verbose=True, FF=False):
     N, R = 1 << LOGN, 1 << LOGR
     T = N // R
     P = (LOGN + LOGR - 1) // LOGR
-    R1 = LOGN - (P - 1) * LOGR
+    RX = LOGN - (P - 1) * LOGR
+    kFF = FF and P >= 2 and RX < LOGR
+    R1 = LOGR if kFF else RX
     LOGROW = 5 if WB == 4 else 4
     PH = 1 << LOGROW
-    s0 = lambda q: 0 if q == 0 else R1 + (q - 1) * LOGR
+    s0 = lambda q: 0 if q == 0 else ((LOGN - LOGR if q == P - 1 else q * LOGR) if kFF else R1 + (q - 1) * LOGR)
     blk_words = lambda q: N if q == 0 else N >> s0(q)
     stride = lambda q: T if q == 0 else blk_words(q) >> LOGR
     wants_perm = lambda q: q >= 1 and stride(q) < PH and blk_words(q) >= PH and R < PH
@@ -51,4 +53,4 @@ def model(LOGN, LOGR, WB, verbose=True):
     return worst
 
 if __name__ == "__main__":
-    model(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]))
+    model(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), FF=len(sys.argv) > 4)
