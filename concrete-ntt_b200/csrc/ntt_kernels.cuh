@@ -451,6 +451,80 @@ k_ntt_cta_pipe(const typename A::Tw* __restrict__ tw, const typename A::Tw* __re
     }
 }
 
+// ---- persistent forward kernel with bulk-asynchronous (TMA engine) input staging: EXPERIMENT, off by default --------------------
+// north_star: "TMA-staged tiles where they measurably help".  Same walk over the batch as k_ntt_cta_pipe, but the NEXT polynomial is
+// fetched by one cp.async.bulk (global -> shared, completion on an mbarrier) issued by one thread per group while the current one is
+// transformed, instead of R register loads per thread: no second register set, no LSU instructions for the global side.  The tile
+// costs N words of shared memory per group on top of the exchange buffers, and the R loads per thread come back as R LDS.
+// Measured on B200 (profiles/r02_experiments.txt, "bulk"): see the log; not shipped.
+#ifndef CNTT_BULK32
+#define CNTT_BULK32 0
+#endif
+#ifndef CNTT_BULK_MINLOGN
+#define CNTT_BULK_MINLOGN 10
+#endif
+#ifndef CNTT_BULK_MAXLOGN
+#define CNTT_BULK_MAXLOGN 13
+#endif
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <class A, int LOGN, int LOGR, int GP>
+__global__ void __launch_bounds__(GP * Geo<LOGN, LOGR>::T)
+k_ntt_cta_bulk(const typename A::Tw* __restrict__ tw, const typename A::Tw* __restrict__ tw_last, const typename A::Mod m,
+               typename A::W* __restrict__ data, unsigned long long nvpoly, unsigned long long poly_stride,
+               const __grid_constant__ TwHead<typename A::Tw> head)
+{
+    typedef Engine<A, LOGN, LOGR> E;
+    typedef typename A::W W;
+    constexpr int T = E::T, R = E::R, N = E::N;
+    constexpr unsigned kBytes = N * sizeof(W);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // layout: [GP stage tiles of N words][GP mbarriers][exchange buffers]
+    W* stage_all = reinterpret_cast<W*>(smem_raw);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)GP * kBytes);
+    W* sm_all = reinterpret_cast<W*>(smem_raw + (size_t)GP * kBytes + 128);
+    const int grp = (GP == 1) ? 0 : (int)(threadIdx.x / T);
+    const int tid = (GP == 1) ? (int)threadIdx.x : (int)(threadIdx.x % T);
+    W* sm = sm_all + (size_t)grp * E::SMEM_WORDS * E::NBUF;
+    W* stage = stage_all + (size_t)grp * N;
+    const uint32_t bar = smem_u32(bars + grp), dst = smem_u32(stage);
+    const typename E::TwSrc tws = {tw, tw_last, &head};
+    const unsigned long long ngroups = (unsigned long long)gridDim.x * GP;
+    const unsigned long long iters = (nvpoly + ngroups - 1) / ngroups; // uniform across the CTA (barriers)
+    unsigned long long g = (unsigned long long)blockIdx.x * GP + grp;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](unsigned long long vp) {
+        if (vp >= nvpoly) vp = nvpoly - 1;
+        const W* src = data + vp * poly_stride;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(kBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(dst), "l"(__cvta_generic_to_global(src)), "r"(kBytes), "r"(bar) : "memory");
+    };
+    if (tid == 0) issue(g);
+    unsigned phase = 0;
+#pragma unroll 1
+    for (unsigned long long it = 0; it < iters; ++it, g += ngroups) {
+        // wait for this group's tile
+        asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}" :: "r"(bar), "r"(phase) : "memory");
+        phase ^= 1u;
+        W x[1][R];
+#pragma unroll
+        for (int k = 0; k < R; k++) x[0][k] = stage[tid + k * T];
+        __syncthreads(); // every thread of the CTA has read its tile: the tile may be overwritten (and the previous iteration's exchanges are done)
+        if (tid == 0 && it + 1 < iters) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy reads of the tile before its async-proxy overwrite
+            issue(g + ngroups);
+        }
+        E::template fwd<1>(x, sm, tws, 1u, tid, m);
+#pragma unroll
+        for (int k = 0; k < R; k++) x[0][k] = A::canon_fwd(x[0][k], m);
+        if (g < nvpoly) store_contig<W, R>(data + g * poly_stride + E::elem_last(tid, 0), x[0]);
+    }
+}
+
 // ---- last-pass twiddle table builder (plan time) ---------------------------------------------------
 // One thread per (sub-block, engine thread): copies the R - 1 heap entries of its last-pass sub-tree into
 // the thread-innermost layout read by Engine::tw_at.  Uses the engine's own thread -> node map, so the
@@ -645,6 +719,31 @@ cudaError_t launch_cta_np(const PlanDev<A>& pl, typename A::W* data, unsigned lo
     // loads were never latency-bound and the second register set costs occupancy), so only the forward pipelines
     // (re-measured after the 256-bit stores: the one-shot kernel now wins up to N = 4096 -- N=256 2311 -> 2631, N=1024 478 -> 517
     // M NTT/s, N=2048 / 4096 within 1 % -- and the persistent one keeps N = 8192, 42.3 -> 45.9, where only two CTAs are resident)
+    constexpr bool kBulk = CNTT_BULK32 != 0 && FWD && NP == 1 && sizeof(typename A::W) == 4 && LOGN >= CNTT_BULK_MINLOGN && LOGN <= CNTT_BULK_MAXLOGN;
+    if constexpr (kBulk) {
+        if (log_sub == 0 && head != nullptr && poly_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(data) & 15u) == 0) {
+            auto kern = k_ntt_cta_bulk<A, LOGN, LOGR, GP>;
+            const size_t smem_b = smem_xchg + (size_t)GP * E::N * sizeof(typename A::W) + 128;
+            static std::atomic<int> resident_b[64];
+            int dev = 0;
+            cudaError_t e = cudaGetDevice(&dev);
+            if (e != cudaSuccess) return e;
+            if (dev < 0 || dev >= 64) dev = 0;
+            int res = resident_b[dev].load(std::memory_order_relaxed);
+            if (res == 0) {
+                if ((e = ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem_b)) != cudaSuccess) return e;
+                int per_sm = 0, sms = 0;
+                if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GP * T, smem_b)) != cudaSuccess) return e;
+                if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+                res = per_sm * sms > 0 ? per_sm * sms : 1;
+                resident_b[dev].store(res, std::memory_order_relaxed);
+            }
+            if (nblk >= 2ull * (unsigned long long)res) {
+                kern<<<(unsigned)res, GP * T, smem_b, st>>>(pl.tw_fwd, last, pl.mod, data, nvpoly, poly_stride, *head);
+                return cudaGetLastError();
+            }
+        }
+    }
     constexpr bool kPipe = FWD && (sizeof(typename A::W) == 4 ? (CNTT_PIPE32 != 0 && LOGN >= CNTT_PIPE32_MINLOGN && LOGN <= CNTT_PIPE32_MAXLOGN && !r32_size<A, LOGN>()) : CNTT_PIPE64 != 0);
     if constexpr (kPipe) {
         // persistent variant: needs whole transforms and at least two polynomials per resident group to pipeline
