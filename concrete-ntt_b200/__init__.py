@@ -138,5 +138,8 @@ fastdiv = _module("fastdiv", Div32=_Div32, Div64=_Div64)
 roots = _module("roots", find_primitive_root64=_find_primitive_root64)
 
 
+HostMulti = _plans.HostMulti  # extension: one host batch over several GPUs in one process
+
+
 def version():
     return _lib.lib().cntt_version().decode()

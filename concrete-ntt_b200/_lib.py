@@ -40,6 +40,9 @@ for _b, _w in (("32", _u32), ("64", _u64)):
         _p + "_fwd_host": (_int, [_vp, _vp, _sz, _sz]),
         _p + "_inv_host": (_int, [_vp, _vp, _sz, _sz]),
         _p + "_fwd_inv_host": (_int, [_vp, _vp, _sz, _sz]),
+        _p + "_fwd_host_multi": (_int, [C.POINTER(_vp), _int, _vp, _sz, _sz]),
+        _p + "_inv_host_multi": (_int, [C.POINTER(_vp), _int, _vp, _sz, _sz]),
+        _p + "_fwd_inv_host_multi": (_int, [C.POINTER(_vp), _int, _vp, _sz, _sz]),
         _p + "_mul_assign_normalize_host": (_int, [_vp, _vp, _vp, _sz]),
         _p + "_normalize_host": (_int, [_vp, _vp, _sz]),
         _p + "_mul_accumulate_host": (_int, [_vp, _vp, _vp, _vp, _sz]),
@@ -59,6 +62,7 @@ SIGNATURES.update({
     "cntt_native_inv_host": (_int, [_vp, _vp, _vp, _sz, _sz]),
     "cntt_native_polymul": (_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
     "cntt_native_polymul_host": (_int, [_vp, _vp, _vp, _vp, _sz, _sz]),
+    "cntt_native_polymul_host_multi": (_int, [C.POINTER(_vp), _int, _vp, _vp, _vp, _sz, _sz]),
     "cntt_native52_plan_new": (_int, [_sz, _int, _int, _int, C.POINTER(_vp)]),
     "cntt_native52_plan_free": (None, [_vp]),
     "cntt_native52_ntt_size": (_sz, [_vp]),

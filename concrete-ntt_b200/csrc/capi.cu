@@ -10,6 +10,7 @@
 #include <cstring>
 #include <functional>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -625,6 +626,46 @@ PRIME_HOST_NTT(64, uint64_t, inv, return run_ntt64(pl, (uint64_t*)d, nb, false, 
 PRIME_HOST_NTT(64, uint64_t, fwd_inv, cudaError_t e = run_ntt64(pl, (uint64_t*)d, nb, true, st); if (e != cudaSuccess) return e;
                return run_ntt64(pl, (uint64_t*)d, nb, false, st);)
 
+// ---- one host batch over several devices ---------------------------------------------------------------------------
+// plans[g] is the same plan (n, p) built on device g (any devices, duplicates allowed); the batch is cut into nplans contiguous
+// shards and every shard runs through its plan's own staging pipeline on its own host thread, so all PCIe links and copy
+// engines work at once.  No collective: polynomials are independent.  Returns the first status that is not CNTT_OK.
+template <class Fn>
+static int host_multi(int nplans, size_t batch, Fn shard_fn)
+{
+    if (nplans <= 0) return CNTT_NULL_POINTER;
+    std::vector<int> rc((size_t)nplans, CNTT_OK);
+    std::vector<std::thread> th;
+    th.reserve((size_t)nplans);
+    for (int g = 0; g < nplans; g++) {
+        const size_t b0 = batch * (size_t)g / (size_t)nplans, b1 = batch * (size_t)(g + 1) / (size_t)nplans;
+        th.emplace_back([&, g, b0, b1]() { rc[(size_t)g] = b1 > b0 ? shard_fn(g, b0, b1 - b0) : CNTT_OK; });
+    }
+    for (auto& t : th) t.join();
+    for (int r : rc)
+        if (r != CNTT_OK) return r;
+    return CNTT_OK;
+}
+#define PRIME_HOST_MULTI(BITS, T, NAME)                                                                                               \
+    CNTT_API int cntt_prime##BITS##_##NAME##_host_multi(const cntt_prime##BITS##_plan* const* plans, int nplans, T* h_buf, size_t len, \
+                                                         size_t batch)                                                                 \
+    {                                                                                                                                  \
+        if (!plans || nplans <= 0 || (!h_buf && len)) return CNTT_NULL_POINTER;                                                        \
+        for (int g = 0; g < nplans; g++)                                                                                               \
+            if (!plans[g] || plans[g]->n != plans[0]->n || plans[g]->p != plans[0]->p) return g && plans[g] ? CNTT_LENGTH_MISMATCH : CNTT_NULL_POINTER; \
+        const size_t n = plans[0]->n;                                                                                                  \
+        if (len != n * batch) return CNTT_LENGTH_MISMATCH;                                                                             \
+        return host_multi(nplans, batch, [&](int g, size_t b0, size_t nb) {                                                            \
+            return cntt_prime##BITS##_##NAME##_host(plans[g], h_buf + b0 * n, nb * n, nb);                                             \
+        });                                                                                                                            \
+    }
+PRIME_HOST_MULTI(32, uint32_t, fwd)
+PRIME_HOST_MULTI(32, uint32_t, inv)
+PRIME_HOST_MULTI(32, uint32_t, fwd_inv)
+PRIME_HOST_MULTI(64, uint64_t, fwd)
+PRIME_HOST_MULTI(64, uint64_t, inv)
+PRIME_HOST_MULTI(64, uint64_t, fwd_inv)
+
 // pointwise host flavours: simple staged version (streams: dst [+a [+b]])
 template <class T, class Fn>
 static int host_pointwise(Staging& stg, int device, T* h_dst, const T* h_a, const T* h_b, size_t nwords, Fn launch)
@@ -941,6 +982,19 @@ CNTT_API int cntt_native_polymul_host(const cntt_native_plan* pl, void* h_prod, 
     CU(cudaStreamSynchronize(stg.stream));
     CU(cudaStreamSynchronize(stg.stream2));
     return CNTT_OK;
+}
+// one host batch of polymuls over several devices (see host_multi above)
+CNTT_API int cntt_native_polymul_host_multi(const cntt_native_plan* const* plans, int nplans, void* h_prod, const void* h_lhs, const void* h_rhs,
+                                            size_t len, size_t batch)
+{
+    if (!plans || nplans <= 0 || ((!h_prod || !h_lhs || !h_rhs) && len)) return CNTT_NULL_POINTER;
+    for (int g = 0; g < nplans; g++)
+        if (!plans[g] || plans[g]->n != plans[0]->n || plans[g]->kind != plans[0]->kind) return g && plans[g] ? CNTT_LENGTH_MISMATCH : CNTT_NULL_POINTER;
+    const size_t n = plans[0]->n, wb = (size_t)native_word_bytes(plans[0]->kind);
+    if (len != n * batch) return CNTT_LENGTH_MISMATCH;
+    return host_multi(nplans, batch, [&](int g, size_t b0, size_t nb) {
+        return cntt_native_polymul_host(plans[g], (char*)h_prod + b0 * n * wb, (const char*)h_lhs + b0 * n * wb, (const char*)h_rhs + b0 * n * wb, nb * n, nb);
+    });
 }
 
 // host-slice flavours of Plan32::fwd / fwd_binary / inv: the reference's call shape (value: n words, mod_p_k: n u32 each;

@@ -523,3 +523,45 @@ class ProductPlan:
         else:
             check(l.cntt_product_mul_accumulate_host(self._h, a.ptr, x.ptr, y.ptr, a.words, a.batch))
         return acc
+
+
+class HostMulti:
+    """EXTENSION: one host batch over several GPUs in ONE process (cntt_*_host_multi).  `plans` are equal plans built on
+    different devices (prime32 / prime64 plans: fwd, inv, fwd_inv; native Plan32: negacyclic_polymul); the batch is cut into
+    len(plans) contiguous shards, each staged and transformed on its own device concurrently, no collective."""
+
+    def __init__(self, plans):
+        if not plans:
+            raise ValueError("at least one plan")
+        self._plans = list(plans)
+        self._arr = (C.c_void_p * len(self._plans))(*[p._h for p in self._plans])
+        self._p0 = self._plans[0]
+
+    def _prime(self, name, buf):
+        p0 = self._p0
+        b = _Buf(None, buf, p0._bits // 8, "buf")
+        if b.is_dev:
+            raise TypeError("HostMulti takes host (numpy) batches; device-resident batches are sharded by the caller")
+        if len(b.shape) == 0 or b.shape[-1] != p0._n:
+            raise ReferencePanic("assert_eq!(buf.len(), self.ntt_size())")
+        fn = getattr(_lib.lib(), "cntt_prime%d_%s_host_multi" % (p0._bits, name))
+        check(fn(self._arr, len(self._plans), b.ptr, b.words, b.words // p0._n), name)
+        return buf
+
+    def fwd(self, buf):
+        return self._prime("fwd", buf)
+
+    def inv(self, buf):
+        return self._prime("inv", buf)
+
+    def fwd_inv(self, buf):
+        return self._prime("fwd_inv", buf)
+
+    def negacyclic_polymul(self, prod, lhs, rhs):
+        p0 = self._p0
+        bufs = [p0._word_buf(x, nm) for x, nm in ((prod, "prod"), (lhs, "lhs"), (rhs, "rhs"))]
+        if any(b.is_dev for b in bufs) or not (bufs[0].batch == bufs[1].batch == bufs[2].batch):
+            raise TypeError("HostMulti.negacyclic_polymul takes three host arrays of one shape")
+        check(_lib.lib().cntt_native_polymul_host_multi(self._arr, len(self._plans), bufs[0].ptr, bufs[1].ptr, bufs[2].ptr,
+                                                        bufs[0].batch * p0._n, bufs[0].batch))
+        return prod

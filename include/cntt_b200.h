@@ -112,6 +112,18 @@ int cntt_prime64_mul_assign_normalize_host(const cntt_prime64_plan* plan, uint64
 int cntt_prime64_normalize_host(const cntt_prime64_plan* plan, uint64_t* h_values, size_t nwords);
 int cntt_prime64_mul_accumulate_host(const cntt_prime64_plan* plan, uint64_t* h_acc, const uint64_t* h_lhs, const uint64_t* h_rhs, size_t nwords);
 
+/* ---- one host batch over several GPUs (extension) ---------------------------------------------------
+ * plans[g] = the same plan (n, p) built on device g.  The batch is cut into nplans contiguous shards, each staged and
+ * transformed on its own device concurrently (one host thread and one staging pipeline per device, no collective --
+ * polynomials are independent); results land in place.  This is the single-process entry point for a box of GPUs;
+ * the per-device calls above remain for callers that do their own sharding (one process per GPU, shard.py). */
+int cntt_prime32_fwd_host_multi(const cntt_prime32_plan* const* plans, int nplans, uint32_t* h_buf, size_t len, size_t batch);
+int cntt_prime32_inv_host_multi(const cntt_prime32_plan* const* plans, int nplans, uint32_t* h_buf, size_t len, size_t batch);
+int cntt_prime32_fwd_inv_host_multi(const cntt_prime32_plan* const* plans, int nplans, uint32_t* h_buf, size_t len, size_t batch);
+int cntt_prime64_fwd_host_multi(const cntt_prime64_plan* const* plans, int nplans, uint64_t* h_buf, size_t len, size_t batch);
+int cntt_prime64_inv_host_multi(const cntt_prime64_plan* const* plans, int nplans, uint64_t* h_buf, size_t len, size_t batch);
+int cntt_prime64_fwd_inv_host_multi(const cntt_prime64_plan* const* plans, int nplans, uint64_t* h_buf, size_t len, size_t batch);
+
 /* ---- native{32,64,128}::Plan32 and native_binary{32,64,128}::Plan32 --------------------------------
  * One handle type; `word_bits` in {32,64,128} and `binary` in {0,1} select the reference plan:
  *   native32::Plan32        (P0..P2)  src/native32.rs:8-12,335-433
@@ -153,6 +165,8 @@ int cntt_native_inv_host(const cntt_native_plan* plan, void* h_value, uint32_t* 
 int cntt_native_polymul(const cntt_native_plan* plan, void* d_prod, const void* d_lhs, const void* d_rhs, size_t batch, void* stream);
 /* host-slice flavour: len = words in each of prod/lhs/rhs; must equal n*batch */
 int cntt_native_polymul_host(const cntt_native_plan* plan, void* h_prod, const void* h_lhs, const void* h_rhs, size_t len, size_t batch);
+/* the same over several GPUs: plans[g] = the same plan kind and n on device g (see cntt_prime32_fwd_host_multi) */
+int cntt_native_polymul_host_multi(const cntt_native_plan* const* plans, int nplans, void* h_prod, const void* h_lhs, const void* h_rhs, size_t len, size_t batch);
 
 /* ---- Plan52 twins: native32 / native64 / native_binary32 / native_binary64 ::Plan52 ----------------------------
  * (src/native32.rs:19,435-496; native64.rs:29-34,1072-1165; native_binary32.rs:19,266-330; native_binary64.rs:29,447-521)

@@ -45,6 +45,15 @@ extern "C" {
     pub fn cntt_prime32_normalize_host(plan: *const Prime32Plan, values: *mut u32, nwords: usize) -> c_int;
     pub fn cntt_prime32_mul_accumulate_host(plan: *const Prime32Plan, acc: *mut u32, lhs: *const u32, rhs: *const u32, nwords: usize) -> c_int;
 
+    // ---- one host batch over several GPUs (extension) ----
+    pub fn cntt_prime32_fwd_host_multi(plans: *const *const Prime32Plan, nplans: c_int, h_buf: *mut u32, len: usize, batch: usize) -> c_int;
+    pub fn cntt_prime32_inv_host_multi(plans: *const *const Prime32Plan, nplans: c_int, h_buf: *mut u32, len: usize, batch: usize) -> c_int;
+    pub fn cntt_prime32_fwd_inv_host_multi(plans: *const *const Prime32Plan, nplans: c_int, h_buf: *mut u32, len: usize, batch: usize) -> c_int;
+    pub fn cntt_prime64_fwd_host_multi(plans: *const *const Prime64Plan, nplans: c_int, h_buf: *mut u64, len: usize, batch: usize) -> c_int;
+    pub fn cntt_prime64_inv_host_multi(plans: *const *const Prime64Plan, nplans: c_int, h_buf: *mut u64, len: usize, batch: usize) -> c_int;
+    pub fn cntt_prime64_fwd_inv_host_multi(plans: *const *const Prime64Plan, nplans: c_int, h_buf: *mut u64, len: usize, batch: usize) -> c_int;
+    pub fn cntt_native_polymul_host_multi(plans: *const *const NativePlan, nplans: c_int, h_prod: *mut c_void, h_lhs: *const c_void, h_rhs: *const c_void, len: usize, batch: usize) -> c_int;
+
     // ---- prime64::Plan ----
     pub fn cntt_prime64_plan_new(n: usize, p: u64, device: c_int, out: *mut *mut Prime64Plan) -> c_int;
     pub fn cntt_prime64_plan_free(plan: *mut Prime64Plan);

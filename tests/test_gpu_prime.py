@@ -285,3 +285,32 @@ def test_buffers_aligned_to_16_bytes_only(cntt, oracle, torch_cuda, bits, n):
     assert (host(d, dt) == ref).all()
     gp.inv(d)
     assert (host(d, dt) == op.inv(ref.copy())).all()
+
+
+def test_host_multi_splits_one_batch_over_plans(cntt, oracle, torch_cuda):
+    """cntt_prime*_host_multi / cntt_native_polymul_host_multi: one host batch cut over several plans (one per GPU; with a single
+    GPU the plans share device 0 and still run their staging pipelines concurrently), bit-equal to the oracle, ragged batch."""
+    ndev = torch_cuda.cuda.device_count()
+    devs = list(range(ndev)) if ndev > 1 else [0, 0, 0]
+    g = rng(77)
+    for bits, n, p, OP, mod in ((32, 1024, 1062862849, oracle.Plan32, cntt.prime32), (64, 2048, 0xFFFFFFFF00000001, oracle.Plan64, cntt.prime64)):
+        dt = np.uint32 if bits == 32 else np.uint64
+        plans = [mod.Plan.try_new(n, p, device=d) for d in devs]
+        multi = cntt.HostMulti(plans)
+        op = OP.try_new(n, p)
+        a = rand_mod(g, p, (37, n), dt)
+        ref = op.fwd(a.copy())
+        b = a.copy()
+        multi.fwd(b)
+        assert (b == ref).all()
+        multi.inv(b)
+        assert (b == op.inv(ref.copy())).all()
+        c = a.copy()
+        multi.fwd_inv(c)
+        assert (c == b).all()
+    n = 256
+    plans = [cntt.native64.Plan32.try_new(n, device=d) for d in devs]
+    lhs, rhs = g.integers(0, 2**64, size=(11, n), dtype=np.uint64), g.integers(0, 2**64, size=(11, n), dtype=np.uint64)
+    prod = np.zeros_like(lhs)
+    cntt.HostMulti(plans).negacyclic_polymul(prod, lhs, rhs)
+    assert (prod == oracle.Native.try_new(n, 64).negacyclic_polymul(lhs, rhs)).all()
