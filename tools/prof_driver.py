@@ -64,6 +64,38 @@ elif which == "split64":   # Plan32::fwd / inv on device residue planes
     planes = torch.empty((plan.num_primes(), batch, n), dtype=torch.int32, device="cuda")
     for _ in range(reps):
         plan.fwd(val, planes)
+elif which == "split64inv":   # Plan32::inv on device residue planes: nprimes inverse transforms + k_native_crt; odd sizes use k_native_reduce
+    plan = cntt.native64.Plan32.try_new(n)
+    val = torch.randint(-2**63, 2**63 - 1, (batch, n), dtype=torch.int64, device="cuda", generator=g)
+    planes = torch.empty((plan.num_primes(), batch, n), dtype=torch.int32, device="cuda")
+    small = cntt.native64.Plan32.try_new(128)     # N < 256: unfused k_native_reduce
+    sval = torch.randint(-2**63, 2**63 - 1, (batch * n // 128, 128), dtype=torch.int64, device="cuda", generator=g)
+    splanes = torch.empty((5, batch * n // 128, 128), dtype=torch.int32, device="cuda")
+    for _ in range(reps):
+        plan.fwd(val, planes)
+        plan.inv(val, planes)
+        small.fwd(sval, splanes)
+elif which == "plan52":       # Plan52 twins: k_native52_reduce + prime64 transforms + k_native52_crt
+    plan = cntt.native64.Plan52.try_new(n)
+    val = torch.randint(-2**63, 2**63 - 1, (batch, n), dtype=torch.int64, device="cuda", generator=g)
+    planes = torch.empty((plan.num_primes(), batch, n), dtype=torch.int64, device="cuda")
+    for _ in range(reps):
+        plan.fwd(val, planes)
+        plan.inv(val, planes)
+elif which in ("product", "product_generic"):
+    f = cntt.prime.largest_prime_in_arithmetic_progression64
+    if which == "product":    # two u32 primes of one class: the fused kernels
+        p1 = f(1 << 17, 1, 1 << 30, 1 << 31); p2 = f(1 << 17, 1, 1 << 30, p1 - 1)
+    else:                     # a u32 and a u64 prime: k_product_reduce / k_product_crt around the prime kernels
+        p1 = f(1 << 17, 1, 1 << 20, 1 << 21); p2 = f(1 << 17, 1, 1 << 41, 1 << 42)
+    plan = cntt.product.Plan.try_new(n, p1 * p2, [p1, p2])
+    std = torch.randint(0, p1 * p2, (batch, n), dtype=torch.int64, device="cuda", generator=g)
+    a = torch.empty((batch, plan.ntt_domain_len()), dtype=torch.int64, device="cuda")
+    acc = torch.zeros_like(a)
+    for _ in range(reps):
+        plan.fwd(a, std)
+        plan.mul_accumulate(acc, a, a)
+        plan.inv(std, a)
 elif which == "polymul128":
     plan = cntt.native128.Plan32.try_new(n)
     lhs = torch.randint(-2**63, 2**63 - 1, (batch, n, 2), dtype=torch.int64, device="cuda", generator=g)
