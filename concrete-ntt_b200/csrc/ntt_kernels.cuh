@@ -627,12 +627,21 @@ k_ntt_strided(const typename A::Tw* __restrict__ tw, const typename A::Mod m, ty
     const typename E::TwSrc tws = {tw, nullptr, nullptr};
 #pragma unroll
     for (int k = 0; k < K; k++) x[0][k] = base[(size_t)k * bsub];
+    // Solinas, leading levels of the whole transform (s0 == 0: heap nodes < 2^LOGK <= 16): multiplier-free shift butterflies
+    bool shifted = false;
+    if constexpr (ShiftHead<A>::value && LOGK <= 4) shifted = s0 == 0 && m.shift_head != 0;
     if constexpr (FWD) {
-        E::template fwd_pass<0, 1>(x, tws, nu, 0, m);
+        if constexpr (ShiftHead<A>::value && LOGK <= 4) {
+            if (shifted) E::template shift_levels_fwd<1>(x, std::make_integer_sequence<int, LOGK>{});
+        }
+        if (!shifted) E::template fwd_pass<0, 1>(x, tws, nu, 0, m);
 #pragma unroll
         for (int k = 0; k < K; k++) base[(size_t)k * bsub] = x[0][k]; // lazy range, consumed by the next level
     } else {
-        E::template inv_pass<0, 1>(x, tws, nu, 0, m);
+        if constexpr (ShiftHead<A>::value && LOGK <= 4) {
+            if (shifted) E::template shift_levels_inv<1>(x, std::make_integer_sequence<int, LOGK>{});
+        }
+        if (!shifted) E::template inv_pass<0, 1>(x, tws, nu, 0, m);
 #pragma unroll
         for (int k = 0; k < K; k++) base[(size_t)k * bsub] = A::canon_inv(x[0][k], m);
     }
