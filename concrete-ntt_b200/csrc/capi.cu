@@ -728,6 +728,7 @@ struct cntt_native_plan {
     int nprimes;
     cntt_prime32_plan* sub[10];
     uint2* d_fused_last; // fwd/inv last-pass tables of the fused kernel's engine for every prime (2 * nprimes * n entries)
+    uint32_t* d_bin0;    // binary plans: pass-0 tables of the {0,1} operand (nprimes * kBin0Entries entries), see native_fused.cuh
     NativePlanDev dev;
     Staging stg;
 };
@@ -747,6 +748,7 @@ static int native_plan_new_impl(size_t n, int word_bits, int binary, int device,
     pl->n = n; pl->kind = kind; pl->device = device; pl->nprimes = native_num_primes(kind);
     for (int k = 0; k < 10; k++) pl->sub[k] = nullptr;
     pl->d_fused_last = nullptr;
+    pl->d_bin0 = nullptr;
     // decide Some/None on the host for every prime before touching the device
     for (int k = 0; k < pl->nprimes; k++) {
         uint64_t psi;
@@ -774,8 +776,51 @@ static int native_plan_new_impl(size_t n, int word_bits, int binary, int device,
     // the fused polymul (N <= 4096) may carry the product on fewer primes than the plan owns (native.hpp, native_fused_np)
     native_lhs_scale(pl->dev.logn, pl->dev.lscale, prime_set,
                      native_fused_supported(pl->dev.logn) ? native_fused_np(kind, pl->nprimes) : pl->nprimes);
-    for (int k = 0; k < 10; k++) pl->dev.fused_fwd_last[k] = pl->dev.fused_inv_last[k] = nullptr;
+    for (int k = 0; k < 10; k++) { pl->dev.fused_fwd_last[k] = pl->dev.fused_inv_last[k] = nullptr; pl->dev.bin0[k] = nullptr; }
     const bool fused = native_fused_supported(pl->dev.logn), large = native_large_supported(pl->dev.logn);
+    if (fused && kind >= NK_BINARY32) {
+        // pass-0 tables of the binary operand (native_fused.cuh, binary_pass0): run the first r1 levels of the forward transform
+        // (root sub-tree: heap nodes 2^lvl + g, the plan's own twiddles) on unit vectors, then sum the columns per nibble pattern
+        const int logn = pl->dev.logn, logr = native_fused_logr(kind, logn), passes = (logn + logr - 1) / logr;
+        const int r1 = logn - (passes - 1) * logr, S = 1 << r1, QB = S < 4 ? S : 4, NQ = S / QB;
+        std::vector<uint32_t> tab((size_t)pl->nprimes * kBin0Entries, 0u);
+        for (int k = 0; k < pl->nprimes && passes >= 2; k++) {
+            const uint64_t p = pl->sub[k]->p;
+            std::vector<std::vector<uint64_t>> col((size_t)S, std::vector<uint64_t>((size_t)S, 0)); // col[m][j]: output j of unit input m
+            for (int mi = 0; mi < S; mi++) {
+                std::vector<uint64_t>& v = col[(size_t)mi];
+                v[(size_t)mi] = 1;
+                for (int lvl = 0; lvl < r1; lvl++) {
+                    const int half = S >> (lvl + 1);
+                    for (int g = 0; g < (1 << lvl); g++) {
+                        const uint64_t w = pl->sub[k]->head_fwd.e[(1 << lvl) + g].x;
+                        for (int u = 0; u < half; u++) {
+                            const uint64_t a = v[(size_t)(2 * half * g + u)], b = v[(size_t)(2 * half * g + u + half)] * w % p;
+                            v[(size_t)(2 * half * g + u)] = (a + b) % p;
+                            v[(size_t)(2 * half * g + u + half)] = (a + p - b) % p;
+                        }
+                    }
+                }
+            }
+            uint32_t* t = tab.data() + (size_t)k * kBin0Entries;
+            for (int q = 0; q < NQ; q++)
+                for (int pat = 0; pat < 16; pat++)
+                    for (int j = 0; j < S; j++) {
+                        uint64_t acc = 0;
+                        for (int i = 0; i < QB; i++)
+                            if (pat >> i & 1) acc = (acc + col[(size_t)(QB * q + i)][(size_t)j]) % p;
+                        t[(q * 16 + pat) * S + j] = (uint32_t)acc;
+                    }
+        }
+        DeviceGuard g(device);
+        cudaError_t e = g.ok ? cudaMalloc(&pl->d_bin0, tab.size() * sizeof(uint32_t)) : cudaErrorInvalidDevice;
+        if (e == cudaSuccess) e = cudaMemcpy(pl->d_bin0, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cntt_native_plan_free(pl);
+            return cuda_fail(e, "native plan upload");
+        }
+        for (int k = 0; k < pl->nprimes; k++) pl->dev.bin0[k] = pl->d_bin0 + (size_t)k * kBin0Entries;
+    }
     if (fused || large) {
         DeviceGuard g(device);
         cudaError_t e = g.ok ? cudaMalloc(&pl->d_fused_last, 2 * (size_t)pl->nprimes * n * sizeof(uint2)) : cudaErrorInvalidDevice;
@@ -813,8 +858,9 @@ CNTT_API void cntt_native_plan_free(cntt_native_plan* pl)
         DeviceGuard g(pl->device);
         pl->stg.release();
         if (pl->d_fused_last) cudaFree(pl->d_fused_last);
+        if (pl->d_bin0) cudaFree(pl->d_bin0);
     }
-    for (int k = 0; k < pl->nprimes; k++) cntt_prime32_plan_free(pl->sub[k]);
+    for (int k = 0; k < pl->nprimes; k++) if (pl->sub[k]) cntt_prime32_plan_free(pl->sub[k]);
     delete pl;
 }
 CNTT_API size_t cntt_native_ntt_size(const cntt_native_plan* pl) { return pl ? pl->n : 0; }

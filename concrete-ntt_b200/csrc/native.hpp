@@ -70,7 +70,12 @@ struct NativePlanDev {
     const uint2* fused_fwd_last[10]; // last-pass twiddle layouts of the fused kernel's engine (Engine::TwSrc::last); N > 4096: of the
                                      // large path's 4096-word row engine (native_large_build_last)
     const uint2* fused_inv_last[10];
+    // binary plans, fused polymul: table of the first register pass of the {0,1} operand's forward transform, per prime
+    // (native_fused.cuh, binary_pass0); nullptr = not built
+    const uint32_t* bin0[10];
 };
+// entries of one prime's bin0 table: [nibble q][4-bit pattern v][output slot j of a 2^r1-slot set]
+constexpr int kBin0Entries = 4 * 16 * 16;
 
 void native_lhs_scale(int logn, uint2 (*out)[4], int set, int np);
 

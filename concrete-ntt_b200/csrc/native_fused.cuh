@@ -28,7 +28,49 @@ namespace cntt {
 #endif
 constexpr int kFusedMinLogN = 5, kFusedMaxLogN = 12;
 
+// Binary plans: rhs in {0,1}^N (src/native_binary64.rs:423-444; anything else is unspecified there).  The first register pass of
+// its forward transform is then a LINEAR map of bits with plan-time coefficients -- the same for every thread, because pass 0
+// uses the root sub-tree -- so it is evaluated from a table instead of with butterflies: the 2^R1 slots of a set are cut into
+// nibbles, tab[q][v][j] = sum over the bits of v of (coefficient of input 4q+bit in output j), and output j is the sum of one row
+// per nibble (at most four canonical values: inside the lazy range [0,4p)).  N = 2048: 24 butterflies per thread become 8 vector
+// loads and 16 additions.  Only bit 0 of an rhs word is read.  B200 (profiles/r02_experiments.txt): binary64 N=2048 26.2 -> 26.8,
+// binary32 40.8 -> 43.0, binary64 N=256 262 -> 275 M polymul/s; with four nibbles (R1 = 4, N = 4096) it loses 8 %, so R1 <= 3 only.
+#ifndef CNTT_BINARY_LUT
+#define CNTT_BINARY_LUT 1
+#endif
+template <class E>
+__device__ __forceinline__ void binary_pass0(uint32_t (&x)[E::R], const uint32_t* __restrict__ tab)
+{
+    constexpr int R1 = E::G::R1, S = 1 << R1, NSETS = E::R >> R1, QB = S < 4 ? S : 4, NQ = S / QB;
+#pragma unroll
+    for (int s = 0; s < NSETS; s++) {
+        uint32_t y[S];
+#pragma unroll
+        for (int j = 0; j < S; j++) y[j] = 0;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int i = 0; i < QB; i++) v |= (x[s + (QB * q + i) * NSETS] & 1u) << i;
+            const uint32_t* row = tab + (q * 16 + v) * S;
+            if constexpr (S >= 4) {
+#pragma unroll
+                for (int j = 0; j < S; j += 4) {
+                    const uint4 t = __ldg(reinterpret_cast<const uint4*>(row + j));
+                    y[j] += t.x; y[j + 1] += t.y; y[j + 2] += t.z; y[j + 3] += t.w;
+                }
+            } else {
+                const uint2 t = __ldg(reinterpret_cast<const uint2*>(row));
+                y[0] += t.x; y[1] += t.y;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < S; j++) x[s + j * NSETS] = y[j];
+    }
+}
+
 struct FusedParams {
+    const uint32_t* bin0[10];
     const uint2* tw_fwd[10];
     const uint2* tw_inv[10];
     const uint2* tw_fwd_last[10];
@@ -129,7 +171,19 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
                 x[1][k] = BINARY ? (uint32_t)rlo[k] : dev::residue<LIMBS, false>(rlo[k], WB == 16 ? rhi[k] : 0ull, c.red[pk], p);
             }
         }
-        E::template fwd<2>(x, sm, typename E::TwSrc{fp.tw_fwd[pk], fp.tw_fwd_last[pk]}, 1u, tid, m);
+        if constexpr (BINARY && CNTT_BINARY_LUT != 0 && E::P >= 2 && !E::kLoopPasses && E::G::R1 <= 3) {
+            const typename E::TwSrc tws = {fp.tw_fwd[pk], fp.tw_fwd_last[pk]};
+            uint32_t xl[1][R];
+#pragma unroll
+            for (int k = 0; k < R; k++) xl[0][k] = x[0][k];
+            E::template fwd_pass<0, 1>(xl, tws, 1u, tid, m);     // lhs: pass 0 with butterflies
+            binary_pass0<E>(x[1], fp.bin0[pk]);                   // rhs: pass 0 from the table
+#pragma unroll
+            for (int k = 0; k < R; k++) x[0][k] = xl[0][k];
+            E::template fwd_after_pass0<2>(x, sm, tws, 1u, tid, m);
+        } else {
+            E::template fwd<2>(x, sm, typename E::TwSrc{fp.tw_fwd[pk], fp.tw_fwd_last[pk]}, 1u, tid, m);
+        }
         uint32_t y[1][R];
         const uint32_t pinv = c.pinv[pk];
 #pragma unroll
@@ -184,6 +238,8 @@ static cudaError_t launch_fused_one(const NativePlanDev& pl, void* prod, const v
     typedef FusedCfg<KIND, LOGN, LOGR> Cfg;
     FusedParams fp;
     for (int k = 0; k < Cfg::NP; k++) {
+        fp.bin0[k] = pl.bin0[k];
+        if (KIND >= NK_BINARY32 && CNTT_BINARY_LUT != 0 && Cfg::E::P >= 2 && Cfg::E::G::R1 <= 3 && !fp.bin0[k]) return cudaErrorInvalidValue;
         fp.tw_fwd[k] = pl.sub[k].tw_fwd;
         fp.tw_inv[k] = pl.sub[k].tw_inv;
         fp.tw_fwd_last[k] = pl.fused_fwd_last[k];

@@ -309,6 +309,17 @@ struct Engine {
             fwd_from<Q + 1, NP>(x, sm, tw, nu0, tid, m);
         }
     }
+    // the rest of a forward transform whose pass 0 the caller has already done (x in pass-0 layout): exchange, passes 1 .. P-1
+    template <int NP>
+    static __device__ __forceinline__ void fwd_after_pass0(W (&x)[NP][R], W* sm, const TwSrc& tw, unsigned nu0, int tid, const Mod& m)
+    {
+        static_assert(!kLoopPasses && P >= 2, "compile-time pass chain only");
+        scatter<0, NP>(x, sm, tid);
+        __syncthreads();
+        gather<1, NP>(x, sm, tid);
+        if constexpr (NBUF == 1 && 2 < P) __syncthreads();
+        fwd_from<1, NP>(x, sm, tw, nu0, tid, m);
+    }
     template <int NP>
     static __device__ __forceinline__ void fwd(W (&x)[NP][R], W* sm, const TwSrc& tw, unsigned nu0, int tid, const Mod& m)
     {
