@@ -55,15 +55,40 @@ constexpr int kMaxCtaLogN = 12; // largest block a CTA keeps on chip when a tran
 #endif
 constexpr bool kR32 = CNTT_R32_MINLOGN != 0;
 template <class A, int LOGN> constexpr bool r32_size() { return kR32 && sizeof(typename A::W) == 4 && LOGN >= CNTT_R32_MINLOGN && LOGN <= CNTT_R32_MAXBLK; }
+constexpr int large_blk32(int logn, bool fwd);
 // size of the contiguous blocks the CTA kernel transforms for a plan of 2^logn words
 template <class A> constexpr int cta_block_logn(int logn, bool fwd)
 {
     if (logn <= kMaxCtaLogN) return logn;
-    if (sizeof(typename A::W) == 4 && kR32) return (logn >= CNTT_R32_MINLOGN && logn <= CNTT_R32_MAXBLK) ? logn : kMaxCtaLogN;
+    if (sizeof(typename A::W) == 4 && kR32) return (logn >= CNTT_R32_MINLOGN && logn <= CNTT_R32_MAXBLK) ? logn : large_blk32(logn, fwd);
     if (logn == 13 && (sizeof(typename A::W) == 4 ? CNTT_CTA13 != 0 : (CNTT_CTA13_64 == 1 || (CNTT_CTA13_64 == 2 && fwd)))) return 13;
 #if CNTT_CTA14
     if (logn == 14 && sizeof(typename A::W) == 4 && (CNTT_CTA14 == 1 || fwd)) return 14;
 #endif
+    return kMaxCtaLogN;
+}
+// 32-bit words beyond the single-CTA sizes: levels one strided launch may run (words per thread = 2^k) and the block size the CTA
+// kernel then transforms.  r01: k <= 4 and 4096-word blocks in both directions.  r02 (profiles/r02_experiments.txt, "strided depth"):
+// the FORWARD transform gains from five leading levels in one strided launch and 1024 / 2048-word blocks (N = 32768 8.0 -> 9.6,
+// N = 65536 4.0 -> 4.6 M NTT/s); six levels lose, and the inverse loses or stays flat with any of it, so it keeps the r01 scheme.
+#ifndef CNTT_STRIDED_MAXK32_FWD
+#define CNTT_STRIDED_MAXK32_FWD 5
+#endif
+#ifndef CNTT_STRIDED_MAXK32_INV
+#define CNTT_STRIDED_MAXK32_INV 4
+#endif
+#define CNTT_STRIDED_MAXK32 (CNTT_STRIDED_MAXK32_FWD > CNTT_STRIDED_MAXK32_INV ? CNTT_STRIDED_MAXK32_FWD : CNTT_STRIDED_MAXK32_INV)
+#ifndef CNTT_LARGE_MINBLK32_FWD
+#define CNTT_LARGE_MINBLK32_FWD 10
+#endif
+constexpr int large_blk32(int logn, bool fwd)
+{
+    // forward: the smallest block >= CNTT_LARGE_MINBLK32_FWD that ONE strided launch reaches; inverse (and everything one launch
+    // cannot reach): 4096-word blocks
+    if (fwd && CNTT_STRIDED_MAXK32_FWD > 4) {
+        const int blk = logn - CNTT_STRIDED_MAXK32_FWD;
+        if (blk <= kMaxCtaLogN) return blk < CNTT_LARGE_MINBLK32_FWD ? CNTT_LARGE_MINBLK32_FWD : blk;
+    }
     return kMaxCtaLogN;
 }
 constexpr int kMaxLogN = 26;    // two-level + repeated strided passes; table memory is the limit
@@ -837,8 +862,11 @@ cudaError_t launch_strided(const PlanDev<A>& pl, int logk, typename A::W* data, 
     case 2: return launch_strided_one<A, 2, FWD>(pl, data, batch, s0, poly_stride, st);
     case 3: return launch_strided_one<A, 3, FWD>(pl, data, batch, s0, poly_stride, st);
     case 4: return launch_strided_one<A, 4, FWD>(pl, data, batch, s0, poly_stride, st);
-    default: return cudaErrorInvalidValue;
+    default: break;
     }
+    if constexpr (sizeof(typename A::W) == 4 && CNTT_STRIDED_MAXK32 >= 5) { if (logk == 5) return launch_strided_one<A, 5, FWD>(pl, data, batch, s0, poly_stride, st); }
+    if constexpr (sizeof(typename A::W) == 4 && CNTT_STRIDED_MAXK32 >= 6) { if (logk == 6) return launch_strided_one<A, 6, FWD>(pl, data, batch, s0, poly_stride, st); }
+    return cudaErrorInvalidValue;
 }
 
 // Full transform of `batch` polynomials.  N <= 4096: one CTA-kernel launch.  Larger: leading stages
@@ -853,11 +881,12 @@ cudaError_t launch_ntt(const PlanDev<A>& pl, typename A::W* data, size_t batch, 
     const int blk = cta_block_logn<A>(pl.logn, FWD);
     if (pl.logn == blk) return launch_cta<A, FWD>(pl, pl.logn, data, batch, 0, poly_stride, st);
     const int lead = pl.logn - blk;
+    constexpr int kmax = sizeof(typename A::W) == 4 ? (FWD ? CNTT_STRIDED_MAXK32_FWD : CNTT_STRIDED_MAXK32_INV) : 4;
     cudaError_t e;
     if constexpr (FWD) {
         int s0 = 0;
         while (s0 < lead) {
-            const int k = (lead - s0) < 4 ? (lead - s0) : 4;
+            const int k = (lead - s0) < kmax ? (lead - s0) : kmax;
             if ((e = launch_strided<A, true>(pl, k, data, batch, s0, poly_stride, st)) != cudaSuccess) return e;
             s0 += k;
         }
@@ -866,7 +895,7 @@ cudaError_t launch_ntt(const PlanDev<A>& pl, typename A::W* data, size_t batch, 
         if ((e = launch_cta<A, false>(pl, blk, data, (unsigned long long)batch << lead, lead, poly_stride, st)) != cudaSuccess) return e;
         // mirror of the forward schedule: last forward chunk first
         int chunks[8], nc = 0, s = 0;
-        while (s < lead) { const int k = (lead - s) < 4 ? (lead - s) : 4; chunks[nc++] = k; s += k; }
+        while (s < lead) { const int k = (lead - s) < kmax ? (lead - s) : kmax; chunks[nc++] = k; s += k; }
         for (int c = nc - 1; c >= 0; c--) {
             s -= chunks[c];
             if ((e = launch_strided<A, false>(pl, chunks[c], data, batch, s, poly_stride, st)) != cudaSuccess) return e;
