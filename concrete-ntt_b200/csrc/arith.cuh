@@ -385,7 +385,7 @@ struct A64S {
     // ---- power-of-two twiddles.  2 has order 192 modulo p (2^96 = -1), so every 64-th root of unity is +-2^k, k < 96: the twiddles
     //      of the first five levels of ANY transform (level j uses primitive 2^(j+2)-th roots).  The reference's root search starts
     //      from -1 and takes square roots (roots.rs:68-91), so those entries do not depend on N: tw[h] = 2^kShiftExp[h] for the heap
-    //      nodes h < 16 (levels 0..3; checked against the real table when a plan is built).  x * 2^(32a+b) with x = (x1:x0), y = x << b
+    //      nodes h < 32 (levels 0..4; checked against the real table when a plan is built).  x * 2^(32a+b) with x = (x1:x0), y = x << b
     //      = (y2:y1:y0) and phi = 2^32 (phi^2 = phi - 1, phi^3 = -1):
     //        a = 0:  (y1:y0) + y2 EPS  =  (y1:y0) - [(~y2) : (y2 + 1)]  (+ p on borrow)     [(~y2):(y2+1) = p - y2 EPS]
     //        a = 1:  (y0:0) - y2 + y1 EPS                                                    the generic 128 -> 64 reduction
@@ -509,12 +509,15 @@ struct A64G {
     static __device__ __forceinline__ W mul_acc(W acc, W a, W b, const Mod& m) { return add(acc, mulmod(a, b, m), m); }
 };
 
-// log2 of the Solinas plan's forward twiddles at heap nodes 1..15 (levels 0..3): tw[h] = 2^kShiftExp[h] mod p, inverse table
-// 2^(192 - kShiftExp[h]).  Derived from the reference's root chain (-1, sqrt, sqrt, ...) and verified per plan (capi.cu).
+// log2 of the Solinas plan's forward twiddles at heap nodes 1..31 (levels 0..4, all the 64-th roots of unity the transform uses):
+// tw[h] = 2^shift_exp(h) mod p, inverse table 2^(192 - shift_exp(h)).  Derived from the reference's root chain (-1, sqrt, sqrt, ...)
+// and verified per plan (capi.cu).
+constexpr int kShiftNodes = 32;
 __host__ __device__ constexpr int shift_exp(int h)
 {
-    constexpr int e[16] = {0, 48, 120, 168, 156, 12, 84, 132, 78, 126, 6, 54, 42, 90, 162, 18};
-    return e[h & 15];
+    constexpr int e[kShiftNodes] = {0,  48, 120, 168, 156, 12, 84,  132, 78,  126, 6,  54, 42, 90,  162, 18,
+                                    39, 87, 159, 15,  3,   51, 123, 171, 117, 165, 45, 93, 81, 129, 9,   57};
+    return e[h & (kShiftNodes - 1)];
 }
 template <class A> struct ShiftHead { static constexpr bool value = false; };
 #ifndef CNTT_SHIFT_HEAD

@@ -435,7 +435,7 @@ static int build_prime64(size_t n, uint64_t p, int device, cntt_prime64_plan** o
     m.shift_head = 0;
     if (cls == C64_S) { // the shift butterflies of the leading levels assume tw[h] = 2^shift_exp(h): check it against the real table
         bool ok = true;
-        for (size_t h = 1; h < 16 && h < n; h++) {
+        for (size_t h = 1; h < (size_t)kShiftNodes && h < n; h++) {
             uint64_t want = 1, wanti = 1;
             for (int k = 0; k < shift_exp((int)h); k++) want = fp.mul(want, 2);
             for (int k = 0; k < (192 - shift_exp((int)h)) % 192; k++) wanti = fp.mul(wanti, 2);

@@ -55,18 +55,6 @@ constexpr int kMaxCtaLogN = 12; // largest block a CTA keeps on chip when a tran
 #endif
 constexpr bool kR32 = CNTT_R32_MINLOGN != 0;
 template <class A, int LOGN> constexpr bool r32_size() { return kR32 && sizeof(typename A::W) == 4 && LOGN >= CNTT_R32_MINLOGN && LOGN <= CNTT_R32_MAXBLK; }
-constexpr int large_blk32(int logn, bool fwd);
-// size of the contiguous blocks the CTA kernel transforms for a plan of 2^logn words
-template <class A> constexpr int cta_block_logn(int logn, bool fwd)
-{
-    if (logn <= kMaxCtaLogN) return logn;
-    if (sizeof(typename A::W) == 4 && kR32) return (logn >= CNTT_R32_MINLOGN && logn <= CNTT_R32_MAXBLK) ? logn : large_blk32(logn, fwd);
-    if (logn == 13 && (sizeof(typename A::W) == 4 ? CNTT_CTA13 != 0 : (CNTT_CTA13_64 == 1 || (CNTT_CTA13_64 == 2 && fwd)))) return 13;
-#if CNTT_CTA14
-    if (logn == 14 && sizeof(typename A::W) == 4 && (CNTT_CTA14 == 1 || fwd)) return 14;
-#endif
-    return kMaxCtaLogN;
-}
 // 32-bit words beyond the single-CTA sizes: levels one strided launch may run (words per thread = 2^k) and the block size the CTA
 // kernel then transforms.  r01: k <= 4 and 4096-word blocks in both directions.  r02 (profiles/r02_experiments.txt, "strided depth"):
 // the FORWARD transform gains from five leading levels in one strided launch and 1024 / 2048-word blocks (N = 32768 8.0 -> 9.6,
@@ -81,6 +69,32 @@ template <class A> constexpr int cta_block_logn(int logn, bool fwd)
 #ifndef CNTT_LARGE_MINBLK32_FWD
 #define CNTT_LARGE_MINBLK32_FWD 10
 #endif
+// Solinas: all five power-of-two levels (heap nodes < 32) in ONE strided launch of shift butterflies (32 words per thread), then
+// small blocks (which run faster per word than 4096-word ones); 4 = the r01 scheme.  Measured (profiles/r02_experiments.txt,
+// "k64s"): within +-4 % of the r01 scheme up to N = 65536 (the 32-word strided kernel needs 174-188 registers), so 4 stays.
+#ifndef CNTT_STRIDED_MAXK64S
+#define CNTT_STRIDED_MAXK64S 4
+#endif
+#ifndef CNTT_LARGE_MINBLK64S
+#define CNTT_LARGE_MINBLK64S 9
+#endif
+#ifndef CNTT_LARGE_MINLOGN64S
+#define CNTT_LARGE_MINLOGN64S 14
+#endif
+constexpr int large_blk32(int logn, bool fwd);
+// size of the contiguous blocks the CTA kernel transforms for a plan of 2^logn words
+template <class A> constexpr int cta_block_logn(int logn, bool fwd)
+{
+    if (logn <= kMaxCtaLogN) return logn;
+    if (sizeof(typename A::W) == 4 && kR32) return (logn >= CNTT_R32_MINLOGN && logn <= CNTT_R32_MAXBLK) ? logn : large_blk32(logn, fwd);
+    if (ShiftHead<A>::value && CNTT_STRIDED_MAXK64S > 4 && logn >= CNTT_LARGE_MINLOGN64S && logn - CNTT_STRIDED_MAXK64S <= kMaxCtaLogN)
+        return logn - CNTT_STRIDED_MAXK64S < CNTT_LARGE_MINBLK64S ? CNTT_LARGE_MINBLK64S : logn - CNTT_STRIDED_MAXK64S;
+    if (logn == 13 && (sizeof(typename A::W) == 4 ? CNTT_CTA13 != 0 : (CNTT_CTA13_64 == 1 || (CNTT_CTA13_64 == 2 && fwd)))) return 13;
+#if CNTT_CTA14
+    if (logn == 14 && sizeof(typename A::W) == 4 && (CNTT_CTA14 == 1 || fwd)) return 14;
+#endif
+    return kMaxCtaLogN;
+}
 constexpr int large_blk32(int logn, bool fwd)
 {
     // forward: the smallest block >= CNTT_LARGE_MINBLK32_FWD that ONE strided launch reaches; inverse (and everything one launch
@@ -502,7 +516,7 @@ k_ntt_cta_bulk(const typename A::Tw* __restrict__ tw, const typename A::Tw* __re
     typedef typename A::W W;
     constexpr int T = E::T, R = E::R, N = E::N;
     constexpr unsigned kBytes = N * sizeof(W);
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: [GP stage tiles of N words][GP mbarriers][exchange buffers]
     W* stage_all = reinterpret_cast<W*>(smem_raw);
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)GP * kBytes);
@@ -652,18 +666,18 @@ k_ntt_strided(const typename A::Tw* __restrict__ tw, const typename A::Mod m, ty
     const typename E::TwSrc tws = {tw, nullptr, nullptr};
 #pragma unroll
     for (int k = 0; k < K; k++) x[0][k] = base[(size_t)k * bsub];
-    // Solinas, leading levels of the whole transform (s0 == 0: heap nodes < 2^LOGK <= 16): multiplier-free shift butterflies
+    // Solinas, leading levels of the whole transform (s0 == 0: heap nodes < 2^LOGK <= 32): multiplier-free shift butterflies
     bool shifted = false;
-    if constexpr (ShiftHead<A>::value && LOGK <= 4) shifted = s0 == 0 && m.shift_head != 0;
+    if constexpr (ShiftHead<A>::value && LOGK <= 5) shifted = s0 == 0 && m.shift_head != 0;
     if constexpr (FWD) {
-        if constexpr (ShiftHead<A>::value && LOGK <= 4) {
+        if constexpr (ShiftHead<A>::value && LOGK <= 5) {
             if (shifted) E::template shift_levels_fwd<1>(x, std::make_integer_sequence<int, LOGK>{});
         }
         if (!shifted) E::template fwd_pass<0, 1>(x, tws, nu, 0, m);
 #pragma unroll
         for (int k = 0; k < K; k++) base[(size_t)k * bsub] = x[0][k]; // lazy range, consumed by the next level
     } else {
-        if constexpr (ShiftHead<A>::value && LOGK <= 4) {
+        if constexpr (ShiftHead<A>::value && LOGK <= 5) {
             if (shifted) E::template shift_levels_inv<1>(x, std::make_integer_sequence<int, LOGK>{});
         }
         if (!shifted) E::template inv_pass<0, 1>(x, tws, nu, 0, m);
@@ -864,6 +878,7 @@ cudaError_t launch_strided(const PlanDev<A>& pl, int logk, typename A::W* data, 
     case 4: return launch_strided_one<A, 4, FWD>(pl, data, batch, s0, poly_stride, st);
     default: break;
     }
+    if constexpr (ShiftHead<A>::value && CNTT_STRIDED_MAXK64S >= 5) { if (logk == 5) return launch_strided_one<A, 5, FWD>(pl, data, batch, s0, poly_stride, st); }
     if constexpr (sizeof(typename A::W) == 4 && CNTT_STRIDED_MAXK32 >= 5) { if (logk == 5) return launch_strided_one<A, 5, FWD>(pl, data, batch, s0, poly_stride, st); }
     if constexpr (sizeof(typename A::W) == 4 && CNTT_STRIDED_MAXK32 >= 6) { if (logk == 6) return launch_strided_one<A, 6, FWD>(pl, data, batch, s0, poly_stride, st); }
     return cudaErrorInvalidValue;
@@ -881,7 +896,7 @@ cudaError_t launch_ntt(const PlanDev<A>& pl, typename A::W* data, size_t batch, 
     const int blk = cta_block_logn<A>(pl.logn, FWD);
     if (pl.logn == blk) return launch_cta<A, FWD>(pl, pl.logn, data, batch, 0, poly_stride, st);
     const int lead = pl.logn - blk;
-    constexpr int kmax = sizeof(typename A::W) == 4 ? (FWD ? CNTT_STRIDED_MAXK32_FWD : CNTT_STRIDED_MAXK32_INV) : 4;
+    constexpr int kmax = sizeof(typename A::W) == 4 ? (FWD ? CNTT_STRIDED_MAXK32_FWD : CNTT_STRIDED_MAXK32_INV) : ShiftHead<A>::value ? CNTT_STRIDED_MAXK64S : 4;
     cudaError_t e;
     if constexpr (FWD) {
         int s0 = 0;
