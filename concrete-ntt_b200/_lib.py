@@ -61,6 +61,7 @@ SIGNATURES.update({
     "cntt_native_fwd_binary_host": (_int, [_vp, _vp, _vp, _sz, _sz]),
     "cntt_native_inv_host": (_int, [_vp, _vp, _vp, _sz, _sz]),
     "cntt_native_polymul": (_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "cntt_native_polymul_ntt_rhs": (_int, [_vp, _vp, _vp, _vp, _sz, _sz, _vp]),
     "cntt_native_polymul_host": (_int, [_vp, _vp, _vp, _vp, _sz, _sz]),
     "cntt_native_polymul_host_multi": (_int, [C.POINTER(_vp), _int, _vp, _vp, _vp, _sz, _sz]),
     "cntt_native52_plan_new": (_int, [_sz, _int, _int, _int, C.POINTER(_vp)]),

@@ -987,6 +987,22 @@ static cudaError_t native_polymul_impl(const cntt_native_plan* pl, void* prod, c
     return native_polymul_unfused(pl, prod, lhs, rhs, batch, st);
 }
 
+// EXTENSION: negacyclic_polymul with the rhs operand already transformed (TFHE keeps its bootstrapping key in the NTT domain).
+// d_rhs_planes: what cntt_native_fwd (cntt_native_fwd_binary for binary plans) wrote for `rhs_batch` polynomials -- plane k of key b at
+// d_rhs_planes[(k * rhs_batch + b) * n]; rhs_batch == batch (one key per product) or 1 (one key for the whole batch).
+CNTT_API int cntt_native_polymul_ntt_rhs(const cntt_native_plan* pl, void* d_prod, const void* d_lhs, const uint32_t* d_rhs_planes, size_t rhs_batch,
+                                         size_t batch, void* stream)
+{
+    if (!pl || ((!d_prod || !d_lhs || !d_rhs_planes) && batch)) return CNTT_NULL_POINTER;
+    if (misaligned16(d_prod, d_lhs, d_rhs_planes)) return CNTT_MISALIGNED;
+    if (rhs_batch != batch && rhs_batch != 1) return CNTT_LENGTH_MISMATCH;
+    if (batch == 0) return CNTT_OK;
+    GUARD(pl->device);
+    const cudaError_t e = native_polymul_fused_pre(pl->dev, d_prod, d_lhs, d_rhs_planes, batch, rhs_batch * pl->n, rhs_batch == 1 ? 0 : pl->n, (cudaStream_t)stream);
+    if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); return CNTT_UNSUPPORTED; } // N < 256 or N > 4096: use fwd / mul_assign_normalize / inv
+    CU(e);
+    return CNTT_OK;
+}
 CNTT_API int cntt_native_polymul(const cntt_native_plan* pl, void* d_prod, const void* d_lhs, const void* d_rhs, size_t batch, void* stream)
 {
     if (!pl || ((!d_prod || !d_lhs || !d_rhs) && batch)) return CNTT_NULL_POINTER;

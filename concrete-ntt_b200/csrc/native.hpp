@@ -104,6 +104,11 @@ constexpr int native_fused_logr(int kind, int logn)
 cudaError_t native_polymul_fused(const NativePlanDev& pl, void* prod, const void* lhs, const void* rhs, size_t batch,
                                  cudaStream_t st);
 
+// the same with the rhs operand already in the NTT domain (residue planes as written by cntt_native_fwd): plane k of key b at
+// rhs_planes + k * plane_stride + b * poly_stride words; poly_stride = 0 shares one key.  cudaErrorNotSupported outside 256 <= N <= 4096
+cudaError_t native_polymul_fused_pre(const NativePlanDev& pl, void* prod, const void* lhs, const uint32_t* rhs_planes, size_t batch,
+                                     size_t plane_stride, size_t poly_stride, cudaStream_t st);
+
 // fused split-phase forward kernel (native_split.cu): what = 0 fwd, 1 fwd_binary; cudaErrorNotSupported when no fused
 // variant exists for the plan's size (the caller then composes reduce / transforms / CRT)
 cudaError_t native_split_fused(const NativePlanDev& pl, void* value, uint32_t* planes, size_t plane_stride, size_t batch, int what,

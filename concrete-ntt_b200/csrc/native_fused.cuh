@@ -70,6 +70,9 @@ __device__ __forceinline__ void binary_pass0(uint32_t (&x)[E::R], const uint32_t
 }
 
 struct FusedParams {
+    // PRE (pre-transformed rhs): `rhs` points at residue planes in the NTT domain, as written by cntt_native_fwd / fwd_binary; plane k of
+    // key b at rhs + k * pre_plane_stride + b * pre_poly_stride words (pre_poly_stride = 0: one key for the whole batch)
+    unsigned long long pre_plane_stride, pre_poly_stride;
     const uint32_t* bin0[10];
     const uint2* tw_fwd[10];
     const uint2* tw_inv[10];
@@ -104,7 +107,11 @@ struct FusedCfg {
 //   two forward NTTs, twiddle loads shared
 //   pointwise Montgomery product  A B 2^-32 = a b / N   in (0,2p)    (replaces mul_assign_normalize)
 //   inverse NTT, canonical residue parked in shared memory
-template <int KIND, int LOGN, int LOGR>
+//
+// PRE = the rhs operand arrives already transformed (the TFHE shape: the key stays in the NTT domain, src/prime32.rs:905-927 is what a
+// caller of the reference does per prime): only the lhs is reduced and transformed, the rhs residues are read in the last-pass layout
+// (R consecutive words per thread), and two of the three transforms per prime remain.
+template <int KIND, int LOGN, int LOGR, bool PRE = false>
 __global__ void __launch_bounds__(FusedCfg<KIND, LOGN, LOGR>::GP * FusedCfg<KIND, LOGN, LOGR>::T, FusedCfg<KIND, LOGN, LOGR>::MINBLK)
 k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ prod, const void* __restrict__ lhs,
                 const void* __restrict__ rhs, unsigned long long batch)
@@ -132,15 +139,18 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
     constexpr bool RELOAD = Cfg::RELOAD, ACC = Cfg::ACC;
     constexpr int CLS = native_np_class(NP);
     constexpr int RK = RELOAD ? 1 : R;
-    uint64_t llo[RK], rlo[RK];
-    uint64_t lhi[(WB == 16 && !RELOAD) ? R : 1], rhi[(WB == 16 && !RELOAD) ? R : 1];
+    uint64_t llo[RK], rlo[PRE ? 1 : RK];
+    uint64_t lhi[(WB == 16 && !RELOAD) ? R : 1], rhi[(WB == 16 && !RELOAD && !PRE) ? R : 1];
     if constexpr (!RELOAD) {
 #pragma unroll
         for (int k = 0; k < R; k++) {
             uint64_t h0, h1;
             dev::load_word<KIND>(lhs, base + tid + k * T, llo[k], h0);
-            dev::load_word<KIND>(rhs, base + tid + k * T, rlo[k], h1);
-            if constexpr (WB == 16) { lhi[k] = h0; rhi[k] = h1; }
+            if constexpr (WB == 16) lhi[k] = h0;
+            if constexpr (!PRE) {
+                dev::load_word<KIND>(rhs, base + tid + k * T, rlo[k], h1);
+                if constexpr (WB == 16) rhi[k] = h1;
+            }
         }
     }
     Word acc[ACC ? R : 1];
@@ -160,18 +170,29 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
             for (int k = 0; k < R; k++) {
                 uint64_t alo, ahi, blo, bhi;
                 dev::load_word<KIND>(lhs, base + tid + k * T, alo, ahi);
-                dev::load_word<KIND>(rhs, base + tid + k * T, blo, bhi);
                 x[0][k] = dev::residue<LIMBS, true>(alo, ahi, fp.lscale[pk], p);
-                x[1][k] = BINARY ? (uint32_t)blo : dev::residue<LIMBS, false>(blo, bhi, c.red[pk], p);
+                if constexpr (!PRE) {
+                    dev::load_word<KIND>(rhs, base + tid + k * T, blo, bhi);
+                    x[1][k] = BINARY ? (uint32_t)blo : dev::residue<LIMBS, false>(blo, bhi, c.red[pk], p);
+                }
             }
         } else {
 #pragma unroll
             for (int k = 0; k < R; k++) {
                 x[0][k] = dev::residue<LIMBS, true>(llo[k], WB == 16 ? lhi[k] : 0ull, fp.lscale[pk], p);
-                x[1][k] = BINARY ? (uint32_t)rlo[k] : dev::residue<LIMBS, false>(rlo[k], WB == 16 ? rhi[k] : 0ull, c.red[pk], p);
+                if constexpr (!PRE) x[1][k] = BINARY ? (uint32_t)rlo[k] : dev::residue<LIMBS, false>(rlo[k], WB == 16 ? rhi[k] : 0ull, c.red[pk], p);
             }
         }
-        if constexpr (BINARY && CNTT_BINARY_LUT != 0 && E::P >= 2 && !E::kLoopPasses && E::G::R1 <= 3) {
+        if constexpr (PRE) {
+            uint32_t xl[1][R];
+#pragma unroll
+            for (int k = 0; k < R; k++) xl[0][k] = x[0][k];
+            E::template fwd<1>(xl, sm, typename E::TwSrc{fp.tw_fwd[pk], fp.tw_fwd_last[pk]}, 1u, tid, m);
+            const uint32_t* rp = reinterpret_cast<const uint32_t*>(rhs) + (size_t)pk * fp.pre_plane_stride + (size_t)b * fp.pre_poly_stride + E::elem_last(tid, 0);
+            load_contig<uint32_t, R>(rp, x[1]);   // canonical residues, the lane's R consecutive words of the last-pass layout
+#pragma unroll
+            for (int k = 0; k < R; k++) x[0][k] = xl[0][k];
+        } else if constexpr (BINARY && CNTT_BINARY_LUT != 0 && E::P >= 2 && !E::kLoopPasses && E::G::R1 <= 3) {
             const typename E::TwSrc tws = {fp.tw_fwd[pk], fp.tw_fwd_last[pk]};
             uint32_t xl[1][R];
 #pragma unroll
@@ -231,12 +252,15 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
     }
 }
 
-template <int KIND, int LOGN>
-static cudaError_t launch_fused_one(const NativePlanDev& pl, void* prod, const void* lhs, const void* rhs, size_t batch, cudaStream_t st)
+template <int KIND, int LOGN, bool PRE = false>
+static cudaError_t launch_fused_one(const NativePlanDev& pl, void* prod, const void* lhs, const void* rhs, size_t batch, cudaStream_t st,
+                                    size_t pre_plane_stride = 0, size_t pre_poly_stride = 0)
 {
     constexpr int LOGR = native_fused_logr(KIND, LOGN);
     typedef FusedCfg<KIND, LOGN, LOGR> Cfg;
     FusedParams fp;
+    fp.pre_plane_stride = pre_plane_stride;
+    fp.pre_poly_stride = pre_poly_stride;
     for (int k = 0; k < Cfg::NP; k++) {
         fp.bin0[k] = pl.bin0[k];
         if (KIND >= NK_BINARY32 && CNTT_BINARY_LUT != 0 && Cfg::E::P >= 2 && Cfg::E::G::R1 <= 3 && !fp.bin0[k]) return cudaErrorInvalidValue;
@@ -248,7 +272,7 @@ static cudaError_t launch_fused_one(const NativePlanDev& pl, void* prod, const v
         fp.mod[k] = pl.sub[k].mod;
         for (int j = 0; j < 4; j++) fp.lscale[k][j] = pl.lscale[k][j];
     }
-    auto kern = k_polymul_fused<KIND, LOGN, LOGR>;
+    auto kern = k_polymul_fused<KIND, LOGN, LOGR, PRE>;
     if (Cfg::SMEM_BYTES > 227 * 1024) return cudaErrorNotSupported;
     if (cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES); e != cudaSuccess) return e;
     const unsigned long long nblk = (batch + Cfg::GP - 1) / Cfg::GP;
@@ -270,6 +294,20 @@ static cudaError_t launch_fused_kind(const NativePlanDev& pl, void* prod, const 
     case 11: return launch_fused_one<KIND, 11>(pl, prod, lhs, rhs, batch, st);
     case 12: return launch_fused_one<KIND, 12>(pl, prod, lhs, rhs, batch, st);
     default: return cudaErrorNotSupported; // larger N: unfused two-level pipeline (capi.cu)
+    }
+}
+// pre-transformed rhs (k_polymul_fused<.., PRE = true>): 256 <= N <= 4096
+template <int KIND>
+static cudaError_t launch_fused_pre_kind(const NativePlanDev& pl, void* prod, const void* lhs, const uint32_t* rhs_planes, size_t batch, size_t plane_stride,
+                                         size_t poly_stride, cudaStream_t st)
+{
+    switch (pl.logn) {
+    case 8: return launch_fused_one<KIND, 8, true>(pl, prod, lhs, rhs_planes, batch, st, plane_stride, poly_stride);
+    case 9: return launch_fused_one<KIND, 9, true>(pl, prod, lhs, rhs_planes, batch, st, plane_stride, poly_stride);
+    case 10: return launch_fused_one<KIND, 10, true>(pl, prod, lhs, rhs_planes, batch, st, plane_stride, poly_stride);
+    case 11: return launch_fused_one<KIND, 11, true>(pl, prod, lhs, rhs_planes, batch, st, plane_stride, poly_stride);
+    case 12: return launch_fused_one<KIND, 12, true>(pl, prod, lhs, rhs_planes, batch, st, plane_stride, poly_stride);
+    default: return cudaErrorNotSupported;
     }
 }
 

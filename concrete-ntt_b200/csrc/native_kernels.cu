@@ -217,6 +217,20 @@ cudaError_t native_fused_build_last(int kind, int logn, const uint2* heap, uint2
     const bool wide = kind == NK_NATIVE128 || kind == NK_BINARY128;
     return wide ? fused_build_last_kind<NK_NATIVE128>(logn, heap, out, st) : fused_build_last_kind<NK_NATIVE64>(logn, heap, out, st);
 }
+cudaError_t native_polymul_fused_pre(const NativePlanDev& pl, void* prod, const void* lhs, const uint32_t* rhs_planes, size_t batch,
+                                     size_t plane_stride, size_t poly_stride, cudaStream_t st)
+{
+    if (batch == 0) return cudaSuccess;
+    switch (pl.kind) {
+    case NK_NATIVE32: return launch_fused_pre_kind<NK_NATIVE32>(pl, prod, lhs, rhs_planes, batch, plane_stride, poly_stride, st);
+    case NK_NATIVE64: return launch_fused_pre_kind<NK_NATIVE64>(pl, prod, lhs, rhs_planes, batch, plane_stride, poly_stride, st);
+    case NK_NATIVE128: return launch_fused_pre_kind<NK_NATIVE128>(pl, prod, lhs, rhs_planes, batch, plane_stride, poly_stride, st);
+    case NK_BINARY32: return launch_fused_pre_kind<NK_BINARY32>(pl, prod, lhs, rhs_planes, batch, plane_stride, poly_stride, st);
+    case NK_BINARY64: return launch_fused_pre_kind<NK_BINARY64>(pl, prod, lhs, rhs_planes, batch, plane_stride, poly_stride, st);
+    case NK_BINARY128: return launch_fused_pre_kind<NK_BINARY128>(pl, prod, lhs, rhs_planes, batch, plane_stride, poly_stride, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
 cudaError_t native_polymul_fused(const NativePlanDev& pl, void* prod, const void* lhs, const void* rhs, size_t batch,
                                  cudaStream_t st)
 {

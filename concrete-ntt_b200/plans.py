@@ -286,6 +286,25 @@ class _NativePlan:
         return prod
 
 
+def _polymul_ntt_rhs(self, prod, lhs, rhs_planes):
+    """EXTENSION: negacyclic_polymul with rhs already transformed -- `rhs_planes` is what fwd (fwd_binary on binary plans) wrote, shape
+    (num_primes, batch, n) or (num_primes, 1, n) / (num_primes, n) for one key shared by the whole batch.  Device tensors only,
+    256 <= n <= 4096."""
+    p = self._word_buf(prod, "prod")
+    l = self._word_buf(lhs, "lhs")
+    r = _Buf(self._device, rhs_planes, 4, "rhs_planes")
+    if not (p.is_dev and l.is_dev and r.is_dev):
+        raise TypeError("negacyclic_polymul_ntt_rhs operates on device-resident tensors")
+    if p.batch != l.batch or r.words not in (self._np * p.batch * self._n, self._np * self._n):
+        raise ReferencePanic("assert_eq!(n, lhs.len())")
+    rb = r.words // (self._np * self._n)
+    check(_lib.lib().cntt_native_polymul_ntt_rhs(self._h, p.ptr, l.ptr, r.ptr, rb, p.batch, _stream_of(p.t)), "negacyclic_polymul_ntt_rhs")
+    return prod
+
+
+_NativePlan.negacyclic_polymul_ntt_rhs = _polymul_ntt_rhs
+
+
 class _Native52Plan:
     """native32 / native64 / native_binary32 / native_binary64 ::Plan52 (src/native64.rs:29-34,1072-1165 and twins): the
     same plans on 2 / 3 / 1 / 2 ~50-bit primes (primes52) with uint64 residue planes, shape (num_primes, batch..., n).

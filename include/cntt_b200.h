@@ -163,6 +163,11 @@ int cntt_native_fwd_binary_host(const cntt_native_plan* plan, const void* h_valu
 int cntt_native_inv_host(const cntt_native_plan* plan, void* h_value, uint32_t* h_mod_p, size_t len, size_t batch);
 /* Plan32::negacyclic_polymul(prod, lhs, rhs) */
 int cntt_native_polymul(const cntt_native_plan* plan, void* d_prod, const void* d_lhs, const void* d_rhs, size_t batch, void* stream);
+/* EXTENSION: the same product with rhs already in the NTT domain -- d_rhs_planes as written by cntt_native_fwd (fwd_binary for the
+ * binary plans) for rhs_batch polynomials, rhs_batch == batch or 1 (one key shared by the whole batch).  One of the three transforms
+ * per prime disappears; this is the shape of a TFHE external product with the key kept transformed (src/prime32.rs:905-927 is the
+ * per-prime step a reference caller composes).  256 <= n <= 4096, CNTT_UNSUPPORTED otherwise. */
+int cntt_native_polymul_ntt_rhs(const cntt_native_plan* plan, void* d_prod, const void* d_lhs, const uint32_t* d_rhs_planes, size_t rhs_batch, size_t batch, void* stream);
 /* host-slice flavour: len = words in each of prod/lhs/rhs; must equal n*batch */
 int cntt_native_polymul_host(const cntt_native_plan* plan, void* h_prod, const void* h_lhs, const void* h_rhs, size_t len, size_t batch);
 /* the same over several GPUs: plans[g] = the same plan kind and n on device g (see cntt_prime32_fwd_host_multi) */

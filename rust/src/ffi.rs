@@ -85,6 +85,7 @@ extern "C" {
     pub fn cntt_native_fwd_binary_host(plan: *const NativePlan, h_value: *const c_void, h_mod_p: *mut u32, len: usize, batch: usize) -> c_int;
     pub fn cntt_native_inv_host(plan: *const NativePlan, h_value: *mut c_void, h_mod_p: *mut u32, len: usize, batch: usize) -> c_int;
     pub fn cntt_native_polymul(plan: *const NativePlan, d_prod: *mut c_void, d_lhs: *const c_void, d_rhs: *const c_void, batch: usize, stream: Stream) -> c_int;
+    pub fn cntt_native_polymul_ntt_rhs(plan: *const NativePlan, d_prod: *mut c_void, d_lhs: *const c_void, d_rhs_planes: *const u32, rhs_batch: usize, batch: usize, stream: Stream) -> c_int;
     pub fn cntt_native_polymul_host(plan: *const NativePlan, h_prod: *mut c_void, h_lhs: *const c_void, h_rhs: *const c_void, len: usize, batch: usize) -> c_int;
 
     // ---- Plan52 twins ----

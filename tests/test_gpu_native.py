@@ -399,3 +399,34 @@ def test_plan52(cntt, oracle, torch_cuda, bits, binary, n):
     dfw = dev(torch, fw)
     gp.inv(torch.empty_like(out), dfw)
     assert (hfw == host(dfw, np.uint64)).all()
+
+
+@pytest.mark.parametrize("bits,binary", [(32, False), (64, False), (128, False), (32, True), (64, True), (128, True)])
+@pytest.mark.parametrize("n", [256, 2048, 4096])
+def test_polymul_with_pretransformed_rhs(cntt, oracle, torch_cuda, bits, binary, n):
+    """EXTENSION cntt_native_polymul_ntt_rhs: rhs handed over as the residue planes Plan32::fwd / fwd_binary wrote (the TFHE shape, key
+    kept in the NTT domain) -- the product must be what negacyclic_polymul returns, per-product keys and one shared key."""
+    torch = torch_cuda
+    mod = getattr(cntt, ("native_binary%d" if binary else "native%d") % bits)
+    gp, op = mod.Plan32.try_new(n), oracle.Native.try_new(n, bits, binary=binary)
+    g = rng(900 + bits + n + int(binary))
+    batch = 5
+    lhs, rhs = rand_words(g, bits, (batch, n)), make_rhs(g, bits, (batch, n), binary)
+    want = op.negacyclic_polymul(lhs, rhs)
+    planes = torch.empty((gp.num_primes(), batch, n), dtype=torch.int32, device="cuda")
+    (gp.fwd_binary if binary else gp.fwd)(dev(torch, rhs), planes)
+    dl = dev(torch, lhs)
+    prod = torch.empty_like(dl)
+    gp.negacyclic_polymul_ntt_rhs(prod, dl, planes)
+    wdt = np.uint32 if bits == 32 else np.uint64
+    assert (host(prod, wdt) == want).all()
+    # one key for the whole batch
+    key = torch.empty((gp.num_primes(), 1, n), dtype=torch.int32, device="cuda")
+    (gp.fwd_binary if binary else gp.fwd)(dev(torch, rhs[:1]), key)
+    gp.negacyclic_polymul_ntt_rhs(prod, dl, key)
+    assert (host(prod, wdt) == op.negacyclic_polymul(lhs, np.repeat(rhs[:1], batch, axis=0))).all()
+    small = mod.Plan32.try_new(64)
+    with pytest.raises(cntt.CnttError):
+        small.negacyclic_polymul_ntt_rhs(torch.empty((1, 64) + ((2,) if bits == 128 else ()), dtype=dl.dtype, device="cuda"),
+                                         torch.empty((1, 64) + ((2,) if bits == 128 else ()), dtype=dl.dtype, device="cuda"),
+                                         torch.empty((small.num_primes(), 1, 64), dtype=torch.int32, device="cuda"))
