@@ -70,14 +70,54 @@ template <int K> __device__ __forceinline__ void inv_bf_shift(u64& z0, u64& z1) 
     const u64 d = (K % 192) >= 96 ? A64S::sub_lazy(z1, z0) : A64S::sub_lazy(z0, z1);
     z0 = a; z1 = shl_mod<K>(d);
 }
+// add_lazy with the end-around fix on the multiply pipe: r + carry * EPS as ONE IMAD.WIDE.  EPS must be opaque to the compiler (a
+// kernel parameter), or ptxas strength-reduces the multiply back into ALU adds.
+__device__ __forceinline__ u64 add_lazy_w(u64 z, u64 x, u32 eps)
+{
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 r0, r1, m;\n\t"
+        ".reg .u64 rr;\n\t"
+        "add.cc.u32   r0, %1, %3;\n\t"
+        "addc.cc.u32  r1, %2, %4;\n\t"
+        "addc.u32     m, 0, 0;\n\t"
+        "mov.b64      rr, {r0, r1};\n\t"
+        "mad.wide.u32 %0, m, %5, rr;\n\t"
+        "}"
+        : "=l"(r) : "r"((u32)z), "r"((u32)(z >> 32)), "r"((u32)x), "r"((u32)(x >> 32)), "r"(eps));
+    return r;
+}
+template <int K> __device__ __forceinline__ void fwd_bf_shift_w(u64& z0, u64& z1, u32 eps)
+{
+    const u64 t = shl_mod<K>(z1);
+    const u64 a = add_lazy_w(z0, t, eps), b = A64S::sub_lazy(z0, t);
+    if constexpr ((K % 192) >= 96) { z0 = b; z1 = a; } else { z0 = a; z1 = b; }
+}
+__device__ __forceinline__ void fwd_bf_w(u64& z0, u64& z1, u64 t, u32 eps)
+{
+    const u64 x = A64S::mul(z1, t);
+    const u64 a = add_lazy_w(z0, x, eps), b = A64S::sub_lazy(z0, x);
+    z0 = a; z1 = b;
+}
 // exponents of the first four transform levels (heap order, entry h = 2^level + block): tw[h] = 2^E[h]
 __device__ constexpr int kExp[16] = {0, 48, 120, 168, 156, 12, 84, 132, 78, 126, 6, 54, 42, 90, 162, 18};
 
 template <int J, int G, int U> struct BfIdx { static constexpr int half = 16 >> (J + 1); static constexpr int i0 = 2 * half * G + U; };
 
-template <int V> __device__ __forceinline__ void pass(u64 (&x)[16], const u64* tw, const Mod64& m)
+template <int V> __device__ __forceinline__ void pass(u64 (&x)[16], const u64* tw, const Mod64& m, u32 eps)
 {
-    if constexpr (V == 0 || V == 2) {
+    if constexpr (V == 4) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int half = 16 >> (j + 1);
+#pragma unroll
+            for (int g = 0; g < (1 << j); g++) {
+                const u64 t = tw[(1 << j) + g];
+#pragma unroll
+                for (int u = 0; u < half; u++) fwd_bf_w(x[2 * half * g + u], x[2 * half * g + u + half], t, eps);
+            }
+        }
+    } else if constexpr (V == 0 || V == 2) {
 #pragma unroll
         for (int j0 = 0; j0 < 4; j0++) {
             const int j = V == 0 ? j0 : 3 - j0;
@@ -95,8 +135,9 @@ template <int V> __device__ __forceinline__ void pass(u64 (&x)[16], const u64* t
     } else {
 #define BF(J, G) { constexpr int half = 16 >> ((J) + 1); _Pragma("unroll") for (int u = 0; u < half; u++) { \
         if constexpr (V == 1) fwd_bf_shift<kExp[(1 << (J)) + (G)]>(x[2 * half * (G) + u], x[2 * half * (G) + u + half]); \
+        else if constexpr (V == 5) fwd_bf_shift_w<kExp[(1 << (J)) + (G)]>(x[2 * half * (G) + u], x[2 * half * (G) + u + half], eps); \
         else inv_bf_shift<(192 - kExp[(1 << (J)) + (G)]) % 192>(x[2 * half * (G) + u], x[2 * half * (G) + u + half]); } }
-        if constexpr (V == 1) {
+        if constexpr (V == 1 || V == 5) {
             BF(0, 0) BF(1, 0) BF(1, 1) BF(2, 0) BF(2, 1) BF(2, 2) BF(2, 3)
             BF(3, 0) BF(3, 1) BF(3, 2) BF(3, 3) BF(3, 4) BF(3, 5) BF(3, 6) BF(3, 7)
         } else {
@@ -109,7 +150,7 @@ template <int V> __device__ __forceinline__ void pass(u64 (&x)[16], const u64* t
 
 struct TwArr { u64 e[16]; };
 template <int V>
-__global__ void __launch_bounds__(128) k_bench(u64* out, const u64* in, const __grid_constant__ TwArr tw, int iters)
+__global__ void __launch_bounds__(128) k_bench(u64* out, const u64* in, const __grid_constant__ TwArr tw, int iters, u32 eps)
 {
     u64 x[16];
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -118,7 +159,7 @@ __global__ void __launch_bounds__(128) k_bench(u64* out, const u64* in, const __
     Mod64 m = {};
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
-        pass<V>(x, tw.e, m);
+        pass<V>(x, tw.e, m, eps);
         if constexpr (V == 2 || V == 3) { /* inverse keeps canonical values */ }
     }
 #pragma unroll
@@ -145,21 +186,21 @@ template <int V> static int run(const char* name, int sms, double ghz, const TwA
 {
     const int iters = 64, blocks = (int)(nthreads / 128);
     // correctness: one iteration against the host reference
-    k_bench<V><<<blocks, 128>>>(d_out, d_in, tw, 1);
+    k_bench<V><<<blocks, 128>>>(d_out, d_in, tw, 1, 0xFFFFFFFFu);
     u64* h_out = (u64*)malloc(nthreads * 16 * 8);
     cudaMemcpy(h_out, d_out, nthreads * 16 * 8, cudaMemcpyDeviceToHost);
     int bad = 0;
     for (size_t t = 0; t < nthreads && t < 4096; t++) {
         u64 x[16];
         for (int k = 0; k < 16; k++) x[k] = h_in[t * 16 + k];
-        ref_pass(x, tw.e, V == 0 || V == 1);
+        ref_pass(x, tw.e, V == 0 || V == 1 || V == 4 || V == 5);
         for (int k = 0; k < 16; k++) if (x[k] % P != h_out[t * 16 + k]) bad++;
     }
     free(h_out);
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    k_bench<V><<<blocks, 128>>>(d_out, d_in, tw, iters);
+    k_bench<V><<<blocks, 128>>>(d_out, d_in, tw, iters, 0xFFFFFFFFu);
     cudaEventRecord(a);
-    k_bench<V><<<blocks, 128>>>(d_out, d_in, tw, iters);
+    k_bench<V><<<blocks, 128>>>(d_out, d_in, tw, iters, 0xFFFFFFFFu);
     cudaEventRecord(b); cudaEventSynchronize(b);
     float ms; cudaEventElapsedTime(&ms, a, b);
     double bf = (double)nthreads * iters * 32;
@@ -189,6 +230,8 @@ int main()
     int bad = 0;
     bad += run<0>("fwd: A64S::fwd_bf, table twiddles (shipped)", sms, ghz, tw, d_in, d_out, h_in, nthreads);
     bad += run<1>("fwd: shift butterflies (levels 0..3)", sms, ghz, tw, d_in, d_out, h_in, nthreads);
+    bad += run<4>("fwd: fwd_bf, add fix as IMAD.WIDE", sms, ghz, tw, d_in, d_out, h_in, nthreads);
+    bad += run<5>("fwd: shift butterflies, add fix as IMAD.WIDE", sms, ghz, tw, d_in, d_out, h_in, nthreads);
     bad += run<2>("inv: A64S::inv_bf, table twiddles (shipped)", sms, ghz, twi, d_in, d_out, h_in, nthreads);
     bad += run<3>("inv: shift butterflies (levels 3..0)", sms, ghz, twi, d_in, d_out, h_in, nthreads);
     return bad ? 1 : 0;
