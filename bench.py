@@ -34,7 +34,7 @@ WORKLOAD = "prime64 Plan N=2048 p=2^64-2^32+1 (Solinas) batch 65536 per GPU, fwd
 ALG_BYTES_PER_NTT = 2 * N_POLY * 8
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_ntt_cta<A64S,11> launch over the batch, from the
 # ncu --set full capture committed under profiles/ (parsed at run time; None if the summary is absent)
-NCU_SUMMARY = os.path.join(ROOT, "profiles", "r01_kernels_v7", "ncu_ntt64s_2048.txt")
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r02_kernels", "ncu_ntt64s_2048.txt")
 
 
 def ncu_traffic(direction):
@@ -544,10 +544,12 @@ def run_ours(args):
                          # integer roofline of the same launch (11 levels x 1024 butterflies per NTT).  Peak = the multiply floor: a
                          # 64 x 64 -> 128-bit product is four 32 x 32 -> 64 products and IMAD.WIDE.U32 issues at 24.4 per clock and SM
                          # (profiles/r01_ubench_int_pipes.txt), i.e. 6.1 butterflies per clock and SM if nothing else cost anything.  The
-                         # butterfly as shipped, alone in registers, reaches 2.40 (profiles/r02_ubench_gold_bf.txt).
+                         # butterflies as shipped, alone in registers, reach 2.40 (multiply) and 3.25 (shift, four of the eleven levels):
+                         # 11 / (7 / 2.40 + 4 / 3.25) = 2.65 for the mix of this transform (profiles/r02_ubench_gold_bf.txt).
                          "int_roofline": {"achieved": bf, "peak": 24.4 / 4, "unit": "butterflies/clk/SM", "frac": bf / (24.4 / 4),
                                           "peak_source": "4-product multiply floor, measured IMAD.WIDE.U32 rate / 4",
-                                          "butterfly_alone": 2.40, "frac_of_butterfly_alone": bf / 2.40},
+                                          "butterflies_alone": {"multiply": 2.40, "shift": 3.25, "mix_of_this_transform": 2.65},
+                                          "frac_of_butterflies_alone": bf / 2.65},
                          "note": "integer-bound kernel: ALU and multiply pipe ~70-75 % busy at once (ncu summary under profiles/); "
                                  "the HBM fraction cannot exceed ~0.4 for this prime on CUDA cores, see DESIGN.md section 4"},
             "extra": extra,
