@@ -103,14 +103,17 @@ def test_very_large_n_solinas(cntt, oracle, torch_cuda):
     assert [int(v) for v in back[0, :64]] == [(int(x) * n) % p for x in a[0, :64]]
 
 
-def test_pointwise_ops(cntt, oracle, torch_cuda):
-    g = rng(42)
-    n, batch = 128, 9
+@pytest.mark.parametrize("n,batch", [(32, 1), (128, 9), (1024, 33), (8192, 5)])
+def test_pointwise_ops(cntt, oracle, torch_cuda, n, batch):
+    g = rng(42 + n)
     for OP, GP, primes, dt in [(oracle.Plan32, cntt.prime32.Plan, primes32(oracle), np.uint32),
                                (oracle.Plan64, cntt.prime64.Plan, primes64(oracle), np.uint64)]:
         for name, p in primes.items():
             op, gp = OP.try_new(n, p), GP.try_new(n, p)
             a, b, c = (rand_mod(g, p, (batch, n), dt) for _ in range(3))
+            a[0, :3] = [0, 1, p - 1]
+            b[0, :3] = [p - 1, p - 1, p - 1]
+            c[0, :3] = [p - 1, 0, p - 1]
             da, db, dc = dev(torch_cuda, a), dev(torch_cuda, b), dev(torch_cuda, c)
             gp.mul_assign_normalize(da, db)
             assert (host(da, dt) == op.mul_assign_normalize(a.copy(), b)).all(), (name, "mul_assign_normalize")
@@ -179,20 +182,27 @@ def test_error_behaviour(cntt, torch_cuda):
     plan.fwd(torch_cuda.zeros((0, 64), dtype=torch_cuda.int32, device="cuda"))
 
 
-def test_full_size_properties(cntt, torch_cuda):
-    """BASELINE config 2 at full size (prime64 Solinas N=2048, batch 65536): size-independent properties --
-    inv(fwd(x)) == N x and linearity fwd(a + b) == fwd(a) + fwd(b) on a checksum."""
+def test_full_size_properties(cntt, oracle, torch_cuda):
+    """BASELINE config 2 at full size (prime64 Solinas N=2048, batch 65536): EVERY word of the forward and of the inverse
+    transform against the oracle (its multi-threaded batch path, bit-checked against the scalar one in test_oracle_simd.py),
+    plus the size-independent properties inv(fwd(x)) == N x and normalize(inv(fwd(x))) == x."""
     torch = torch_cuda
     n, p, batch = 2048, 0xFFFFFFFF00000001, 65536
     plan = cntt.prime64.Plan.try_new(n, p)
+    op = oracle.Plan64.try_new(n, p)
     g = rng(2)
     a = rand_mod(g, p, (batch, n), np.uint64)
     d = dev(torch, a)
     plan.fwd(d)
     f = host(d, np.uint64)
     assert (f < np.uint64(p)).all()
+    ref = a.copy()
+    op.fwd_batch(ref, oracle.max_threads())
+    assert (f == ref).all()
     plan.inv(d)
     back = host(d, np.uint64)
+    op.inv_batch(ref, oracle.max_threads())
+    assert (back == ref).all()
     rows = g.integers(0, batch, 64)
     for r in rows:
         assert [int(v) for v in back[r, :8]] == [(int(x) * n) % p for x in a[r, :8]]
