@@ -271,6 +271,9 @@ struct A64L2 : A64L4 {
 //      (carry chains are never mixed: ptxas hands `subc` the raw carry predicate after an add.cc)
 //      Between forward stages values are arbitrary 64-bit representatives ("lazy"); only products are
 //      canonical.  Between inverse stages all values are canonical.
+#ifndef CNTT_MUL128
+#define CNTT_MUL128 0
+#endif
 struct A64S {
     typedef uint64_t W;
     typedef uint64_t Tw; // no Shoup companion
@@ -291,6 +294,12 @@ struct A64S {
     static __device__ __forceinline__ W mul(W a, W b) // any a, b; result canonical
     {
         uint32_t c0, c1, c2, c3, r0, r1;
+#if CNTT_MUL128
+        {   // the compiler's own 64 x 64 -> 128 product: 3 IMAD.WIDE + IMAD.WIDE.X + 2 adds (two instructions fewer than the chain below)
+            const u128_t w = (u128_t)a * b;
+            c0 = (uint32_t)w; c1 = (uint32_t)(w >> 32); c2 = (uint32_t)(w >> 64); c3 = (uint32_t)(w >> 96);
+        }
+#else
         asm("{\n\t"
             "mul.lo.u32      %0, %4, %6;\n\t"
             "mul.hi.u32      %1, %4, %6;\n\t"
@@ -305,6 +314,7 @@ struct A64S {
             "}"
             : "=&r"(c0), "=&r"(c1), "=&r"(c2), "=&r"(c3)
             : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)));
+#endif
         // X = (c1:c0) - c3 (borrow: the wrap added 2^64 = EPS too much);  r = X + c2*EPS mod 2^64, carry m.
         // m = 1: true value r + 2^64 = r + EPS, and r <= 2^64 - 2^33 so the sum does not wrap and is < p.
         // m = 0 and r >= p (r1 all ones, r0 != 0): r + EPS wraps to r - p.  Either way: r += EPS mod 2^64.
