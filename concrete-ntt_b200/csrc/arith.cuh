@@ -287,9 +287,16 @@ struct A64S {
     // x >= p  ->  x - p   (x - p = (0 : x0 - 1) because x1 must be 0xFFFFFFFF)
     static __device__ __forceinline__ W canon(W x)
     {
-        const uint32_t x0 = (uint32_t)x, x1 = (uint32_t)(x >> 32);
-        if (x1 == 0xFFFFFFFFu && x0 != 0u) x = (uint64_t)(x0 - 1u);
-        return x;
+        uint32_t x0 = (uint32_t)x, x1 = (uint32_t)(x >> 32);
+        asm("{\n\t"
+            ".reg .pred q;\n\t"
+            "setp.eq.u32     q, %1, 0xFFFFFFFF;\n\t"
+            "setp.ne.and.u32 q, %0, 0, q;\n\t"
+            "@q add.u32      %0, %0, 0xFFFFFFFF;\n\t"
+            "@q mov.u32      %1, 0;\n\t"
+            "}"
+            : "+r"(x0), "+r"(x1));   // 5 SASS instructions; the C form of the same test compiled to 8
+        return pack(x0, x1);
     }
     static __device__ __forceinline__ W mul(W a, W b) // any a, b; result canonical
     {
