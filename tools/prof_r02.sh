@@ -4,6 +4,7 @@
 OUT=gpurun_out/r02_kernels; mkdir -p $OUT
 run() { # name kernel-regex driver-args...
   local name=$1 rx=$2; shift 2
+  if [ -n "$ONLY" ] && ! [[ $name =~ $ONLY ]]; then return; fi   # ONLY=<regex over names>: re-capture a subset
   timeout 900 ncu --set full --clock-control none -k regex:"$rx" -s ${SKIP:-1} -c ${COUNT:-2} -f -o $OUT/prof_$name python tools/prof_driver.py "$@" > $OUT/ncu_$name.log 2>&1
   echo "$name rc=$?"
   python tools/ncu_summary.py $OUT/prof_$name.ncu-rep > $OUT/ncu_$name.txt 2>&1
