@@ -10,7 +10,6 @@
 #pragma once
 #include "ntt_engine.cuh"
 #include <atomic>
-#include <cstdlib>
 
 namespace cntt {
 
@@ -889,24 +888,13 @@ cudaError_t launch_strided(const PlanDev<A>& pl, int logk, typename A::W* data, 
 // strided (<= 4 per launch) until the remaining contiguous blocks are 4096 words, then the CTA
 // kernel on all batch * 2^s blocks; the inverse runs the same schedule backwards.
 // poly_stride: distance in words between consecutive polynomials of the batch (0: contiguous, = N)
-// Transforms that take more than one launch (N beyond the CTA sizes) move the whole batch through HBM once per launch.  With
-// CNTT_L2_CHUNK_MB > 0 the batch is walked in slices of that many MB: the strided launch of a slice leaves its words in the L2
-// (126 MB), and the CTA launch of the same slice finds them there.  The environment variable of the same name overrides the
-// compiled default (experiments).
-#ifndef CNTT_L2_CHUNK_MB
-#define CNTT_L2_CHUNK_MB 0
-#endif
-inline size_t l2_chunk_bytes()
-{
-    static const size_t v = [] {
-        const char* s = std::getenv("CNTT_L2_CHUNK_MB");
-        return (size_t)(s != nullptr ? std::atol(s) : (long)CNTT_L2_CHUNK_MB) << 20;
-    }();
-    return v;
-}
 template <class A, bool FWD>
-cudaError_t launch_ntt_slice(const PlanDev<A>& pl, int blk, typename A::W* data, size_t batch, cudaStream_t st, size_t poly_stride)
+cudaError_t launch_ntt(const PlanDev<A>& pl, typename A::W* data, size_t batch, cudaStream_t st, size_t poly_stride = 0)
 {
+    if (batch == 0) return cudaSuccess;
+    if (poly_stride == 0) poly_stride = (size_t)1 << pl.logn;
+    const int blk = cta_block_logn<A>(pl.logn, FWD);
+    if (pl.logn == blk) return launch_cta<A, FWD>(pl, pl.logn, data, batch, 0, poly_stride, st);
     const int lead = pl.logn - blk;
     constexpr int kmax = sizeof(typename A::W) == 4 ? (FWD ? CNTT_STRIDED_MAXK32_FWD : CNTT_STRIDED_MAXK32_INV) : ShiftHead<A>::value ? CNTT_STRIDED_MAXK64S : 4;
     cudaError_t e;
@@ -929,28 +917,6 @@ cudaError_t launch_ntt_slice(const PlanDev<A>& pl, int blk, typename A::W* data,
         }
         return cudaSuccess;
     }
-}
-template <class A, bool FWD>
-cudaError_t launch_ntt(const PlanDev<A>& pl, typename A::W* data, size_t batch, cudaStream_t st, size_t poly_stride = 0)
-{
-    if (batch == 0) return cudaSuccess;
-    if (poly_stride == 0) poly_stride = (size_t)1 << pl.logn;
-    const int blk = cta_block_logn<A>(pl.logn, FWD);
-    if (pl.logn == blk) return launch_cta<A, FWD>(pl, pl.logn, data, batch, 0, poly_stride, st);
-    // multi-launch transforms: walk the batch in slices that fit the L2, so that the words a strided launch leaves are still
-    // cached when the next launch of the same slice reads them (see CNTT_L2_CHUNK_MB)
-    if (const size_t chunk = l2_chunk_bytes(); chunk != 0) {
-        const size_t poly_bytes = poly_stride * sizeof(typename A::W);
-        const size_t per = chunk / poly_bytes > 0 ? chunk / poly_bytes : 1;
-        if (batch > per) {
-            for (size_t b0 = 0; b0 < batch; b0 += per) {
-                const size_t nb = batch - b0 < per ? batch - b0 : per;
-                if (cudaError_t e = launch_ntt_slice<A, FWD>(pl, blk, data + b0 * poly_stride, nb, st, poly_stride); e != cudaSuccess) return e;
-            }
-            return cudaSuccess;
-        }
-    }
-    return launch_ntt_slice<A, FWD>(pl, blk, data, batch, st, poly_stride);
 }
 
 template <class A, int OP>
