@@ -341,6 +341,21 @@ struct Engine {
             inv_from<Q - 1, NP>(x, sm, tw, nu0, tid, m);
         }
     }
+    // the inverse passes P-1 .. QSTOP only (x leaves in pass-QSTOP layout): the cluster kernel runs pass 0 across CTAs itself
+    template <int Q, int QSTOP, int NP>
+    static __device__ __forceinline__ void inv_down(W (&x)[NP][R], W* sm, const TwSrc& tw, unsigned nu0, int tid, const Mod& m)
+    {
+        static_assert(!kLoopPasses, "compile-time pass chain only");
+        inv_pass<Q, NP>(x, tw, node<Q>(tid, nu0), tid, m);
+        if constexpr (Q > QSTOP) {
+            W* buf = sm + ((NBUF == 2 && (Q & 1)) ? SMEM_WORDS : 0);
+            scatter<Q, NP>(x, buf, tid);
+            __syncthreads();
+            gather<Q - 1, NP>(x, buf, tid);
+            if constexpr (NBUF == 1) __syncthreads();
+            inv_down<Q - 1, QSTOP, NP>(x, sm, tw, nu0, tid, m);
+        }
+    }
     template <int NP>
     static __device__ __forceinline__ void inv(W (&x)[NP][R], W* sm, const TwSrc& tw, unsigned nu0, int tid, const Mod& m)
     {

@@ -53,6 +53,9 @@ constexpr int kMaxCtaLogN = 12; // largest block a CTA keeps on chip when a tran
 #ifndef CNTT_R32_MAXBLK
 #define CNTT_R32_MAXBLK 14
 #endif
+#ifndef CNTT_CLUSTER32
+#define CNTT_CLUSTER32 0 // 1: N = 32768 (32-bit words) as one launch of two-CTA clusters (k_ntt_cluster, experiment)
+#endif
 constexpr bool kR32 = CNTT_R32_MINLOGN != 0;
 template <class A, int LOGN> constexpr bool r32_size() { return kR32 && sizeof(typename A::W) == 4 && LOGN >= CNTT_R32_MINLOGN && LOGN <= CNTT_R32_MAXBLK; }
 // 32-bit words beyond the single-CTA sizes: levels one strided launch may run (words per thread = 2^k) and the block size the CTA
@@ -86,6 +89,7 @@ constexpr int large_blk32(int logn, bool fwd);
 template <class A> constexpr int cta_block_logn(int logn, bool fwd)
 {
     if (logn <= kMaxCtaLogN) return logn;
+    if (sizeof(typename A::W) == 4 && kR32 && CNTT_CLUSTER32 && logn == 15) return 14; // cluster of two 16384-word halves (k_ntt_cluster)
     if (sizeof(typename A::W) == 4 && kR32) return (logn >= CNTT_R32_MINLOGN && logn <= CNTT_R32_MAXBLK) ? logn : large_blk32(logn, fwd);
     if (ShiftHead<A>::value && CNTT_STRIDED_MAXK64S > 4 && logn >= CNTT_LARGE_MINLOGN64S && logn - CNTT_STRIDED_MAXK64S <= kMaxCtaLogN)
         return logn - CNTT_STRIDED_MAXK64S < CNTT_LARGE_MINBLK64S ? CNTT_LARGE_MINBLK64S : logn - CNTT_STRIDED_MAXK64S;
@@ -686,6 +690,109 @@ k_ntt_strided(const typename A::Tw* __restrict__ tw, const typename A::Mod m, ty
     }
 }
 
+// ---- cluster kernel: EXPERIMENT (CNTT_CLUSTER32, off by default) ---------------------------------------------------
+// One polynomial of 2^LOGN 32-bit words per thread-block cluster of C = 2^LOGC CTAs: a single launch that reads and writes every
+// word once, for a size whose exchange buffer does not fit one CTA at useful occupancy.  The cluster as a whole is the engine
+// Engine<A, LOGN, 5> (thread u = rank * T + tid): its pass 0 pairs words N/2 .. N/32 apart, i.e. words of different CTAs' halves,
+// and runs in registers on words read straight from global memory.  The exchange after pass 0 is the only one that crosses CTAs:
+// register slot k belongs to CTA k / (32 / C) afterwards -- a compile-time property of the slot -- so every thread PUSHES its words
+// into the owner's shared memory (st.shared::cluster; remote stores are fire-and-forget, remote loads would wait ~215 cycles each),
+// one cluster barrier, and from there each CTA is the sub-block engine Engine<A, LOGN - LOGC, 5> with nu0 = C + rank on local
+// shared memory only.  The inverse mirrors it (push in the pass-0 layout after the local passes).
+__device__ __forceinline__ unsigned cluster_ctarank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() { cluster_arrive(); cluster_wait(); }
+__device__ __forceinline__ uint32_t cluster_map(const void* smem_ptr, unsigned rank) // this CTA's shared address -> CTA `rank`'s
+{
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_ptr), r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster(uint32_t addr, uint32_t v) { asm volatile("st.shared::cluster.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+
+template <class A, int LOGN, int LOGC, bool FWD>
+__global__ void __launch_bounds__(Geo<LOGN - LOGC, 5>::T, 2)
+k_ntt_cluster(const typename A::Tw* __restrict__ tw, const typename A::Tw* __restrict__ tw_last, const typename A::Mod m,
+              typename A::W* __restrict__ data, unsigned long long poly_stride, const __grid_constant__ TwHead<typename A::Tw> head)
+{
+    typedef Engine<A, LOGN, 5> EC;          // the cluster: only its pass 0 is used
+    typedef Engine<A, LOGN - LOGC, 5> ES;   // one CTA's sub-block: passes 1 .. P-1
+    typedef typename A::W W;
+    static_assert(sizeof(W) == 4, "32-bit words");
+    static_assert(EC::P == ES::P && EC::G::R1 == ES::G::R1 + LOGC && EC::G::R1 <= 5, "pass 0 of the cluster = LOGC levels + pass 0 of the sub-block");
+    static_assert(!ES::kXor && !ES::kLoopPasses, "padded layout, compile-time pass chain");
+    constexpr int C = 1 << LOGC, T = ES::T, TC = EC::T, R = 32, NS = ES::N, PER = R / C;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    W* sm = reinterpret_cast<W*>(smem_raw);
+    const unsigned rank = cluster_ctarank();
+    const int tid = (int)threadIdx.x, u = (int)rank * T + tid;
+    W* base = data + (unsigned long long)(blockIdx.x >> LOGC) * poly_stride;
+    const typename EC::TwSrc twc = {tw, nullptr, &head};
+    const typename ES::TwSrc tws = {tw, tw_last + (size_t)rank * ES::LAST_WORDS, nullptr};
+    const unsigned nu0 = (unsigned)C + rank;
+    W x[1][R];
+    if constexpr (FWD) {
+        cluster_arrive(); // a CTA's shared memory may only be written once that CTA runs: everybody says so first ...
+#pragma unroll
+        for (int k = 0; k < R; k++) x[0][k] = ld_data(base + u + k * TC);
+        EC::template fwd_pass<0, 1>(x, twc, 1u, u, m);
+        cluster_wait();   // ... and is heard after the loads and pass 0
+        // slot k = owner (k / PER), local element (k % PER) * TC + u, in the padded layout gather<1> of the sub-block engine reads
+#pragma unroll
+        for (int d = 0; d < C; d++) {
+            if ((unsigned)d == rank) {
+#pragma unroll
+                for (int kk = 0; kk < PER; kk++) sm[pad_idx<W>(kk * TC + u)] = x[0][d * PER + kk];
+            } else {
+                const uint32_t rb = cluster_map(sm, (unsigned)d);
+#pragma unroll
+                for (int kk = 0; kk < PER; kk++) st_cluster(rb + 4u * (uint32_t)pad_idx<W>(kk * TC + u), x[0][d * PER + kk]);
+            }
+        }
+        cluster_sync_all();
+        ES::template gather<1, 1>(x, sm, tid);
+        if constexpr (ES::NBUF == 1 && 2 < ES::P) __syncthreads();
+        ES::template fwd_from<1, 1>(x, sm, tws, nu0, tid, m);
+#pragma unroll
+        for (int k = 0; k < R; k++) x[0][k] = A::canon_fwd(x[0][k], m);
+        store_contig<W, R>(base + (size_t)rank * NS + ES::elem_last(tid, 0), x[0]);
+    } else {
+        load_contig<W, R>(base + (size_t)rank * NS + ES::elem_last(tid, 0), x[0]);
+        ES::template inv_down<ES::P - 1, 1, 1>(x, sm, tws, nu0, tid, m);
+        // pass-1 layout of the sub-block: element blk * B1 + o + k * S1 (blk = tid / S1, o = tid % S1), global element rank * NS + that
+        // = slot (rank * PER + blk) of cluster thread (o + k * S1) in the pass-0 layout: owner CTA (o + k S1) / T, its thread (o + k S1) % T
+        constexpr int S1 = ES::template stride<1>();
+        static_assert(ES::template blk_words<1>() == TC && S1 * R == TC, "pass-1 blocks of the sub-block = pass-0 stride of the cluster");
+        const int blk = tid / S1, o = tid % S1;
+        const int slot = (int)rank * PER + blk;
+        cluster_sync_all(); // every CTA of the cluster is done reading its exchange buffer
+#pragma unroll
+        for (int d = 0; d < C; d++) {
+            constexpr int KPER = T / S1; // register slots per owner
+            if ((unsigned)d == rank) {
+#pragma unroll
+                for (int kk = 0; kk < KPER; kk++) sm[slot * T + o + kk * S1] = x[0][d * KPER + kk];
+            } else {
+                const uint32_t rb = cluster_map(sm, (unsigned)d);
+#pragma unroll
+                for (int kk = 0; kk < KPER; kk++) st_cluster(rb + 4u * (uint32_t)(slot * T + o + kk * S1), x[0][d * KPER + kk]);
+            }
+        }
+        cluster_sync_all();
+#pragma unroll
+        for (int k = 0; k < R; k++) x[0][k] = sm[k * T + tid];
+        EC::template inv_pass<0, 1>(x, twc, 1u, u, m);
+#pragma unroll
+        for (int k = 0; k < R; k++) st_data(base + u + k * TC, A::canon_inv(x[0][k], m));
+    }
+}
+
 // ---- pointwise --------------------------------------------------------------------------------
 enum PointwiseOp { OP_MUL_ASSIGN_NORMALIZE = 0, OP_NORMALIZE = 1, OP_MUL_ACCUMULATE = 2 };
 
@@ -884,6 +991,29 @@ cudaError_t launch_strided(const PlanDev<A>& pl, int logk, typename A::W* data, 
     return cudaErrorInvalidValue;
 }
 
+template <class A, int LOGN, int LOGC, bool FWD>
+cudaError_t launch_cluster(const PlanDev<A>& pl, typename A::W* data, size_t batch, size_t poly_stride, cudaStream_t st)
+{
+    typedef Engine<A, LOGN - LOGC, 5> ES;
+    const TwHead<typename A::Tw>* head = FWD ? pl.head_fwd : pl.head_inv;
+    if (head == nullptr) return cudaErrorInvalidValue;
+    if (((unsigned long long)batch << LOGC) > 0x7fffffffull) return cudaErrorInvalidValue;
+    auto kern = k_ntt_cluster<A, LOGN, LOGC, FWD>;
+    const size_t smem = (size_t)ES::SMEM_WORDS * ES::NBUF * sizeof(typename A::W);
+    if (cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem); e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(batch << LOGC));
+    cfg.blockDim = dim3(ES::T);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1 << LOGC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, FWD ? pl.tw_fwd : pl.tw_inv, FWD ? pl.tw_fwd_last : pl.tw_inv_last, pl.mod, data,
+                              (unsigned long long)poly_stride, *head);
+}
+
 // Full transform of `batch` polynomials.  N <= 4096: one CTA-kernel launch.  Larger: leading stages
 // strided (<= 4 per launch) until the remaining contiguous blocks are 4096 words, then the CTA
 // kernel on all batch * 2^s blocks; the inverse runs the same schedule backwards.
@@ -896,6 +1026,11 @@ cudaError_t launch_ntt(const PlanDev<A>& pl, typename A::W* data, size_t batch, 
     const int blk = cta_block_logn<A>(pl.logn, FWD);
     if (pl.logn == blk) return launch_cta<A, FWD>(pl, pl.logn, data, batch, 0, poly_stride, st);
     const int lead = pl.logn - blk;
+#if CNTT_CLUSTER32
+    if constexpr (sizeof(typename A::W) == 4) {
+        if (pl.logn == 15 && blk == 14 && (FWD ? pl.head_fwd : pl.head_inv) != nullptr) return launch_cluster<A, 15, 1, FWD>(pl, data, batch, poly_stride, st);
+    }
+#endif
     constexpr int kmax = sizeof(typename A::W) == 4 ? (FWD ? CNTT_STRIDED_MAXK32_FWD : CNTT_STRIDED_MAXK32_INV) : ShiftHead<A>::value ? CNTT_STRIDED_MAXK64S : 4;
     cudaError_t e;
     if constexpr (FWD) {

@@ -42,21 +42,27 @@ for c in cases:
         print("native%d split n=%d batch=%d: fwd %.3f ms (%.1f M/s)  inv %.3f ms (%.1f M/s)" % (bits, n, batch, tf, batch / tf / 1e3, ti, batch / ti / 1e3))
         continue
     if kind.startswith("pre"):      # polymul with the rhs already transformed (cntt_native_polymul_ntt_rhs), one key per product
-        bits = int(kind[3:])
-        plan = getattr(cntt, "native%d" % bits).Plan32.try_new(n)
+        binary = kind.startswith("preb")   # preb64: native_binary64, the {0,1} operand is the pre-transformed key
+        bits = int(kind[4:] if binary else kind[3:])
+        plan = getattr(cntt, ("native_binary%d" if binary else "native%d") % bits).Plan32.try_new(n)
         dt = torch.int32 if bits == 32 else torch.int64
         hi = 2**31 - 1 if bits == 32 else 2**63 - 1
         shape = (batch, n, 2) if bits == 128 else (batch, n)
         lhs = torch.randint(-hi - 1, hi, shape, dtype=dt, device="cuda", generator=g)
         rhs = torch.randint(-hi - 1, hi, shape, dtype=dt, device="cuda", generator=g)
         planes = torch.empty((plan.num_primes(), batch, n), dtype=torch.int32, device="cuda")
-        plan.fwd(rhs, planes)
+        if binary:
+            rhs &= 1
+            if bits == 128: rhs[..., 1] = 0
+            plan.fwd_binary(rhs, planes)
+        else:
+            plan.fwd(rhs, planes)
         key = planes[:, :1].contiguous()
         prod = torch.empty_like(lhs)
         ms = bench(lambda: plan.negacyclic_polymul_ntt_rhs(prod, lhs, planes))
         ms1 = bench(lambda: plan.negacyclic_polymul_ntt_rhs(prod, lhs, key))
-        print("native%d polymul, rhs pre-transformed n=%d batch=%d: %.3f ms  %.2f M polymul/s (one key per product)   %.3f ms  %.2f M polymul/s (shared key)"
-              % (bits, n, batch, ms, batch / ms / 1e3, ms1, batch / ms1 / 1e3))
+        print("%s%d polymul, rhs pre-transformed n=%d batch=%d: %.3f ms  %.2f M polymul/s (one key per product)   %.3f ms  %.2f M polymul/s (shared key)"
+              % ("native_binary" if binary else "native", bits, n, batch, ms, batch / ms / 1e3, ms1, batch / ms1 / 1e3))
         continue
     if kind.startswith("native") or kind.startswith("binary"):
         bits = int(kind.replace("native", "").replace("binary", ""))
