@@ -296,6 +296,30 @@ def cpu_baseline_leg():
             "sample": "%d of the %d polynomials, fwd+inv %d times after one warm-up pass (%.1f core-s); %s" % (sample, BATCH, passes, dt * threads, desc)}
 
 
+def cpu_prime32_leg(n=1024, p=1062862849, sample=32768):
+    """configs[0]'s transform on the host cores (rank 0, N=1 only): the 16- / 8-lane Shoup port of the reference's prime32 SIMD path
+    (oracle/cntt_simd32.c, src/prime32/shoup.rs:305-451), OpenMP over polynomials, ~2 s."""
+    from oracle import oracle as O
+    try:
+        O.build(native=True)
+        native = True
+    except Exception:
+        native = False
+    threads = host_threads()
+    plan = O.Plan32.try_new(n, p, native=native)
+    buf = np.random.default_rng(3).integers(0, p, size=(sample, n), dtype=np.uint32)   # 128 MiB: larger than the host caches
+    plan.fwd_batch(buf, threads)
+    plan.inv_batch(buf, threads)
+    passes, t0 = 0, time.perf_counter()
+    while passes < 3 or time.perf_counter() - t0 < 1.5:
+        plan.fwd_batch(buf, threads)
+        plan.inv_batch(buf, threads)
+        passes += 1
+    dt = time.perf_counter() - t0
+    return {"ntts_per_s": 2.0 * sample * passes / dt, "cores": threads, "kind": "port", "isa": O.simd_isa(native),
+            "sample": "%d polynomials, fwd+inv %d times after one warm-up pass" % (sample, passes)}
+
+
 # ------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -452,6 +476,8 @@ def run_ours(args):
             "hbm_frac_fwd": 2 * 1024 * 4 * BATCH / (res["fwd"] * 1e-3) / 1e9 / peak,
             "hbm_frac_inv": 2 * 1024 * 4 * BATCH / (res["inv"] * 1e-3) / 1e9 / peak, "per": "GPU"}
         del d32
+        if rank == 0 and world == 1:
+            extra["prime32_n1024_p0_b65536"]["cpu"] = cpu_prime32_leg()
     except Exception as e:
         extra["prime32_error"] = repr(e)
 

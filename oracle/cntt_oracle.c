@@ -1396,22 +1396,26 @@ EXPORT int o_max_threads(void)
 #define PAR_FOR
 #endif
 
+/* CPU-baseline legs of bench.py: the SIMD ports of the reference's vector paths where the host has the ISA (cntt_simd.c: Solinas,
+ * cntt_simd32.c: 32-bit Shoup-form primes) */
+#include "cntt_simd.c"
+#include "cntt_simd32.c"
+static int g_batch_isa = -1; /* -1 best available, 0 scalar, 2 AVX2, 3 AVX-512 */
+EXPORT void o_set_batch_isa(int isa) { g_batch_isa = isa; }
 EXPORT void o_plan32_fwd_batch(const o_plan32 *pl, u32 *buf, size_t batch, int nthreads)
 {
     (void)nthreads;
+    const int isa = g_batch_isa;
     PAR_FOR
-    for (long b = 0; b < (long)batch; b++) o_plan32_fwd(pl, buf + (size_t)b * pl->n);
+    for (long b = 0; b < (long)batch; b++) o_plan32_fwd_simd(pl, buf + (size_t)b * pl->n, isa);
 }
 EXPORT void o_plan32_inv_batch(const o_plan32 *pl, u32 *buf, size_t batch, int nthreads)
 {
     (void)nthreads;
+    const int isa = g_batch_isa;
     PAR_FOR
-    for (long b = 0; b < (long)batch; b++) o_plan32_inv(pl, buf + (size_t)b * pl->n);
+    for (long b = 0; b < (long)batch; b++) o_plan32_inv_simd(pl, buf + (size_t)b * pl->n, isa);
 }
-/* CPU-baseline legs of bench.py: the SIMD port of the reference's vector path where the host has the ISA (cntt_simd.c) */
-#include "cntt_simd.c"
-static int g_batch_isa = -1; /* -1 best available, 0 scalar, 2 AVX2, 3 AVX-512 */
-EXPORT void o_set_batch_isa(int isa) { g_batch_isa = isa; }
 EXPORT void o_plan64_fwd_batch(const o_plan64 *pl, u64 *buf, size_t batch, int nthreads)
 {
     (void)nthreads;

@@ -18,7 +18,7 @@ def build(native=False):
     """Compile the oracle if the shared object is missing (gcc is in the image)."""
     name = "libcntt_oracle_native.so" if native else "libcntt_oracle.so"
     path = os.path.join(_HERE, name)
-    srcs = [os.path.join(_HERE, f) for f in ("cntt_oracle.c", "cntt_simd.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("cntt_oracle.c", "cntt_simd.c", "cntt_simd32.c")]
     if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "native" if native else "all"],
                               stdout=subprocess.DEVNULL)
@@ -83,6 +83,8 @@ def _load(native=False):
         "o_set_batch_isa": (None, [C.c_int]),
         "o_plan64_fwd_simd": (None, [vp, vp, C.c_int]),
         "o_plan64_inv_simd": (None, [vp, vp, C.c_int]),
+        "o_plan32_fwd_simd": (None, [vp, vp, C.c_int]),
+        "o_plan32_inv_simd": (None, [vp, vp, C.c_int]),
         "o_native_polymul_batch": (None, [vp, vp, vp, vp, sz, C.c_int]),
     }
     for name, (res, args) in sig.items():
@@ -205,6 +207,22 @@ class _PrimePlan:
         self._chk(buf)
         getattr(self._L, self._pre + "_inv_batch")(self._h, _ptr(buf), buf.size // self.n, nthreads)
 
+    def _simd(self, name, buf, isa):
+        self._chk(buf)
+        assert buf.shape[-1] == self.n
+        fn = getattr(self._L, "%s_%s_simd" % (self._pre, name))
+        for row in buf.reshape(-1, self.n):
+            fn(self._h, _ptr(row), ISA_CODES[isa])
+        return buf
+
+    def fwd_simd(self, buf, isa="best"):
+        """Plan::fwd through the AVX-512 / AVX2 port of the reference's vector path (cntt_simd.c: Solinas; cntt_simd32.c: 32-bit
+        primes below 2^31); every other class runs the scalar path"""
+        return self._simd("fwd", buf, isa)
+
+    def inv_simd(self, buf, isa="best"):
+        return self._simd("inv", buf, isa)
+
     def mul_assign_normalize(self, lhs, rhs):
         self._chk(lhs, rhs)
         getattr(self._L, self._pre + "_mul_assign_normalize")(self._h, _ptr(lhs), _ptr(rhs), min(lhs.size, rhs.size))
@@ -233,20 +251,6 @@ class Plan64(_PrimePlan):
     _pre = "o_plan64"
     _dt = np.dtype(np.uint64)
 
-    def _simd(self, name, buf, isa):
-        self._chk(buf)
-        assert buf.shape[-1] == self.n
-        fn = getattr(self._L, "o_plan64_%s_simd" % name)
-        for row in buf.reshape(-1, self.n):
-            fn(self._h, _ptr(row), ISA_CODES[isa])
-        return buf
-
-    def fwd_simd(self, buf, isa="best"):
-        """Plan::fwd through the AVX-512 / AVX2 port of the reference's vector path (cntt_simd.c; Solinas only)"""
-        return self._simd("fwd", buf, isa)
-
-    def inv_simd(self, buf, isa="best"):
-        return self._simd("inv", buf, isa)
 
 
 ISA_CODES = {"best": -1, "scalar": 0, "avx2": 2, "avx512": 3}
