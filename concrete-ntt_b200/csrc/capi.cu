@@ -639,7 +639,12 @@ static int host_multi(int nplans, size_t batch, Fn shard_fn)
     th.reserve((size_t)nplans);
     for (int g = 0; g < nplans; g++) {
         const size_t b0 = batch * (size_t)g / (size_t)nplans, b1 = batch * (size_t)(g + 1) / (size_t)nplans;
-        th.emplace_back([&, g, b0, b1]() { rc[(size_t)g] = b1 > b0 ? shard_fn(g, b0, b1 - b0) : CNTT_OK; });
+        if (b1 <= b0) continue;
+        try {
+            th.emplace_back([&, g, b0, b1]() { rc[(size_t)g] = shard_fn(g, b0, b1 - b0); });
+        } catch (...) { // no thread to be had (std::system_error): run the shard on the calling thread rather than throw across the C ABI
+            rc[(size_t)g] = shard_fn(g, b0, b1 - b0);
+        }
     }
     for (auto& t : th) t.join();
     for (int r : rc)

@@ -20,4 +20,10 @@ for t in memcheck racecheck synccheck; do
   run $t product 32 2048
   run $t product_generic 16 2048
 done
+if [ -f build/libcntt_cl.so ]; then   # the cluster experiment (DSMEM push exchange), variant library
+  export CNTT_B200_LIB=build/libcntt_cl.so
+  echo "== variant build/libcntt_cl.so (-DCNTT_CLUSTER32=1)" >> $OUT
+  for t in memcheck synccheck racecheck; do run $t ntt32 6 32768; done
+  unset CNTT_B200_LIB
+fi
 cat $OUT
