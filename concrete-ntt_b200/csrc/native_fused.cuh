@@ -11,21 +11,42 @@
 
 namespace cntt {
 
-// Per-kind configuration (bit k = NativeKind k; tools/build_variant.sh overrides these for A/B runs):
+// Per-kind configuration:
 //   RELOAD: the operands are re-read from global memory (L2 hits after the first prime) for every prime instead of
 //           living in registers across the prime loop (128-bit words: 64 registers per thread)
 //   ACC:    the reconstruction sum of reconstruct_bounded is accumulated per prime in registers (word + float per
 //           coefficient) instead of parking np residue polynomials in shared memory -- for the 128-bit kinds that
 //           is 160 KB at N = 4096, which pinned the kernel at one CTA per SM
+// The two go together (fused_acc_reload): without the stash a CTA needs 34 KB of shared memory instead of 75 KB, without the
+// operand registers it fits 128 registers, and the kernel is then compiled for 512 resident threads (four CTAs of 128 threads
+// per SM instead of three).  Measured per kind on B200 (profiles/r02_experiments.txt, "acc occupancy"), M polymul/s at N = 2048:
+//   128-bit kinds (N <= 2048)   native128 5.43 -> 5.64 (N = 1024: 12.1 -> 13.2), binary128 11.1 -> 11.9              -> on
+//   native32                    27.3 -> 28.6 (N = 1024: 58.2 -> 56.5)                                                  -> on at N = 2048
+//   pre-transformed rhs         native32 35.0 -> 38.6, native64 18.5 -> 20.2, binary32 47.3 -> 55.4, binary64 32.7 -> 32.3
+//                               (N = 1024 loses 2 %)                                                                   -> on at N = 2048 but binary64
+//   native64, binary32/64       14.9 -> 14.3, 43.0 -> 41.7, 26.9 -> 25.9 (the accumulators spill)                      -> off
+// CNTT_FUSED_RELOAD_MASK / CNTT_FUSED_ACC_MASK (bit k = NativeKind k) override the table for A/B runs (tools/build_variant.sh).
 #ifndef CNTT_FUSED_RELOAD_MASK
-#define CNTT_FUSED_RELOAD_MASK 0x24
+#define CNTT_FUSED_RELOAD_MASK (-1)
 #endif
 #ifndef CNTT_FUSED_ACC_MASK
-#define CNTT_FUSED_ACC_MASK 0x24
+#define CNTT_FUSED_ACC_MASK (-1)
 #endif
 #ifndef CNTT_FUSED_MINTHREADS
-#define CNTT_FUSED_MINTHREADS 768 // resident threads per SM the kernel is compiled for (register cap 65536 / this)
+#define CNTT_FUSED_MINTHREADS 0 // resident threads per SM the kernel is compiled for (register cap 65536 / this); 0: 512 with ACC + RELOAD, else 768
 #endif
+constexpr bool fused_acc_reload(int kind, int logn, bool pre)
+{
+    if (kind == NK_NATIVE128 || kind == NK_BINARY128) return logn <= 11;
+    if (logn != 11) return false;
+    return kind == NK_NATIVE32 || (pre && (kind == NK_NATIVE64 || kind == NK_BINARY32));
+}
+constexpr bool fused_reload(int kind, int logn, bool pre) { return CNTT_FUSED_RELOAD_MASK >= 0 ? (((CNTT_FUSED_RELOAD_MASK >> kind) & 1) != 0 && logn <= 11) : fused_acc_reload(kind, logn, pre); }
+constexpr bool fused_acc(int kind, int logn, bool pre) { return CNTT_FUSED_ACC_MASK >= 0 ? (((CNTT_FUSED_ACC_MASK >> kind) & 1) != 0 && logn <= 11) : fused_acc_reload(kind, logn, pre); }
+constexpr int fused_minthreads(int kind, int logn, bool pre)
+{
+    return CNTT_FUSED_MINTHREADS != 0 ? CNTT_FUSED_MINTHREADS : (fused_reload(kind, logn, pre) && fused_acc(kind, logn, pre)) ? 512 : 768;
+}
 constexpr int kFusedMinLogN = 5, kFusedMaxLogN = 12;
 
 // Binary plans: rhs in {0,1}^N (src/native_binary64.rs:423-444; anything else is unspecified there).  The first register pass of
@@ -82,21 +103,19 @@ struct FusedParams {
     uint2 lscale[10][4];
 };
 
-template <int KIND, int LOGN, int LOGR>
+template <int KIND, int LOGN, int LOGR, bool PRE = false>
 struct FusedCfg {
     typedef Engine<A32L4, LOGN, LOGR> E;
     static constexpr int NP = native_fused_np(KIND, dev::KindInfo<KIND>::NP); // native128: nine of the ten primes (native.hpp)
     static constexpr int T = E::T;
     static constexpr int GP = T >= 128 ? 1 : 128 / T;
     static constexpr int XCHG_WORDS = 2 * E::NBUF * E::SMEM_WORDS;   // two polynomials in flight (lhs, rhs)
-    // measured on B200 (native128): N = 2048 4.74 -> 4.99 M polymul/s with RELOAD + ACC, N = 4096 2.46 -> 2.25 (512
-    // threads per CTA leave 128 registers per thread either way, and the accumulators spill), so N <= 2048 only;
-    // the 32/64-bit kinds lose 4 % with ACC (registers) and are left on the shared-memory stash
-    static constexpr bool RELOAD = ((CNTT_FUSED_RELOAD_MASK >> KIND) & 1) != 0 && LOGN <= 11;
-    static constexpr bool ACC = ((CNTT_FUSED_ACC_MASK >> KIND) & 1) != 0 && LOGN <= 11;
+    static constexpr bool RELOAD = fused_reload(KIND, LOGN, PRE);
+    static constexpr bool ACC = fused_acc(KIND, LOGN, PRE);
+    static constexpr int MINTHREADS = fused_minthreads(KIND, LOGN, PRE);
     static constexpr int STASH_WORDS = ACC ? 0 : NP * E::N;
     static constexpr size_t SMEM_BYTES = (size_t)GP * (XCHG_WORDS + STASH_WORDS) * sizeof(uint32_t);
-    static constexpr int BLK_BY_THREADS = CNTT_FUSED_MINTHREADS > GP * T ? CNTT_FUSED_MINTHREADS / (GP * T) : 1;
+    static constexpr int BLK_BY_THREADS = MINTHREADS > GP * T ? MINTHREADS / (GP * T) : 1;
     static constexpr int BLK_BY_SMEM = (int)((size_t)227 * 1024 / (SMEM_BYTES + 1024)) > 0 ? (int)((size_t)227 * 1024 / (SMEM_BYTES + 1024)) : 1;
     static constexpr int MINBLK = BLK_BY_THREADS < BLK_BY_SMEM ? BLK_BY_THREADS : BLK_BY_SMEM; // no point capping registers below what shared memory admits
 };
@@ -112,11 +131,11 @@ struct FusedCfg {
 // caller of the reference does per prime): only the lhs is reduced and transformed, the rhs residues are read in the last-pass layout
 // (R consecutive words per thread), and two of the three transforms per prime remain.
 template <int KIND, int LOGN, int LOGR, bool PRE = false>
-__global__ void __launch_bounds__(FusedCfg<KIND, LOGN, LOGR>::GP * FusedCfg<KIND, LOGN, LOGR>::T, FusedCfg<KIND, LOGN, LOGR>::MINBLK)
+__global__ void __launch_bounds__(FusedCfg<KIND, LOGN, LOGR, PRE>::GP * FusedCfg<KIND, LOGN, LOGR, PRE>::T, FusedCfg<KIND, LOGN, LOGR, PRE>::MINBLK)
 k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ prod, const void* __restrict__ lhs,
                 const void* __restrict__ rhs, unsigned long long batch)
 {
-    typedef FusedCfg<KIND, LOGN, LOGR> Cfg;
+    typedef FusedCfg<KIND, LOGN, LOGR, PRE> Cfg;
     typedef typename Cfg::E E;
     typedef typename dev::KindInfo<KIND>::Word Word;
     constexpr int T = Cfg::T, R = E::R, N = E::N, NP = Cfg::NP, GP = Cfg::GP;
@@ -257,7 +276,7 @@ static cudaError_t launch_fused_one(const NativePlanDev& pl, void* prod, const v
                                     size_t pre_plane_stride = 0, size_t pre_poly_stride = 0)
 {
     constexpr int LOGR = native_fused_logr(KIND, LOGN);
-    typedef FusedCfg<KIND, LOGN, LOGR> Cfg;
+    typedef FusedCfg<KIND, LOGN, LOGR, PRE> Cfg;
     FusedParams fp;
     fp.pre_plane_stride = pre_plane_stride;
     fp.pre_poly_stride = pre_poly_stride;

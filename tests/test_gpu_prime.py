@@ -324,3 +324,37 @@ def test_host_multi_splits_one_batch_over_plans(cntt, oracle, torch_cuda):
     prod = np.zeros_like(lhs)
     cntt.HostMulti(plans).negacyclic_polymul(prod, lhs, rhs)
     assert (prod == oracle.Native.try_new(n, 64).negacyclic_polymul(lhs, rhs)).all()
+
+
+def test_device_calls_are_graph_capturable(cntt, oracle, torch_cuda):
+    """Every device entry point is stream-ordered and allocation-free: a pipeline of them -- multi-launch
+    transforms included -- can be captured into a CUDA graph and replayed.  Replays are checked against the oracle."""
+    torch = torch_cuda
+    P = 0xFFFFFFFF00000001
+    g = rng(77)
+    cases = [(cntt.prime64.Plan, oracle.Plan64, 2048, P, np.uint64), (cntt.prime64.Plan, oracle.Plan64, 16384, P, np.uint64),
+             (cntt.prime32.Plan, oracle.Plan32, 1024, 1062862849, np.uint32), (cntt.prime32.Plan, oracle.Plan32, 65536, 1062862849, np.uint32)]
+    for GP, OP, n, p, dt in cases:
+        gp, op = GP.try_new(n, p), OP.try_new(n, p)
+        a, b = rand_mod(g, p, (3, n), dt), rand_mod(g, p, (3, n), dt)
+        da, db = dev(torch, a), dev(torch, b)
+        src_a, src_b = da.clone(), db.clone()
+        gp.fwd(da); gp.inv(da)                       # warm-up outside the capture (module load, shared-memory attributes)
+        gp.mul_assign_normalize(da, db)
+        s = torch.cuda.Stream()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(s):
+            da.copy_(src_a); db.copy_(src_b)
+            s.synchronize()
+            with torch.cuda.graph(graph, stream=s):  # negacyclic product of a and b, in place in da
+                gp.fwd(da)
+                gp.fwd(db)
+                gp.mul_assign_normalize(da, db)
+                gp.inv(da)
+        want = op.inv(op.mul_assign_normalize(op.fwd(a.copy()), op.fwd(b.copy())))
+        for _ in range(3):
+            da.copy_(src_a); db.copy_(src_b)
+            torch.cuda.synchronize()
+            graph.replay()
+            torch.cuda.synchronize()
+            assert (host(da, dt) == want).all(), (n, p)
