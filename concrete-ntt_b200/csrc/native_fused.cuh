@@ -32,6 +32,9 @@ namespace cntt {
 #ifndef CNTT_FUSED_ACC_MASK
 #define CNTT_FUSED_ACC_MASK (-1)
 #endif
+#ifndef CNTT_FUSED_SEQ_MASK
+#define CNTT_FUSED_SEQ_MASK 0
+#endif
 #ifndef CNTT_FUSED_MINTHREADS
 #define CNTT_FUSED_MINTHREADS 0 // resident threads per SM the kernel is compiled for (register cap 65536 / this); 0: 512 with ACC + RELOAD, else 768
 #endif
@@ -109,11 +112,15 @@ struct FusedCfg {
     static constexpr int NP = native_fused_np(KIND, dev::KindInfo<KIND>::NP); // native128: nine of the ten primes (native.hpp)
     static constexpr int T = E::T;
     static constexpr int GP = T >= 128 ? 1 : 128 / T;
-    static constexpr int XCHG_WORDS = 2 * E::NBUF * E::SMEM_WORDS;   // two polynomials in flight (lhs, rhs)
-    static constexpr bool RELOAD = fused_reload(KIND, LOGN, PRE);
     static constexpr bool ACC = fused_acc(KIND, LOGN, PRE);
-    static constexpr int MINTHREADS = fused_minthreads(KIND, LOGN, PRE);
-    static constexpr int STASH_WORDS = ACC ? 0 : NP * E::N;
+    // SEQ (experiment, CNTT_FUSED_SEQ_MASK): the two forward transforms of a prime run one after the other through ONE set of exchange
+    // buffers, the last prime's residues stay in registers instead of the stash, the operands are re-read per prime, and the kernel is
+    // compiled for 512 resident threads: 50 KB instead of 75 KB of shared memory at N = 2048 with five primes, four CTAs per SM
+    static constexpr bool SEQ = ((CNTT_FUSED_SEQ_MASK >> KIND) & 1) != 0 && LOGN == 11 && !PRE && !ACC && KIND < NK_BINARY32;
+    static constexpr int XCHG_WORDS = ((PRE || SEQ) ? 1 : 2) * E::NBUF * E::SMEM_WORDS;   // polynomials in flight: lhs and rhs, or one at a time
+    static constexpr bool RELOAD = fused_reload(KIND, LOGN, PRE) || SEQ;
+    static constexpr int MINTHREADS = SEQ ? 512 : fused_minthreads(KIND, LOGN, PRE);
+    static constexpr int STASH_WORDS = ACC ? 0 : (SEQ ? NP - 1 : NP) * E::N;
     static constexpr size_t SMEM_BYTES = (size_t)GP * (XCHG_WORDS + STASH_WORDS) * sizeof(uint32_t);
     static constexpr int BLK_BY_THREADS = MINTHREADS > GP * T ? MINTHREADS / (GP * T) : 1;
     static constexpr int BLK_BY_SMEM = (int)((size_t)227 * 1024 / (SMEM_BYTES + 1024)) > 0 ? (int)((size_t)227 * 1024 / (SMEM_BYTES + 1024)) : 1;
@@ -179,6 +186,7 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
         for (int k = 0; k < R; k++) { acc[k] = 0; accf[k] = 0.0f; }
     }
 
+    uint32_t y[1][R]; // one prime's product residues; after the loop: the last prime's (SEQ reads them from here)
 #pragma unroll 1
     for (int pk = 0; pk < NP; pk++) {
         const Mod32 m = fp.mod[pk];
@@ -221,10 +229,21 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
 #pragma unroll
             for (int k = 0; k < R; k++) x[0][k] = xl[0][k];
             E::template fwd_after_pass0<2>(x, sm, tws, 1u, tid, m);
+        } else if constexpr (Cfg::SEQ) {
+            static_assert(!Cfg::SEQ || (E::P == 3 && E::NBUF == 2), "back-to-back transforms without a barrier in between: two exchanges on two buffers");
+            const typename E::TwSrc tws = {fp.tw_fwd[pk], fp.tw_fwd_last[pk]};
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint32_t xl[1][R];
+#pragma unroll
+                for (int k = 0; k < R; k++) xl[0][k] = x[h][k];
+                E::template fwd<1>(xl, sm, tws, 1u, tid, m);
+#pragma unroll
+                for (int k = 0; k < R; k++) x[h][k] = xl[0][k];
+            }
         } else {
             E::template fwd<2>(x, sm, typename E::TwSrc{fp.tw_fwd[pk], fp.tw_fwd_last[pk]}, 1u, tid, m);
         }
-        uint32_t y[1][R];
         const uint32_t pinv = c.pinv[pk];
 #pragma unroll
         for (int k = 0; k < R; k++) y[0][k] = dev::mont(dev::red2p(x[0][k], p), dev::red2p(x[1][k], p), p, pinv);
@@ -242,9 +261,12 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
                 acc[k] += (Word)yk * mk;
                 accf[k] = fmaf(__uint2float_rn(yk), ip, accf[k]);
             }
-        } else {
+        } else if (!Cfg::SEQ || pk < NP - 1) {
 #pragma unroll
             for (int k = 0; k < R; k++) stash[pk * N + tid + k * T] = A32L4::canon_inv(y[0][k], m);
+        } else {
+#pragma unroll
+            for (int k = 0; k < R; k++) y[0][k] = A32L4::canon_inv(y[0][k], m);
         }
         if constexpr (E::NBUF == 1 && E::P >= 2) __syncthreads(); // inv gather vs next prime's fwd scatter
     }
@@ -264,7 +286,7 @@ k_polymul_fused(const NativeConsts c, const FusedParams fp, void* __restrict__ p
             for (int k = 0; k < R; k++) {
                 uint32_t r[NP];
 #pragma unroll
-                for (int pk = 0; pk < NP; pk++) r[pk] = stash[pk * N + tid + k * T];
+                for (int pk = 0; pk < NP; pk++) r[pk] = (Cfg::SEQ && pk == NP - 1) ? y[0][k] : stash[pk * N + tid + k * T];
                 dev::store_word<KIND>(prod, base + tid + k * T, dev::reconstruct_bounded<KIND, NP>(r, c));
             }
         }
