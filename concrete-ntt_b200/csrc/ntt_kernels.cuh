@@ -310,27 +310,18 @@ __host__ __device__ constexpr bool cta_stages_out()
 #ifndef CNTT_CTA_MINTHREADS32_INV
 #define CNTT_CTA_MINTHREADS32_INV 1024
 #endif
-// EXPERIMENT: sub-block launches (the CTA level of a multi-launch transform) carrying the SAME sub-block of CNTT_NP32_SUB consecutive
-// polynomials per thread group, so that the sub-block's twiddles -- read through L1, not the constant bank -- are loaded once for both
-#ifndef CNTT_NP32_SUB
-#define CNTT_NP32_SUB 1
-#endif
-#ifndef CNTT_NP32_SUB_MINTHREADS
-#define CNTT_NP32_SUB_MINTHREADS 512
-#endif
 #ifndef CNTT_CTA_MINTHREADS32_FWD_SUB
 #define CNTT_CTA_MINTHREADS32_FWD_SUB 1280
 #endif
-template <class A, int LOGN, int LOGR, int GP, bool FWD, bool HEAD, int NP = 1>
+template <class A, int LOGN, int LOGR, int GP, bool FWD, bool HEAD>
 constexpr int cta_min_blocks()
 {
-    if (NP >= 2 && !HEAD) return CNTT_NP32_SUB_MINTHREADS > GP * Geo<LOGN, LOGR>::T ? CNTT_NP32_SUB_MINTHREADS / (GP * Geo<LOGN, LOGR>::T) : 0;
     constexpr int want = sizeof(typename A::W) == 8 ? ((LOGN == 13 && CNTT_CTA13_64_MINTHREADS) ? CNTT_CTA13_64_MINTHREADS : CNTT_CTA_MINTHREADS64) :
                          (LOGN == 13 && (FWD ? CNTT_CTA13_MINTHREADS_FWD : CNTT_CTA13_MINTHREADS_INV)) ? (FWD ? CNTT_CTA13_MINTHREADS_FWD : CNTT_CTA13_MINTHREADS_INV) : !FWD ? CNTT_CTA_MINTHREADS32_INV : !HEAD ? CNTT_CTA_MINTHREADS32_FWD_SUB : 0;
     return want > GP * Geo<LOGN, LOGR>::T ? want / (GP * Geo<LOGN, LOGR>::T) : 0; // 0 = unspecified (not the same as 1: ptxas then keeps its default register heuristic)
 }
 template <class A, int LOGN, int LOGR, int GP, bool FWD, bool HEAD, int NP>
-__global__ void __launch_bounds__(GP * Geo<LOGN, LOGR>::T, cta_min_blocks<A, LOGN, LOGR, GP, FWD, HEAD, NP>())
+__global__ void __launch_bounds__(GP * Geo<LOGN, LOGR>::T, cta_min_blocks<A, LOGN, LOGR, GP, FWD, HEAD>())
 k_ntt_cta(const typename A::Tw* __restrict__ tw, const typename A::Tw* __restrict__ tw_last, const typename A::Mod m,
           typename A::W* __restrict__ data, unsigned long long nvpoly, int log_sub, unsigned long long poly_stride,
           const __grid_constant__ TwHead<typename A::Tw> head)
@@ -343,17 +334,13 @@ k_ntt_cta(const typename A::Tw* __restrict__ tw, const typename A::Tw* __restric
 
     const int grp = (GP == 1) ? 0 : (int)(threadIdx.x / T);
     const int tid = (GP == 1) ? (int)threadIdx.x : (int)(threadIdx.x % T);
-    // group g owns polynomials [g NP, g NP + NP); with log_sub > 0 it owns sub-block (g mod 2^log_sub) of the NP polynomials
-    // [(g >> log_sub) NP, ...): the same sub-tree of the twiddle heap for all of them
-    const unsigned long long gidx = (unsigned long long)blockIdx.x * GP + grp;
-    const unsigned long long submask = (1ull << log_sub) - 1ull;
-    const unsigned long long vp0 = (HEAD || NP == 1) ? gidx * NP : (((gidx >> log_sub) * NP) << log_sub) + (gidx & submask);
-    const unsigned long long vstep = (HEAD || NP == 1) ? 1ull : (1ull << log_sub);
+    // group g owns polynomials [g NP, g NP + NP); with log_sub > 0 they are sub-blocks and NP == 1
+    const unsigned long long vp0 = ((unsigned long long)blockIdx.x * GP + grp) * NP;
     W* base[NP];
     bool active[NP];
 #pragma unroll
     for (int np = 0; np < NP; np++) {
-        unsigned long long vp = vp0 + np * vstep;
+        unsigned long long vp = vp0 + np;
         active[np] = vp < nvpoly;
         if (!active[np]) vp = nvpoly - 1; // keep the group in lock-step (barriers), discard its result
         // polynomial (vp >> log_sub) starts at poly_stride words per polynomial (product plans interleave planes;
@@ -870,7 +857,7 @@ cudaError_t launch_cta_np(const PlanDev<A>& pl, typename A::W* data, unsigned lo
     constexpr int GP = T >= 128 ? 1 : 128 / T;
     const size_t smem_xchg = (size_t)GP * NP * E::NBUF * E::SMEM_WORDS * sizeof(typename A::W);
     const size_t smem = smem_xchg;
-    const unsigned long long ngrp = (log_sub == 0 || NP == 1) ? (nvpoly + NP - 1) / NP : ((((nvpoly >> log_sub) + NP - 1) / NP) << log_sub);
+    const unsigned long long ngrp = (nvpoly + NP - 1) / NP;
     const unsigned long long nblk = (ngrp + GP - 1) / GP;
     if (nblk == 0) return cudaSuccess;
     if (nblk > 0x7fffffffull) return cudaErrorInvalidValue;
@@ -940,8 +927,8 @@ cudaError_t launch_cta_np(const PlanDev<A>& pl, typename A::W* data, unsigned lo
     }
     if (log_sub == 0 && head != nullptr) return launch(k_ntt_cta<A, LOGN, LOGR, GP, FWD, true, NP>, *head);
     static const TwHead<typename A::Tw> none = {};
-    if constexpr (NP == 1 || (NP == CNTT_NP32_SUB && sizeof(typename A::W) == 4 && LOGN >= 10 && LOGN <= 12)) return launch(k_ntt_cta<A, LOGN, LOGR, GP, FWD, false, NP>, none);
-    else return cudaErrorInvalidValue; // no such instantiation
+    if constexpr (NP == 1) return launch(k_ntt_cta<A, LOGN, LOGR, GP, FWD, false, 1>, none);
+    else return cudaErrorInvalidValue; // sub-block launches carry one block per group
 }
 // u32 whole transforms carry CNTT_NP32 polynomials per thread group (twiddle reuse); sub-blocks of a large
 // transform, 64-bit words and tiny batches carry one.
@@ -949,9 +936,6 @@ template <class A, int LOGN, bool FWD>
 cudaError_t launch_cta_one(const PlanDev<A>& pl, typename A::W* data, unsigned long long nvpoly, int log_sub, size_t poly_stride, cudaStream_t st)
 {
     constexpr int NPW = (sizeof(typename A::W) == 4 && CtaCfg<A, LOGN>::E::P >= 2) ? CNTT_NP32 : 1;
-    if constexpr (CNTT_NP32_SUB > 1 && sizeof(typename A::W) == 4 && LOGN >= 10 && LOGN <= 12) {
-        if (log_sub > 0 && (nvpoly >> log_sub) >= 2ull * CNTT_NP32_SUB) return launch_cta_np<A, LOGN, FWD, CNTT_NP32_SUB>(pl, data, nvpoly, log_sub, poly_stride, st);
-    }
     if constexpr (NPW > 1) {
         const TwHead<typename A::Tw>* head = FWD ? pl.head_fwd : pl.head_inv;
         if (log_sub == 0 && head != nullptr && nvpoly >= 2ull * NPW * 148ull) return launch_cta_np<A, LOGN, FWD, NPW>(pl, data, nvpoly, log_sub, poly_stride, st);
