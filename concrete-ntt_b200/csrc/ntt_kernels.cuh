@@ -1,8 +1,11 @@
 // ntt_kernels.cuh -- batched single-prime kernels built on the engine, and their launchers.
 //
-//   k_ntt_cta      one polynomial (or contiguous sub-block of a large polynomial) per thread group,
-//                  all of its stages in registers + shared memory          (N' <= 4096)
-//   k_ntt_strided  the leading 1..4 stages of a large transform, strided through global memory
+//   k_ntt_cta      one polynomial (or contiguous sub-block of a large polynomial) per thread group, all of its stages in
+//                  registers + shared memory: N' <= 4096 with 16 words per thread; 32-bit words also N' = 8192 / 16384 with
+//                  32 words per thread and one exchange buffer; 64-bit words N' = 8192 (forward)
+//   k_ntt_cta_pipe persistent, software-pipelined flavour of the same (kept for A/B runs; the one-shot kernel is what ships)
+//   k_ntt_strided  the leading 1..5 stages of a larger transform, strided through global memory (shift butterflies for Solinas)
+//   k_ntt_cluster  N = 32768 on two-CTA clusters with a DSMEM exchange (experiment, off: measured slower than strided + CTA)
 //   k_pointwise    mul_assign_normalize / normalize / mul_accumulate streams
 //
 // Batch layout everywhere: polynomial-major contiguous, buf[b*N + i] (the reference's slices
@@ -1014,8 +1017,8 @@ cudaError_t launch_cluster(const PlanDev<A>& pl, typename A::W* data, size_t bat
                               (unsigned long long)poly_stride, *head);
 }
 
-// Full transform of `batch` polynomials.  N <= 4096: one CTA-kernel launch.  Larger: leading stages
-// strided (<= 4 per launch) until the remaining contiguous blocks are 4096 words, then the CTA
+// Full transform of `batch` polynomials.  Sizes one CTA holds (cta_block_logn): one CTA-kernel launch.  Larger: leading stages
+// strided (kmax per launch) until the remaining contiguous blocks have the size cta_block_logn names, then the CTA
 // kernel on all batch * 2^s blocks; the inverse runs the same schedule backwards.
 // poly_stride: distance in words between consecutive polynomials of the batch (0: contiguous, = N)
 template <class A, bool FWD>
