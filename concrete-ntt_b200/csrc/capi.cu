@@ -1273,11 +1273,15 @@ struct cntt_product_plan {
     ProductConsts c;
     cntt_prime32_plan* p32[kProductMaxPrimes];
     cntt_prime64_plan* p64[kProductMaxPrimes];
+    uint2* d_pf_last[2][2]; // [fwd, inv][prime]: last-pass tables of the fused kernels where they differ from the prime plans' (product_fused.hpp)
     Staging stg;
 };
 
 static void product_free(cntt_product_plan* pl)
 {
+    for (int d = 0; d < 2; d++)
+        for (int j = 0; j < 2; j++)
+            if (pl->d_pf_last[d][j]) cudaFree(pl->d_pf_last[d][j]);
     for (int k = 0; k < kProductMaxPrimes; k++) {
         if (pl->p32[k]) cntt_prime32_plan_free(pl->p32[k]);
         if (pl->p64[k]) cntt_prime64_plan_free(pl->p64[k]);
@@ -1285,6 +1289,8 @@ static void product_free(cntt_product_plan* pl)
     pl->stg.release();
     delete pl;
 }
+
+static bool product_fused_args(const cntt_product_plan* pl, ProductFusedArgs* a);
 
 // try_new (product.rs:152-251): None (a status != OK) for odd n, zero or duplicate factors, a product of the
 // factors (1s skipped, checked multiplication) different from `modulus`, or any factor rejected by its prime plan.
@@ -1317,6 +1323,7 @@ CNTT_API int cntt_product_plan_new(size_t n, uint64_t modulus, const uint64_t* f
     cntt_product_plan* pl = new cntt_product_plan();
     pl->n = n; pl->modulus = modulus; pl->device = device;
     for (int k = 0; k < kProductMaxPrimes; k++) { pl->p32[k] = nullptr; pl->p64[k] = nullptr; }
+    for (int d = 0; d < 2; d++) pl->d_pf_last[d][0] = pl->d_pf_last[d][1] = nullptr;
     ProductConsts& c = pl->c;
     std::memset(&c, 0, sizeof(c));
     c.modulus = modulus; c.n = n;
@@ -1341,6 +1348,17 @@ CNTT_API int cntt_product_plan_new(size_t n, uint64_t modulus, const uint64_t* f
     if (c.count32 == 2 && c.p[1] < (1ull << 31)) {
         c.inv10_32[0] = (uint32_t)c.inv[1][0];
         c.inv10_32[1] = (uint32_t)((c.inv[1][0] << 32) / c.p[1]);
+    }
+    if (ProductFusedArgs fa; product_fused_args(pl, &fa) && product_fused_own_tables(fa.logn)) {
+        DeviceGuard guard(device);
+        cudaError_t e = guard.ok ? cudaSuccess : cudaGetLastError();
+        for (int d = 0; d < 2 && e == cudaSuccess; d++)
+            for (int j = 0; j < 2 && e == cudaSuccess; j++) {
+                if ((e = cudaMalloc(&pl->d_pf_last[d][j], n * sizeof(uint2))) != cudaSuccess) break;
+                e = product_fused_build_last(fa.cls, fa.logn, d == 0 ? fa.tw_fwd[j] : fa.tw_inv[j], pl->d_pf_last[d][j], nullptr);
+            }
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { product_free(pl); return cuda_fail(e, "product plan tables"); }
     }
     *out = pl;
     return CNTT_OK;
@@ -1435,7 +1453,8 @@ static bool product_fused_args(const cntt_product_plan* pl, ProductFusedArgs* a)
     const cntt_prime32_plan* q[2] = {q0, q1};
     for (int j = 0; j < 2; j++) {
         a->tw_fwd[j] = q[j]->d_fwd; a->tw_inv[j] = q[j]->d_inv;
-        a->last_fwd[j] = q[j]->d_fwd_last; a->last_inv[j] = q[j]->d_inv_last;
+        a->last_fwd[j] = pl->d_pf_last[0][j] ? pl->d_pf_last[0][j] : q[j]->d_fwd_last;
+        a->last_inv[j] = pl->d_pf_last[1][j] ? pl->d_pf_last[1][j] : q[j]->d_inv_last;
         a->mod[j] = q[j]->mod;
         a->head_fwd[j] = &q[j]->head_fwd; a->head_inv[j] = &q[j]->head_inv;
     }

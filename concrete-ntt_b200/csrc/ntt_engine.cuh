@@ -97,6 +97,9 @@ template <class W> __device__ __forceinline__ int pad_idx(int i) { return i + (i
 #ifndef CNTT_NBUF64
 #define CNTT_NBUF64 1
 #endif
+#ifndef CNTT_WARPSYNC
+#define CNTT_WARPSYNC 1
+#endif
 #ifndef CNTT_NBUF32
 #define CNTT_NBUF32 2
 #endif
@@ -122,6 +125,15 @@ struct Engine {
     static constexpr int N = G::N, R = G::R, T = G::T, P = G::P;
     static constexpr int LOGROW = PadCfg<W>::LOGROW;
     static constexpr int PH = 1 << LOGROW;                      // lanes served by one shared-memory phase
+
+    // Exchange barrier of ONE polynomial group.  A group of at most 32 threads is (part of) one warp -- groups are aligned to their
+    // size inside the CTA -- so a warp-level barrier orders its shared-memory traffic, and the other groups of the CTA are not
+    // stalled on it (CNTT_WARPSYNC; profiles/r02_experiments.txt, "warpsync")
+    static __device__ __forceinline__ void gsync()
+    {
+        if constexpr (CNTT_WARPSYNC != 0 && T <= 32) __syncwarp();
+        else __syncthreads();
+    }
 
     // ---- layouts ------------------------------------------------------------------------
     // Pass q >= 1 works on blocks of B = N >> s0(q) words, S = B / R apart inside a thread.  When S is
@@ -295,7 +307,7 @@ struct Engine {
     // fwd: x enters in pass-0 layout (slot k <-> element tid + kT), leaves in pass-(P-1) layout
     //      (slot k <-> element tid*R + k when P >= 2), lazy range of the policy (not canonical).
     // `sm` points at this polynomial group's shared memory (NP * NBUF * SMEM_WORDS words).
-    // All threads of the CTA must call (uses __syncthreads()).
+    // All threads of the group must call (uses gsync()).
     template <int Q, int NP>
     static __device__ __forceinline__ void fwd_from(W (&x)[NP][R], W* sm, const TwSrc& tw, unsigned nu0, int tid, const Mod& m)
     {
@@ -303,9 +315,9 @@ struct Engine {
         if constexpr (Q + 1 < P) {
             W* buf = sm + ((NBUF == 2 && (Q & 1)) ? SMEM_WORDS : 0);
             scatter<Q, NP>(x, buf, tid);
-            __syncthreads();
+            gsync();
             gather<Q + 1, NP>(x, buf, tid);
-            if constexpr (NBUF == 1 && Q + 2 < P) __syncthreads();
+            if constexpr (NBUF == 1 && Q + 2 < P) gsync();
             fwd_from<Q + 1, NP>(x, sm, tw, nu0, tid, m);
         }
     }
@@ -315,9 +327,9 @@ struct Engine {
     {
         static_assert(!kLoopPasses && P >= 2, "compile-time pass chain only");
         scatter<0, NP>(x, sm, tid);
-        __syncthreads();
+        gsync();
         gather<1, NP>(x, sm, tid);
-        if constexpr (NBUF == 1 && 2 < P) __syncthreads();
+        if constexpr (NBUF == 1 && 2 < P) gsync();
         fwd_from<1, NP>(x, sm, tw, nu0, tid, m);
     }
     template <int NP>
@@ -335,9 +347,9 @@ struct Engine {
         if constexpr (Q > 0) {
             W* buf = sm + ((NBUF == 2 && (Q & 1)) ? SMEM_WORDS : 0);
             scatter<Q, NP>(x, buf, tid);
-            __syncthreads();
+            gsync();
             gather<Q - 1, NP>(x, buf, tid);
-            if constexpr (NBUF == 1 && Q >= 2) __syncthreads();
+            if constexpr (NBUF == 1 && Q >= 2) gsync();
             inv_from<Q - 1, NP>(x, sm, tw, nu0, tid, m);
         }
     }
@@ -350,9 +362,9 @@ struct Engine {
         if constexpr (Q > QSTOP) {
             W* buf = sm + ((NBUF == 2 && (Q & 1)) ? SMEM_WORDS : 0);
             scatter<Q, NP>(x, buf, tid);
-            __syncthreads();
+            gsync();
             gather<Q - 1, NP>(x, buf, tid);
-            if constexpr (NBUF == 1) __syncthreads();
+            if constexpr (NBUF == 1) gsync();
             inv_down<Q - 1, QSTOP, NP>(x, sm, tw, nu0, tid, m);
         }
     }
@@ -385,14 +397,14 @@ struct Engine {
                 W* buf = sm + ((NBUF == 2 && (Q & 1)) ? SMEM_WORDS : 0);
                 if constexpr (FWD) {
                     scatter<Q, NP>(x, buf, tid);
-                    __syncthreads();
+                    gsync();
                     gather<Q + 1, NP>(x, buf, tid);
                 } else {
                     scatter<Q + 1, NP>(x, buf, tid);
-                    __syncthreads();
+                    gsync();
                     gather<Q, NP>(x, buf, tid);
                 }
-                if constexpr (NBUF == 1 && P >= 3) __syncthreads();
+                if constexpr (NBUF == 1 && P >= 3) gsync();
             } else {
                 xchg_rt<Q + 1, NP, FWD>(q, x, sm, tid);
             }

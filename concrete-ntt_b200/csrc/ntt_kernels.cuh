@@ -136,8 +136,15 @@ struct PlanDev {
 #ifndef CNTT_LOGR32
 #define CNTT_LOGR32 4
 #endif
+// N = 1024 x 32-bit with 32 words per thread: ONE warp per polynomial and ONE exchange (5 + 5 levels), warp-level barrier only
+#ifndef CNTT_R32_LOGN10
+#define CNTT_R32_LOGN10 1
+#endif
+#ifndef CNTT_R32_LOGN9
+#define CNTT_R32_LOGN9 0
+#endif
 template <class A, int LOGN> struct CtaCfg {
-    static constexpr int LOGR_MAX = sizeof(typename A::W) == 8 ? CNTT_LOGR64 : r32_size<A, LOGN>() ? 5 : CNTT_LOGR32;
+    static constexpr int LOGR_MAX = sizeof(typename A::W) == 8 ? CNTT_LOGR64 : (r32_size<A, LOGN>() || (CNTT_R32_LOGN10 != 0 && LOGN == 10) || (CNTT_R32_LOGN9 != 0 && LOGN == 9)) ? 5 : CNTT_LOGR32;
     static constexpr int LOGR = LOGN < LOGR_MAX ? LOGN : LOGR_MAX;
     typedef Engine<A, LOGN, LOGR> E;
 };

@@ -13,7 +13,11 @@ struct ProductFusedDev {
 
 template <class A, int LOGN>
 struct ProductFusedCfg {
-    typedef typename CtaCfg<A, LOGN>::E E;
+    // the engine of the prime plan's own CTA kernel, except at N = 1024: there prime32 runs 32 words per thread (one warp per
+    // polynomial), which the fused kernels -- 64-bit words on top of the 32 residues -- pay for in registers (B200, batch 65536:
+    // fwd 0.317 -> 0.346 ms, inv 0.328 -> 0.399 ms), so they stay on 16 words per thread with last-pass tables of their own
+    static constexpr int LOGR = LOGN == 10 ? 4 : CtaCfg<A, LOGN>::LOGR;
+    typedef Engine<A, LOGN, LOGR> E;
     static constexpr int T = E::T;
     static constexpr int GP = T >= 128 ? 1 : 128 / T;
     // forward output staged through a swizzled tile for coalesced stores, as in k_ntt_cta_pipe (ntt_kernels.cuh): pays
@@ -212,6 +216,20 @@ cudaError_t product_fused_inv(const ProductConsts& c, const ProductFusedArgs& a,
 {
     if (!product_fused_supported(a.cls, a.logn)) return cudaErrorNotSupported;
     return a.cls == 0 ? launch_class<A32L4, false>(c, a, ntt, standard, mode, 0, batch, st) : launch_class<A32L2, false>(c, a, ntt, standard, mode, 0, batch, st);
+}
+
+bool product_fused_own_tables(int logn) { return logn == 10; }
+template <class A>
+static cudaError_t build_last_class(int logn, const uint2* heap, uint2* out, cudaStream_t st)
+{
+    switch (logn) {
+    case 10: return launch_build_last_e<typename ProductFusedCfg<A, 10>::E>(heap, out, 0, st);
+    default: return cudaErrorNotSupported;
+    }
+}
+cudaError_t product_fused_build_last(int cls, int logn, const uint2* heap, uint2* out, cudaStream_t st)
+{
+    return cls == 0 ? build_last_class<A32L4>(logn, heap, out, st) : build_last_class<A32L2>(logn, heap, out, st);
 }
 
 } // namespace cntt

@@ -26,6 +26,10 @@ struct ProductFusedArgs {
 };
 
 bool product_fused_supported(int cls, int logn);
+// true: the fused kernels of this size use an engine geometry of their own, and last_fwd / last_inv must be tables built by
+// product_fused_build_last (heap: the prime plan's heap-ordered table, out: 2^logn entries), not the prime plans' own
+bool product_fused_own_tables(int logn);
+cudaError_t product_fused_build_last(int cls, int logn, const uint2* heap, uint2* out, cudaStream_t st);
 // cudaErrorNotSupported when no fused variant exists for (cls, logn)
 cudaError_t product_fused_fwd(const ProductConsts& c, const ProductFusedArgs& a, uint64_t* ntt, const uint64_t* standard, int mode,
                               uint64_t bound, size_t batch, cudaStream_t st);
