@@ -14,21 +14,22 @@ dump() { # name mangled-substring
 # thread kernels of N = 8192, a Shoup-64 class, a sub-block flavour; strided leading levels; table builder
 dump ntt64s_n2048_fwd  'k_ntt_ctaINS_4A64SELi11ELi4ELi1ELb1ELb1ELi1'
 dump ntt64s_n2048_inv  'k_ntt_ctaINS_4A64SELi11ELi4ELi1ELb0ELb1ELi1'
-dump ntt32_n1024_fwd   'k_ntt_ctaINS_5A32L4ELi10ELi4ELi2ELb1ELb1ELi1'
-dump ntt32_n1024_inv   'k_ntt_ctaINS_5A32L4ELi10ELi4ELi2ELb0ELb1ELi1'
+dump ntt32_n1024_fwd   'k_ntt_ctaINS_5A32L4ELi10ELi5ELi4ELb1ELb1ELi1'
+dump ntt32_n1024_inv   'k_ntt_ctaINS_5A32L4ELi10ELi5ELi4ELb0ELb1ELi1'
 dump ntt32_n8192_fwd_r32 'k_ntt_ctaINS_5A32L4ELi13ELi5ELi1ELb1ELb1ELi1'
 dump ntt32_n8192_inv_r32 'k_ntt_ctaINS_5A32L4ELi13ELi5ELi1ELb0ELb1ELi1'
 dump ntt64l4_n2048_fwd 'k_ntt_ctaINS_5A64L4ELi11ELi4ELi1ELb1ELb1ELi1'
 dump ntt32_sub4096_fwd 'k_ntt_ctaINS_5A32L4ELi12ELi4ELi1ELb1ELb0ELi1'
 dump strided32_k4_fwd  'k_ntt_stridedINS_5A32L4ELi4ELb1'
 dump strided64s_k4_inv 'k_ntt_stridedINS_4A64SELi4ELb0'
-dump build_last32_n1024 'k_build_lastINS_6EngineINS_5A32L4ELi10ELi4'
+dump build_last32_n1024 'k_build_lastINS_6EngineINS_5A32L4ELi10ELi5'
 # pointwise streams
 dump pointwise32_mul_assign_normalize 'k_pointwiseINS_5A32L4ELi0'
 dump pointwise64s_mul_accumulate 'k_pointwiseINS_4A64SELi2'
 dump pointwise32_strided_mul_accumulate 'k_pointwise_stridedINS_5A32L4ELi2'
 # native plans: fused polymul (configs[2], configs[3]), split fwd, reduce / crt, large-N pipeline (configs[4]), Plan52
-dump polymul_native64_n2048 'k_polymul_fusedILi1ELi11ELi4'
+dump polymul_native64_n2048 'k_polymul_fusedILi1ELi11ELi4ELb0'
+dump polymul_native64_pre_n2048 'k_polymul_fusedILi1ELi11ELi4ELb1'   # rhs already in the NTT domain (register CRT accumulation, four CTAs per SM)
 dump polymul_native128_n4096 'k_polymul_fusedILi2ELi12ELi3'
 dump native64_fwd_fused_n2048 'k_native_fwd_fusedILi1ELi11ELb0'
 dump native64_reduce 'k_native_reduceILi8ELi5ELb0'
@@ -45,6 +46,6 @@ dump product_inv_fused_n2048 'k_product_inv_fusedINS_5A32L2ELi11'
 dump product_reduce 'k_product_reduce'
 dump product_crt 'k_product_crt'
 : > $OUT/pipecount.txt
-for pat in 'k_ntt_ctaINS_4A64SELi11ELi4ELi1' 'k_ntt_ctaINS_5A32L4ELi10ELi4ELi2' 'k_ntt_ctaINS_5A32L4ELi13ELi5ELi1ELb' 'k_polymul_fusedILi1ELi11ELi4' 'k_polymul_fusedILi2ELi12ELi3' 'k_native_fwd_fusedILi1ELi11ELb0' 'k_product_fwd_fusedINS_5A32L2ELi11' 'k_product_inv_fusedINS_5A32L2ELi11'; do
+for pat in 'k_ntt_ctaINS_4A64SELi11ELi4ELi1' 'k_ntt_ctaINS_5A32L4ELi10ELi5ELi4' 'k_ntt_ctaINS_5A32L4ELi13ELi5ELi1ELb' 'k_polymul_fusedILi1ELi11ELi4' 'k_polymul_fusedILi2ELi12ELi3' 'k_native_fwd_fusedILi1ELi11ELb0' 'k_product_fwd_fusedINS_5A32L2ELi11' 'k_product_inv_fusedINS_5A32L2ELi11'; do
   python tools/sass/pipecount.py $LIB "$pat" >> $OUT/pipecount.txt
 done
