@@ -230,8 +230,9 @@ static cudaError_t build_last32(cntt_prime32_plan* pl)
     const bool uses = pl->cls == C32_L4 ? uses_last_A32L4(pl->logn) : pl->cls == C32_L2 ? uses_last_A32L2(pl->logn) : uses_last_A32G(pl->logn);
     if (!uses) return cudaSuccess;
     cudaError_t e;
-    if ((e = cudaMalloc(&pl->d_fwd_last, pl->n * sizeof(uint2))) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&pl->d_inv_last, pl->n * sizeof(uint2))) != cudaSuccess) return e;
+    const size_t entries = last_table_entries<A32L4>(pl->logn); // the same for every 32-bit class: two layouts at N = 1024 (ntt_kernels.cuh)
+    if ((e = cudaMalloc(&pl->d_fwd_last, entries * sizeof(uint2))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&pl->d_inv_last, entries * sizeof(uint2))) != cudaSuccess) return e;
     for (int dir = 0; dir < 2; dir++) {
         const uint2* heap = dir ? pl->d_inv : pl->d_fwd;
         uint2* o = dir ? pl->d_inv_last : pl->d_fwd_last;

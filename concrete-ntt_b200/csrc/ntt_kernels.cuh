@@ -606,6 +606,20 @@ cudaError_t launch_build_last_e(const typename E::Tw* heap, typename E::Tw* out,
         return cudaGetLastError();
     }
 }
+// Sizes whose whole-transform kernel has two geometries (CtaCfg WHOLE / !WHOLE): the FORWARD transform of N = 1024 x 32-bit runs 32 words per
+// thread (one warp per polynomial, one exchange) from CNTT_R32_LOGN10_MINBATCH polynomials on, and the 16-word kernel (64 threads per
+// polynomial) below that and for the inverse.  B200, M NTT/s fwd / inv (profiles/r02_experiments.txt, "warpsync"):
+//   batch     16 words      32 words            a single transform under a CUDA graph: 2.5 us against 3.5 us
+//   9472      410 / 424     396 / 391
+//   18944     475 / 512     488 / 490
+//   65536     515 / 572     562 / 571
+// Such plans carry both last-pass layouts, the second behind the first.
+#ifndef CNTT_R32_LOGN10_MINBATCH
+#define CNTT_R32_LOGN10_MINBATCH 16384
+#endif
+template <class A, int LOGN> constexpr bool cta_has_alt() { return CtaCfg<A, LOGN, true>::LOGR != CtaCfg<A, LOGN, false>::LOGR; }
+// entries of one last-pass table (per direction) of a plan of 2^logn words
+template <class A> constexpr size_t last_table_entries(int logn) { return ((size_t)1 << logn) * ((logn == 10 && cta_has_alt<A, 10>()) ? 2 : 1); }
 // does the CTA kernel of a transform of 2^logn words (class A) read a last-pass table?
 template <class A, int LOGN> constexpr bool cta_uses_last() { return CtaCfg<A, LOGN>::E::kLastXp; }
 template <class A>
@@ -649,8 +663,12 @@ cudaError_t launch_build_last(int logn, bool fwd, const typename A::Tw* heap, ty
     case 7: return launch_build_last_e<typename CtaCfg<A, 7>::E>(heap, out, log_sub, st);
     case 8: return launch_build_last_e<typename CtaCfg<A, 8>::E>(heap, out, log_sub, st);
     case 9: return launch_build_last_e<typename CtaCfg<A, 9>::E>(heap, out, log_sub, st);
-    case 10: return log_sub == 0 ? launch_build_last_e<typename CtaCfg<A, 10, true>::E>(heap, out, log_sub, st)
-                                 : launch_build_last_e<typename CtaCfg<A, 10, false>::E>(heap, out, log_sub, st);
+    case 10:
+        if (log_sub != 0) return launch_build_last_e<typename CtaCfg<A, 10, false>::E>(heap, out, log_sub, st);
+        if constexpr (cta_has_alt<A, 10>()) { // second layout behind the first (last_table_entries): the small-batch kernel's
+            if (cudaError_t e = launch_build_last_e<typename CtaCfg<A, 10, false>::E>(heap, out + ((size_t)1 << 10), 0, st); e != cudaSuccess) return e;
+        }
+        return launch_build_last_e<typename CtaCfg<A, 10, true>::E>(heap, out, log_sub, st);
     case 11: return launch_build_last_e<typename CtaCfg<A, 11>::E>(heap, out, log_sub, st);
     case 12: return launch_build_last_e<typename CtaCfg<A, 12>::E>(heap, out, log_sub, st);
     default: return cudaErrorInvalidValue;
@@ -876,6 +894,7 @@ cudaError_t launch_cta_np(const PlanDev<A>& pl, typename A::W* data, unsigned lo
     if (nblk > 0x7fffffffull) return cudaErrorInvalidValue;
     const typename A::Tw* last = FWD ? pl.tw_fwd_last : pl.tw_inv_last;
     if (E::kLastXp && last == nullptr) return cudaErrorInvalidValue; // plan built without its last-pass table
+    if constexpr (!WHOLE) { if (log_sub == 0 && last != nullptr) last += (size_t)1 << LOGN; } // whole transform on the block geometry: second layout
     const TwHead<typename A::Tw>* head = FWD ? pl.head_fwd : pl.head_inv;
     auto launch = [&](auto kern, const TwHead<typename A::Tw>& h) -> cudaError_t {
         cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem);
@@ -953,8 +972,8 @@ cudaError_t launch_cta_one(const PlanDev<A>& pl, typename A::W* data, unsigned l
         const TwHead<typename A::Tw>* head = FWD ? pl.head_fwd : pl.head_inv;
         if (log_sub == 0 && head != nullptr && nvpoly >= 2ull * NPW * 148ull) return launch_cta_np<A, LOGN, FWD, NPW>(pl, data, nvpoly, log_sub, poly_stride, st);
     }
-    if constexpr (CtaCfg<A, LOGN, true>::LOGR != CtaCfg<A, LOGN, false>::LOGR) {
-        if (log_sub > 0) return launch_cta_np<A, LOGN, FWD, 1, false>(pl, data, nvpoly, log_sub, poly_stride, st);
+    if constexpr (cta_has_alt<A, LOGN>()) {
+        if (log_sub > 0 || !FWD || nvpoly < (unsigned long long)CNTT_R32_LOGN10_MINBATCH) return launch_cta_np<A, LOGN, FWD, 1, false>(pl, data, nvpoly, log_sub, poly_stride, st);
     }
     return launch_cta_np<A, LOGN, FWD, 1>(pl, data, nvpoly, log_sub, poly_stride, st);
 }
