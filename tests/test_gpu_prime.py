@@ -234,6 +234,26 @@ def test_prime32_persistent_forward_kernel(cntt, oracle, torch_cuda, n, batch):
     assert (host(d, np.uint32) == a).all()
 
 
+@pytest.mark.parametrize("batch", [16383, 16384, 16387])
+def test_prime32_n1024_both_geometries(cntt, oracle, torch_cuda, batch):
+    """N = 1024 x 32-bit has two kernels: 64 threads per polynomial below 16384 polynomials (and for the inverse), one warp per
+    polynomial with 32 words per thread from there on (forward).  Either side of the switch, every arithmetic class, ragged groups:
+    the whole batch against the oracle."""
+    torch = torch_cuda
+    g = rng(batch)
+    for name, p in primes32(oracle).items():
+        gp, op = cntt.prime32.Plan.try_new(1024, p), oracle.Plan32.try_new(1024, p)
+        a = rand_mod(g, p, (batch, 1024), np.uint32)
+        ref = a.copy()
+        op.fwd_batch(ref, 8)
+        d = dev(torch, a)
+        gp.fwd(d)
+        assert (host(d, np.uint32) == ref).all(), (name, batch, "fwd")
+        op.inv_batch(ref, 8)
+        gp.inv(d)
+        assert (host(d, np.uint32) == ref).all(), (name, batch, "inv")
+
+
 def test_concurrent_streams_share_a_plan(cntt, oracle, torch_cuda):
     """Plans are immutable after creation (the reference's are Send + Sync): four host threads, each on its own CUDA
     stream and buffer, drive the same prime32 / prime64 / native64 plans concurrently."""
