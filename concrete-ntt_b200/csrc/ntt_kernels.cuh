@@ -140,13 +140,13 @@ struct PlanDev {
 #ifndef CNTT_R32_LOGN10
 #define CNTT_R32_LOGN10 1
 #endif
-#ifndef CNTT_R32_LOGN9
-#define CNTT_R32_LOGN9 0
+#ifndef CNTT_R32_WHOLE_MASK
+#define CNTT_R32_WHOLE_MASK 0 // A/B runs: bit LOGN = whole transforms of 2^LOGN x 32-bit words at 32 words per thread (N = 512: rejected, r02 "warpsync")
 #endif
 // WHOLE: the kernel transforms whole polynomials (log_sub == 0).  It only matters at N = 1024 x 32-bit: as the 1024-word block of a
 // larger transform (N = 32768 forward) the 32-word flavour loses (0.844 -> 0.887 ms per 8192 polynomials), so blocks keep 16 words
 template <class A, int LOGN, bool WHOLE = true> struct CtaCfg {
-    static constexpr int LOGR_MAX = sizeof(typename A::W) == 8 ? CNTT_LOGR64 : (r32_size<A, LOGN>() || (WHOLE && CNTT_R32_LOGN10 != 0 && LOGN == 10) || (WHOLE && CNTT_R32_LOGN9 != 0 && LOGN == 9)) ? 5 : CNTT_LOGR32;
+    static constexpr int LOGR_MAX = sizeof(typename A::W) == 8 ? CNTT_LOGR64 : (r32_size<A, LOGN>() || (WHOLE && CNTT_R32_LOGN10 != 0 && LOGN == 10) || (WHOLE && ((CNTT_R32_WHOLE_MASK >> LOGN) & 1) != 0)) ? 5 : CNTT_LOGR32;
     static constexpr int LOGR = LOGN < LOGR_MAX ? LOGN : LOGR_MAX;
     typedef Engine<A, LOGN, LOGR> E;
 };
@@ -619,7 +619,11 @@ cudaError_t launch_build_last_e(const typename E::Tw* heap, typename E::Tw* out,
 #endif
 template <class A, int LOGN> constexpr bool cta_has_alt() { return CtaCfg<A, LOGN, true>::LOGR != CtaCfg<A, LOGN, false>::LOGR; }
 // entries of one last-pass table (per direction) of a plan of 2^logn words
-template <class A> constexpr size_t last_table_entries(int logn) { return ((size_t)1 << logn) * ((logn == 10 && cta_has_alt<A, 10>()) ? 2 : 1); }
+template <class A> constexpr bool cta_has_alt_rt(int logn)
+{
+    return logn == 9 ? cta_has_alt<A, 9>() : logn == 10 ? cta_has_alt<A, 10>() : logn == 11 ? cta_has_alt<A, 11>() : logn == 12 ? cta_has_alt<A, 12>() : false;
+}
+template <class A> constexpr size_t last_table_entries(int logn) { return ((size_t)1 << logn) * (cta_has_alt_rt<A>(logn) ? 2 : 1); }
 // does the CTA kernel of a transform of 2^logn words (class A) read a last-pass table?
 template <class A, int LOGN> constexpr bool cta_uses_last() { return CtaCfg<A, LOGN>::E::kLastXp; }
 template <class A>
@@ -645,7 +649,18 @@ bool cta_uses_last_rt(int l)
 }
 template <class A>
 bool plan_uses_last(int logn) { return cta_uses_last_rt<A>(cta_block_logn<A>(logn, true)) || cta_uses_last_rt<A>(cta_block_logn<A>(logn, false)); }
-// heap (2^logn entries) -> last-pass table (2^logn entries) for the CTA kernel this plan size launches
+// one size with (possibly) two geometries: blocks of a larger transform take the block layout; whole transforms the whole-transform
+// layout and, where the two differ, the block layout behind it (last_table_entries)
+template <class A, int L>
+cudaError_t launch_build_last_size(const typename A::Tw* heap, typename A::Tw* out, int log_sub, cudaStream_t st)
+{
+    if (log_sub != 0) return launch_build_last_e<typename CtaCfg<A, L, false>::E>(heap, out, log_sub, st);
+    if constexpr (cta_has_alt<A, L>()) {
+        if (cudaError_t e = launch_build_last_e<typename CtaCfg<A, L, false>::E>(heap, out + ((size_t)1 << L), 0, st); e != cudaSuccess) return e;
+    }
+    return launch_build_last_e<typename CtaCfg<A, L, true>::E>(heap, out, 0, st);
+}
+// heap (2^logn entries) -> last-pass table (last_table_entries) for the CTA kernel this plan size launches
 template <class A>
 cudaError_t launch_build_last(int logn, bool fwd, const typename A::Tw* heap, typename A::Tw* out, cudaStream_t st)
 {
@@ -662,15 +677,10 @@ cudaError_t launch_build_last(int logn, bool fwd, const typename A::Tw* heap, ty
     case 6: return launch_build_last_e<typename CtaCfg<A, 6>::E>(heap, out, log_sub, st);
     case 7: return launch_build_last_e<typename CtaCfg<A, 7>::E>(heap, out, log_sub, st);
     case 8: return launch_build_last_e<typename CtaCfg<A, 8>::E>(heap, out, log_sub, st);
-    case 9: return launch_build_last_e<typename CtaCfg<A, 9>::E>(heap, out, log_sub, st);
-    case 10:
-        if (log_sub != 0) return launch_build_last_e<typename CtaCfg<A, 10, false>::E>(heap, out, log_sub, st);
-        if constexpr (cta_has_alt<A, 10>()) { // second layout behind the first (last_table_entries): the small-batch kernel's
-            if (cudaError_t e = launch_build_last_e<typename CtaCfg<A, 10, false>::E>(heap, out + ((size_t)1 << 10), 0, st); e != cudaSuccess) return e;
-        }
-        return launch_build_last_e<typename CtaCfg<A, 10, true>::E>(heap, out, log_sub, st);
-    case 11: return launch_build_last_e<typename CtaCfg<A, 11>::E>(heap, out, log_sub, st);
-    case 12: return launch_build_last_e<typename CtaCfg<A, 12>::E>(heap, out, log_sub, st);
+    case 9: return launch_build_last_size<A, 9>(heap, out, log_sub, st);
+    case 10: return launch_build_last_size<A, 10>(heap, out, log_sub, st);
+    case 11: return launch_build_last_size<A, 11>(heap, out, log_sub, st);
+    case 12: return launch_build_last_size<A, 12>(heap, out, log_sub, st);
     default: return cudaErrorInvalidValue;
     }
 }
