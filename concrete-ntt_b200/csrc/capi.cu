@@ -50,7 +50,7 @@ CNTT_API const char* cntt_status_string(int s)
     }
 }
 CNTT_API const char* cntt_last_cuda_error(void) { return t_cuda_err.c_str(); }
-CNTT_API const char* cntt_version(void) { return "cntt_b200 0.1 (sm_100a; concrete-ntt 0.2.0 semantics)"; }
+CNTT_API const char* cntt_version(void) { return "cntt_b200 0.2 (sm_100a; concrete-ntt 0.2.0 semantics)"; }
 
 // device batches are accessed with 128-bit (and, when they allow it, 256-bit) loads and stores
 static inline bool misaligned16(const void* a, const void* b = nullptr, const void* c = nullptr)

@@ -50,7 +50,7 @@ typedef enum cntt_status {
 const char* cntt_status_string(int status);
 /* text of the last CUDA error seen by the calling thread ("" if none) */
 const char* cntt_last_cuda_error(void);
-/* library / build identification, e.g. "cntt_b200 0.1 sm_100a" */
+/* library / build identification, e.g. "cntt_b200 0.2 (sm_100a; concrete-ntt 0.2.0 semantics)" */
 const char* cntt_version(void);
 
 /* ---- plan-time helpers (host only) ------------------------------------------------------------- */

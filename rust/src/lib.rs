@@ -63,7 +63,7 @@ pub mod prime {
     }
 }
 
-/// Version string of the loaded library, e.g. `cntt_b200 0.1 (sm_100a; concrete-ntt 0.2.0 semantics)`.
+/// Version string of the loaded library, e.g. `cntt_b200 0.2 (sm_100a; concrete-ntt 0.2.0 semantics)`.
 pub fn backend_version() -> String {
     unsafe { core::ffi::CStr::from_ptr(ffi::cntt_version()) }.to_string_lossy().into_owned()
 }
