@@ -99,6 +99,47 @@ __device__ __forceinline__ void fwd_bf_w(u64& z0, u64& z1, u64 t, u32 eps)
     const u64 a = add_lazy_w(z0, x, eps), b = A64S::sub_lazy(z0, x);
     z0 = a; z1 = b;
 }
+// Karatsuba: three 32 x 32 products instead of four.  The 33-bit sums and the 66-bit middle term are
+// left to the compiler (unsigned __int128); the 128 -> 64-bit reduction is A64S::mul's.
+__device__ __forceinline__ u64 mul_kara(u64 a, u64 b)
+{
+    typedef unsigned __int128 u128;
+    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    const u64 z0 = (u64)a0 * b0, z2 = (u64)a1 * b1;
+    const u64 sa = (u64)a0 + a1, sb = (u64)b0 + b1;
+    const u32 sal = (u32)sa, sbl = (u32)sb;
+    const bool ca = (sa >> 32) != 0, cb = (sb >> 32) != 0;
+    u128 z1 = (u128)((u64)sal * sbl) + ((u128)(ca ? sbl : 0u) << 32) + ((u128)(cb ? sal : 0u) << 32) + ((u128)((ca && cb) ? 1u : 0u) << 64);
+    z1 -= z0; z1 -= z2;
+    const u128 w = (u128)z0 + (z1 << 32) + ((u128)z2 << 64);
+    const u32 c0 = (u32)w, c1 = (u32)(w >> 32), c2 = (u32)(w >> 64), c3 = (u32)(w >> 96);
+    u32 r0, r1;
+    asm("{\n\t"
+        ".reg .u32 m;\n\t"
+        ".reg .pred q;\n\t"
+        "sub.cc.u32      %0, %2, %5;\n\t"
+        "subc.cc.u32     %1, %3, 0;\n\t"
+        "subc.u32        m, 0, 0;\n\t"
+        "sub.cc.u32      %0, %0, m;\n\t"
+        "subc.u32        %1, %1, 0;\n\t"
+        "mad.lo.cc.u32   %0, %4, 0xFFFFFFFF, %0;\n\t"
+        "madc.hi.cc.u32  %1, %4, 0xFFFFFFFF, %1;\n\t"
+        "addc.u32        m, 0, 0;\n\t"
+        "setp.eq.u32     q, %1, 0xFFFFFFFF;\n\t"
+        "setp.ne.and.u32 q, %0, 0, q;\n\t"
+        "setp.ne.or.u32  q, m, 0, q;\n\t"
+        "@q add.cc.u32   %0, %0, 0xFFFFFFFF;\n\t"
+        "@q addc.u32     %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(r0), "=&r"(r1) : "r"(c0), "r"(c1), "r"(c2), "r"(c3));
+    return (u64)r0 | ((u64)r1 << 32);
+}
+__device__ __forceinline__ void fwd_bf_kara(u64& z0, u64& z1, u64 t)
+{
+    const u64 x = mul_kara(z1, t);
+    const u64 a = A64S::add_lazy(z0, x), b = A64S::sub_lazy(z0, x);
+    z0 = a; z1 = b;
+}
 // exponents of the first four transform levels (heap order, entry h = 2^level + block): tw[h] = 2^E[h]
 __device__ constexpr int kExp[16] = {0, 48, 120, 168, 156, 12, 84, 132, 78, 126, 6, 54, 42, 90, 162, 18};
 
@@ -106,7 +147,18 @@ template <int J, int G, int U> struct BfIdx { static constexpr int half = 16 >> 
 
 template <int V> __device__ __forceinline__ void pass(u64 (&x)[16], const u64* tw, const Mod64& m, u32 eps)
 {
-    if constexpr (V == 4) {
+    if constexpr (V == 6) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int half = 16 >> (j + 1);
+#pragma unroll
+            for (int g = 0; g < (1 << j); g++) {
+                const u64 t = tw[(1 << j) + g];
+#pragma unroll
+                for (int u = 0; u < half; u++) fwd_bf_kara(x[2 * half * g + u], x[2 * half * g + u + half], t);
+            }
+        }
+    } else if constexpr (V == 4) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int half = 16 >> (j + 1);
@@ -193,7 +245,7 @@ template <int V> static int run(const char* name, int sms, double ghz, const TwA
     for (size_t t = 0; t < nthreads && t < 4096; t++) {
         u64 x[16];
         for (int k = 0; k < 16; k++) x[k] = h_in[t * 16 + k];
-        ref_pass(x, tw.e, V == 0 || V == 1 || V == 4 || V == 5);
+        ref_pass(x, tw.e, V == 0 || V == 1 || V == 4 || V == 5 || V == 6);
         for (int k = 0; k < 16; k++) if (x[k] % P != h_out[t * 16 + k]) bad++;
     }
     free(h_out);
@@ -232,6 +284,7 @@ int main()
     bad += run<1>("fwd: shift butterflies (levels 0..3)", sms, ghz, tw, d_in, d_out, h_in, nthreads);
     bad += run<4>("fwd: fwd_bf, add fix as IMAD.WIDE", sms, ghz, tw, d_in, d_out, h_in, nthreads);
     bad += run<5>("fwd: shift butterflies, add fix as IMAD.WIDE", sms, ghz, tw, d_in, d_out, h_in, nthreads);
+    bad += run<6>("fwd: fwd_bf with a Karatsuba (3-product) multiply", sms, ghz, tw, d_in, d_out, h_in, nthreads);
     bad += run<2>("inv: A64S::inv_bf, table twiddles (shipped)", sms, ghz, twi, d_in, d_out, h_in, nthreads);
     bad += run<3>("inv: shift butterflies (levels 3..0)", sms, ghz, twi, d_in, d_out, h_in, nthreads);
     return bad ? 1 : 0;
