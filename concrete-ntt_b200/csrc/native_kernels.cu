@@ -213,9 +213,10 @@ static cudaError_t fused_build_last_kind(int logn, const uint2* heap, uint2* out
 }
 cudaError_t native_fused_build_last(int kind, int logn, const uint2* heap, uint2* out, cudaStream_t st)
 {
-    // the layout depends on the kind only through native_fused_logr: one 64-bit and one 128-bit representative
+    // the layout depends on the kind only through native_fused_logr: one representative per class of that function
     const bool wide = kind == NK_NATIVE128 || kind == NK_BINARY128;
-    return wide ? fused_build_last_kind<NK_NATIVE128>(logn, heap, out, st) : fused_build_last_kind<NK_NATIVE64>(logn, heap, out, st);
+    if (wide) return fused_build_last_kind<NK_NATIVE128>(logn, heap, out, st);
+    return kind >= NK_BINARY32 ? fused_build_last_kind<NK_BINARY64>(logn, heap, out, st) : fused_build_last_kind<NK_NATIVE64>(logn, heap, out, st);
 }
 cudaError_t native_polymul_fused_pre(const NativePlanDev& pl, void* prod, const void* lhs, const uint32_t* rhs_planes, size_t batch,
                                      size_t plane_stride, size_t poly_stride, cudaStream_t st)
